@@ -1,0 +1,367 @@
+// HBM-bound companions of the tensor-core kernels: GroupNorm statistics / apply (+SiLU, +resample),
+// row softmax, timestep embedding, small dense layers, input preparation.  All NHWC, 128-bit accesses.
+#include "ops.h"
+#include <cuda_fp16.h>
+#include <math.h>
+
+namespace dsb {
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+
+__device__ __forceinline__ void split_h16(float v, __half& hi, __half& lo) {
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(v - __half2float(hi));
+}
+
+// ------------------------------------------------------------------------------------------ GN stats
+// grid (chunks, B); block (ncol4 <= 384, rows).  Thread (tx, ty) owns float4 column tx.
+__global__ void gn_stats_kernel(ds_gn_stats_desc d, int pix_per_cta) {
+    __shared__ double s_sum[64];
+    __shared__ double s_sq[64];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if (tid < 64) { s_sum[tid] = 0.0; s_sq[tid] = 0.0; }
+    __syncthreads();
+    const int C = d.C0 + d.C1;
+    const int cpg = C / d.groups;
+    const int n = blockIdx.y;
+    const int ncol4 = C / 4;
+    const int p_begin = blockIdx.x * pix_per_cta;
+    int p_end = p_begin + pix_per_cta;
+    if (p_end > d.HW) p_end = d.HW;
+    for (int col = threadIdx.x; col < ncol4; col += blockDim.x) {
+        const int c = col * 4;
+        const float* base;
+        int pitch, cc;
+        if (c < d.C0) { base = d.src0; pitch = d.C0; cc = c; }
+        else { base = d.src1; pitch = d.C1; cc = c - d.C0; }
+        const int gA = c / cpg;
+        const int gB = (c + 3) / cpg;
+        const int nA = (gA == gB) ? 4 : ((gA + 1) * cpg - c);   // channels of this float4 that belong to group A
+        float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+        for (int p = p_begin + threadIdx.y; p < p_end; p += blockDim.y) {
+            const float4 v = *reinterpret_cast<const float4*>(base + ((long long)n * d.HW + p) * pitch + cc);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < nA) { sA += e[j]; qA += e[j] * e[j]; }
+                else { sB += e[j]; qB += e[j] * e[j]; }
+            }
+        }
+        atomicAdd(&s_sum[gA], (double)sA);
+        atomicAdd(&s_sq[gA], (double)qA);
+        if (gB != gA) {
+            atomicAdd(&s_sum[gB], (double)sB);
+            atomicAdd(&s_sq[gB], (double)qB);
+        }
+    }
+    __syncthreads();
+    if (tid < d.groups) {
+        atomicAdd(&d.sums[((long long)n * d.groups + tid) * 2 + 0], s_sum[tid]);
+        atomicAdd(&d.sums[((long long)n * d.groups + tid) * 2 + 1], s_sq[tid]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ GN apply
+// grid (chunks, B), block 256. smem: mean[C], a[C] (= rstd*gamma*(1+ada_scale)), b[C] (= beta*(1+ada_scale)+ada_shift)
+__global__ void gn_apply_kernel(ds_gn_apply_desc d, int items_per_cta) {
+    extern __shared__ float sm[];
+    const int C = d.C0 + d.C1;
+    float* s_mean = sm;
+    float* s_a = sm + C;
+    float* s_b = sm + 2 * C;
+    const int n = blockIdx.y;
+    const bool norm = d.sums != nullptr;
+    if (norm) {
+        const int cpg = C / d.groups;
+        const double cnt = (double)cpg * d.H * d.W;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const int g = c / cpg;
+            const double s = d.sums[((long long)n * d.groups + g) * 2 + 0];
+            const double q = d.sums[((long long)n * d.groups + g) * 2 + 1];
+            const double mean = s / cnt;
+            double var = q / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+            float a = rstd * d.gamma[c];
+            float b = d.beta[c];
+            if (d.ada) {
+                const float sc = d.ada[(long long)n * d.ada_stride + c] + 1.0f;
+                const float sh = d.ada[(long long)n * d.ada_stride + C + c];
+                a *= sc;
+                b = b * sc + sh;
+            }
+            s_mean[c] = (float)mean;
+            s_a[c] = a;
+            s_b[c] = b;
+        }
+    }
+    __syncthreads();
+
+    const int Ho = d.resample == 1 ? d.H / 2 : (d.resample == 2 ? d.H * 2 : d.H);
+    const int Wo = d.resample == 1 ? d.W / 2 : (d.resample == 2 ? d.W * 2 : d.W);
+    const int nc8 = C / 8;
+    const long long items = (long long)Ho * Wo * nc8;
+    const long long plane = (long long)d.B * Ho * Wo * C;
+    long long i_begin = (long long)blockIdx.x * items_per_cta;
+    long long i_end = i_begin + items_per_cta;
+    if (i_end > items) i_end = items;
+    __half* oact = reinterpret_cast<__half*>(d.out_act);
+    __half* oraw = reinterpret_cast<__half*>(d.out_raw);
+    for (long long it = i_begin + threadIdx.x; it < i_end; it += blockDim.x) {
+        const int c8 = (int)(it % nc8);
+        const int po = (int)(it / nc8);
+        const int ho = po / Wo, wo = po - ho * Wo;
+        const int c = c8 * 8;
+        const float* base;
+        int pitch, cc;
+        if (c < d.C0) { base = d.src0; pitch = d.C0; cc = c; }
+        else { base = d.src1; pitch = d.C1; cc = c - d.C0; }
+        float act[8], raw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { act[j] = 0.f; raw[j] = 0.f; }
+        const int ntap = d.resample == 1 ? 4 : 1;
+        for (int t = 0; t < ntap; ++t) {
+            int hi, wi;
+            if (d.resample == 1) { hi = ho * 2 + (t >> 1); wi = wo * 2 + (t & 1); }
+            else if (d.resample == 2) { hi = ho >> 1; wi = wo >> 1; }
+            else { hi = ho; wi = wo; }
+            const float* src = base + (((long long)n * d.H + hi) * d.W + wi) * pitch + cc;
+            const float4 v0 = *reinterpret_cast<const float4*>(src);
+            const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
+            const float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            const float wgt = d.resample == 1 ? 0.25f : 1.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                raw[j] += wgt * e[j];
+                if (norm) {
+                    float y = (e[j] - s_mean[c + j]) * s_a[c + j] + s_b[c + j];
+                    if (d.silu) y = silu_f(y);
+                    act[j] += wgt * y;
+                }
+            }
+        }
+        const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + c;
+        if (oact) {
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_h16(act[j], hi[j], lo[j]);
+            *reinterpret_cast<uint4*>(oact + o) = *reinterpret_cast<const uint4*>(hi);
+            if (d.nplanes > 1) *reinterpret_cast<uint4*>(oact + plane + o) = *reinterpret_cast<const uint4*>(lo);
+        }
+        if (oraw) {
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_h16(raw[j], hi[j], lo[j]);
+            *reinterpret_cast<uint4*>(oraw + o) = *reinterpret_cast<const uint4*>(hi);
+            if (d.nplanes > 1) *reinterpret_cast<uint4*>(oraw + plane + o) = *reinterpret_cast<const uint4*>(lo);
+        }
+        if (d.out_raw_f32) {
+            *reinterpret_cast<float4*>(d.out_raw_f32 + o) = make_float4(raw[0], raw[1], raw[2], raw[3]);
+            *reinterpret_cast<float4*>(d.out_raw_f32 + o + 4) = make_float4(raw[4], raw[5], raw[6], raw[7]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ softmax
+// one warp per row
+__global__ void softmax_kernel(ds_softmax_desc d) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= d.rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* s = d.S + row * d.L;
+    float m = -INFINITY;
+    for (int j = lane * 4; j < d.L; j += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(s + j);
+        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int j = lane * 4; j < d.L; j += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(s + j);
+        sum += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    __half* P = reinterpret_cast<__half*>(d.P);
+    const long long plane = d.rows * d.L;
+    for (int j = lane * 4; j < d.L; j += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(s + j);
+        const float e[4] = {expf(v.x - m) * inv, expf(v.y - m) * inv, expf(v.z - m) * inv, expf(v.w - m) * inv};
+        __align__(8) __half hi[4];
+        __align__(8) __half lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) split_h16(e[k], hi[k], lo[k]);
+        *reinterpret_cast<uint2*>(P + row * d.L + j) = *reinterpret_cast<const uint2*>(hi);
+        if (d.nplanes > 1) *reinterpret_cast<uint2*>(P + plane + row * d.L + j) = *reinterpret_cast<const uint2*>(lo);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ embedding
+__global__ void posemb_kernel(ds_posemb_desc d) {
+    const int n = blockIdx.x;
+    const float sigma = d.sigma[n];
+    const float sd = d.sigma_data;
+    const float s2 = sigma * sigma + sd * sd;
+    const float c_noise = logf(sigma) / 4.0f;
+    if (threadIdx.x == 0) {
+        d.coef[n * 4 + 0] = sd * sd / s2;
+        d.coef[n * 4 + 1] = sigma * sd / sqrtf(s2);
+        d.coef[n * 4 + 2] = 1.0f / sqrtf(s2);
+        d.coef[n * 4 + 3] = c_noise;
+    }
+    const int half = d.num_channels / 2;
+    for (int i = threadIdx.x; i < half; i += blockDim.x) {
+        // freqs = (1/10000) ** (i / (half - endpoint))   (networks_edm.py:193-195)
+        const float fr = (float)i / (float)(half - (d.endpoint ? 1 : 0));
+        const float freq = powf(1.0f / 10000.0f, fr);
+        const float a = c_noise * freq;
+        const float cs = cosf(a), sn = sinf(a);
+        // reference layout is [cos | sin]; SongUNet then swaps the halves to [sin | cos]
+        if (d.swap_sincos) { d.emb[n * d.num_channels + i] = sn; d.emb[n * d.num_channels + half + i] = cs; }
+        else { d.emb[n * d.num_channels + i] = cs; d.emb[n * d.num_channels + half + i] = sn; }
+    }
+}
+
+// one warp per output feature; loops over rows re-using the weight row held in registers
+template <int MAXF>
+__global__ void linear_kernel(ds_linear_desc d) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (o >= d.out_f) return;
+    const int lane = threadIdx.x & 31;
+    float w[MAXF / 32];
+#pragma unroll
+    for (int k = 0; k < MAXF / 32; ++k) {
+        const int i = lane + 32 * k;
+        w[k] = (i < d.in_f) ? d.W[(long long)o * d.in_f + i] : 0.f;
+    }
+    const float bias = d.b ? d.b[o] : 0.f;
+    for (int n = blockIdx.y; n < d.n_rows; n += gridDim.y) {
+        const float* x = d.in + (long long)n * d.in_stride;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXF / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i < d.in_f) acc += w[k] * (d.in_scale * x[i]);
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+        if (lane == 0) {
+            float v = acc + bias;
+            if (d.add) v += d.add[(long long)n * d.add_stride + o];
+            if (d.act == 1) v = silu_f(v);
+            d.out[(long long)n * d.out_f + o] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ input prep
+__global__ void prep_input_kernel(ds_prep_input_desc d) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (n, pixel, 8-ch group)
+    const long long total = (long long)d.B * d.HW * 8;
+    if (idx >= total) return;
+    const int c8 = (int)(idx & 7);
+    const long long px = idx >> 3;
+    const int n = (int)(px / d.HW);
+    const int hw = (int)(px - (long long)n * d.HW);
+    const float cin = d.coef[n * d.coef_stride + 2];
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c8 * 8 + j;
+        float v = 0.f;
+        if (c < d.C) v = cin * d.x[((long long)n * d.C + c) * d.HW + hw];
+        split_h16(v, hi[j], lo[j]);
+    }
+    __half* o = reinterpret_cast<__half*>(d.out);
+    const long long off = px * 64 + c8 * 8;
+    *reinterpret_cast<uint4*>(o + off) = *reinterpret_cast<const uint4*>(hi);
+    if (d.nplanes > 1) *reinterpret_cast<uint4*>(o + (long long)d.B * d.HW * 64 + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
+__global__ void chanmean_kernel(ds_chanmean_desc d) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= d.rows) return;
+    const int lane = threadIdx.x & 31;
+    float s = 0.f;
+    for (int c = lane; c < d.C; c += 32) s += d.src[row * d.C + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) d.out[row] = s / (float)d.C;
+}
+
+static inline int ok() { return cudaGetLastError() == cudaSuccess ? 0 : -1; }
+
+}  // namespace dsb
+
+using namespace dsb;
+
+extern "C" int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream) {
+    const int C = d->C0 + d->C1;
+    if (C % 4 || d->groups > 64 || C % d->groups || (d->C0 % 4)) return -2;
+    const int ncol4 = C / 4;
+    int bx = ncol4 < 256 ? ncol4 : 256;
+    // keep bx a divisor-friendly size; columns loop with stride bx anyway
+    int by = 256 / bx; if (by < 1) by = 1;
+    int pix_per_cta = 64;
+    if (pix_per_cta < by) pix_per_cta = by;
+    const int chunks = (d->HW + pix_per_cta - 1) / pix_per_cta;
+    gn_stats_kernel<<<dim3(chunks, d->B), dim3(bx, by), 0, stream>>>(*d, pix_per_cta);
+    return ok();
+}
+
+extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream) {
+    const int C = d->C0 + d->C1;
+    if (C % 8 || (d->C0 % 8)) return -2;
+    const int Ho = d->resample == 1 ? d->H / 2 : (d->resample == 2 ? d->H * 2 : d->H);
+    const int Wo = d->resample == 1 ? d->W / 2 : (d->resample == 2 ? d->W * 2 : d->W);
+    const long long items = (long long)Ho * Wo * (C / 8);
+    const int items_per_cta = 256 * 8;
+    const int chunks = (int)((items + items_per_cta - 1) / items_per_cta);
+    const size_t smem = (size_t)3 * C * sizeof(float);
+    gn_apply_kernel<<<dim3(chunks, d->B), 256, smem, stream>>>(*d, items_per_cta);
+    return ok();
+}
+
+extern "C" int ds_softmax_launch(const ds_softmax_desc* d, cudaStream_t stream) {
+    if (d->L % 4) return -2;
+    const int wpb = 8;
+    const long long blocks = (d->rows + wpb - 1) / wpb;
+    softmax_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(*d);
+    return ok();
+}
+
+extern "C" int ds_posemb_launch(const ds_posemb_desc* d, cudaStream_t stream) {
+    posemb_kernel<<<d->nsig, 128, 0, stream>>>(*d);
+    return ok();
+}
+
+extern "C" int ds_linear_launch(const ds_linear_desc* d, cudaStream_t stream) {
+    const int wpb = 4;
+    const int bx = (d->out_f + wpb - 1) / wpb;
+    int by = d->n_rows < 16 ? d->n_rows : 16;
+    if (by < 1) by = 1;
+    if (d->in_f <= 256) linear_kernel<256><<<dim3(bx, by), wpb * 32, 0, stream>>>(*d);
+    else if (d->in_f <= 512) linear_kernel<512><<<dim3(bx, by), wpb * 32, 0, stream>>>(*d);
+    else if (d->in_f <= 1024) linear_kernel<1024><<<dim3(bx, by), wpb * 32, 0, stream>>>(*d);
+    else if (d->in_f <= 2048) linear_kernel<2048><<<dim3(bx, by), wpb * 32, 0, stream>>>(*d);
+    else return -2;
+    return ok();
+}
+
+extern "C" int ds_prep_input_launch(const ds_prep_input_desc* d, cudaStream_t stream) {
+    if (d->C > 64) return -2;
+    const long long total = (long long)d->B * d->HW * 8;
+    prep_input_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(*d);
+    return ok();
+}
+
+extern "C" int ds_chanmean_launch(const ds_chanmean_desc* d, cudaStream_t stream) {
+    const int wpb = 8;
+    chanmean_kernel<<<(unsigned)((d->rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(*d);
+    return ok();
+}

@@ -1,0 +1,432 @@
+// tcgen05 implicit-GEMM convolution / GEMM for sm_100a.
+//
+// One persistent, warp-specialised kernel serves every contraction of the denoiser U-Net
+// (reference: diff-solvers-main/models/networks_edm.py:60-82 Conv2d, :105-118 AttentionOp,
+//  :174-178 qkv/proj): 3x3 and 1x1 convolutions over NHWC fp16 activations, the 1x1 skip
+// projection appended along K, and the batched Q.K^T / P.V products of self-attention.
+//
+//   warp 0      TMA producer   (cp.async.bulk.tensor 4-D boxes for A = shifted pixel tiles, 3-D for B)
+//   warp 1      MMA issuer     (tcgen05.mma kind::f16, 128 x BN x 16, fp32 accumulators in TMEM)
+//   warps 2..5  epilogue       (tcgen05.ld -> bias / embedding / residual / scale -> fp32 and/or fp16 hi/lo)
+//
+// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA, and two TMEM accumulator
+// buffers (tmem_full/tmem_empty) between MMA and epilogue so tile i+1 is multiplied while tile i drains.
+#include "ops.h"
+#include "ptx.cuh"
+#include <cuda_fp16.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace dsb {
+
+static constexpr int kMaxStages = 8;
+static constexpr int kATileBytes = 128 * 128;   // 128 rows x 64 fp16
+static constexpr int kThreads = 192;
+
+struct alignas(64) GemmKernelParams {
+    CUtensorMap tmA, tmA2, tmB;
+    int BN, m_tiles, n_tiles, num_z, nh;
+    int taps, cpb, nkb_main, nkb_aux, npass;
+    int a_mode, conv_H, conv_W, a_bn_dummy;
+    int a_plane_n, a2_plane_n, b_plane_batch;
+    int a_c_per_zh, a_n_per_zb, a_n_per_zh;
+    int b_k0, b_k_per_zh, b_row_per_zh, b_z_per_zb, b_z_per_zh;
+    int m_valid, n_valid;
+    int num_stages;
+    float* out_f32;
+    __half* out_h16;
+    long long o_zb, o_zh, ldo, o_plane;
+    const float* bias_n;
+    const float* bias_m;
+    const float* rowvec;
+    long long rowvec_stride;
+    int rows_per_sample;
+    const float* residual;
+    long long ldr;
+    float scale;
+    int edm_out;
+    const float* edm_x;
+    const float* edm_coef;
+    int edm_coef_stride;
+    int edm_C;
+    float* edm_D;
+};
+
+struct SmemCtl {
+    uint64_t full[kMaxStages];
+    uint64_t empty[kMaxStages];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int W>
+__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const float* v, long long grow_in_z, int col0,
+                                               bool row_ok, int z, int zb, int zh) {
+    // v[W]: accumulators of this thread's row, columns col0 .. col0+W-1 (tile-local col0 already globalised)
+    if (!row_ok) return;
+    float r[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) r[j] = v[j];
+    const bool full = (col0 + W <= p.n_valid);
+    if (p.bias_n) {
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if (full || col0 + j < p.n_valid) r[j] += __ldg(p.bias_n + col0 + j);
+    }
+    if (p.bias_m) {
+        const float bm = __ldg(p.bias_m + grow_in_z);
+#pragma unroll
+        for (int j = 0; j < W; ++j) r[j] += bm;
+    }
+    if (p.rowvec) {
+        const long long s = (p.rowvec_stride == 0) ? 0 : (grow_in_z / p.rows_per_sample) * p.rowvec_stride;
+        const float* rv = p.rowvec + s + col0;
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+            if (full || col0 + j < p.n_valid) r[j] += __ldg(rv + j);
+    }
+    if (p.residual) {
+        const float* rs = p.residual + grow_in_z * p.ldr + col0;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < W; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(rs + j);
+                r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (col0 + j < p.n_valid) r[j] += rs[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) r[j] *= p.scale;
+
+    if (p.edm_out) {
+        // D = c_skip * x + c_out * F, written NCHW (reference: networks_edm.py:488-495)
+        const int HW = p.rows_per_sample;
+        const long long n = grow_in_z / HW;
+        const long long hw = grow_in_z % HW;
+        const float cskip = __ldg(p.edm_coef + n * p.edm_coef_stride + 0);
+        const float cout = __ldg(p.edm_coef + n * p.edm_coef_stride + 1);
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const int c = col0 + j;
+            if (c < p.edm_C) {
+                const long long idx = (n * p.edm_C + c) * HW + hw;
+                p.edm_D[idx] = cskip * __ldg(p.edm_x + idx) + cout * r[j];
+            }
+        }
+        return;
+    }
+
+    const long long obase = (long long)zb * p.o_zb + (long long)zh * p.o_zh + grow_in_z * p.ldo + col0;
+    if (p.out_f32) {
+        float* o = p.out_f32 + obase;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < W; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (col0 + j < p.n_valid) o[j] = r[j];
+        }
+    }
+    if (p.out_h16) {
+        __half* oh = p.out_h16 + obase;
+        if (full) {
+            __align__(16) __half hi[W];
+            __align__(16) __half lo[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                hi[j] = __float2half_rn(r[j]);
+                lo[j] = __float2half_rn(r[j] - __half2float(hi[j]));
+            }
+#pragma unroll
+            for (int j = 0; j < W; j += 8) *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(hi + j);
+            if (p.o_plane) {
+#pragma unroll
+                for (int j = 0; j < W; j += 8)
+                    *reinterpret_cast<uint4*>(oh + p.o_plane + j) = *reinterpret_cast<const uint4*>(lo + j);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (col0 + j < p.n_valid) {
+                    const __half h = __float2half_rn(r[j]);
+                    oh[j] = h;
+                    if (p.o_plane) oh[p.o_plane + j] = __float2half_rn(r[j] - __half2float(h));
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle; the runtime only guarantees 16.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_bytes = kATileBytes + p.BN * 128;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.num_stages * stage_bytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nkb_total = p.nkb_main + p.nkb_aux;
+    const int n_iters = p.npass * nkb_total;
+    const int tiles_per_z = p.m_tiles * p.n_tiles;
+    const int total_tiles = p.num_z * tiles_per_z;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        if (p.nkb_aux) tma_prefetch_desc(&p.tmA2);
+        for (int s = 0; s < p.num_stages; ++s) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&ctl->tmem_full[a], 1);
+            mbar_init(&ctl->tmem_empty[a], 4);
+        }
+        fence_barrier_init();
+    } else if (warp == 1) {
+        tmem_alloc(&ctl->tmem_base, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int z = tile / tiles_per_z;
+                const int t2 = tile - z * tiles_per_z;
+                const int mt = t2 / p.n_tiles;
+                const int nt = t2 - mt * p.n_tiles;
+                const int zb = z / p.nh, zh = z - zb * p.nh;
+                int aw0, ah0, an0;
+                if (p.a_mode == 0) {
+                    const int HW = p.conv_H * p.conv_W;
+                    const int p0 = mt * 128;
+                    an0 = p0 / HW;
+                    ah0 = (p0 - an0 * HW) / p.conv_W;
+                    aw0 = 0;
+                } else {
+                    aw0 = mt * 128;
+                    ah0 = 0;
+                    an0 = zb * p.a_n_per_zb + zh * p.a_n_per_zh;
+                }
+                const int a_c_off = zh * p.a_c_per_zh;
+                const int b_k_off = p.b_k0 + zh * p.b_k_per_zh;
+                const int b_row = nt * p.BN + zh * p.b_row_per_zh;
+                const int b_z = zb * p.b_z_per_zb + zh * p.b_z_per_zh;
+                for (int it = 0; it < n_iters; ++it) {
+                    const int pass = it / nkb_total;
+                    const int kb = it - pass * nkb_total;
+                    mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    uint8_t* sb = sa + kATileBytes;
+                    mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
+                    const int pa = (pass == 1) ? 1 : 0;
+                    const int pb = (pass == 2) ? 1 : 0;
+                    if (kb < p.nkb_main) {
+                        const int tap = kb / p.cpb;
+                        const int c0 = (kb - tap * p.cpb) * 64;
+                        int dh = 0, dw = 0;
+                        if (p.taps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                        tma_load_4d(&p.tmA, &ctl->full[stage], sa, c0 + a_c_off, aw0 + dw, ah0 + dh, an0 + pa * p.a_plane_n);
+                    } else {
+                        const int c0 = (kb - p.nkb_main) * 64;
+                        tma_load_4d(&p.tmA2, &ctl->full[stage], sa, c0, aw0, ah0, an0 + pa * p.a2_plane_n);
+                    }
+                    tma_load_3d(&p.tmB, &ctl->full[stage], sb, kb * 64 + b_k_off, b_row, b_z + pb * p.b_plane_batch);
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16((uint32_t)p.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int it = 0; it < n_iters; ++it) {
+                    mbar_wait(&ctl->full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t sb = sa + kATileBytes;
+                    const uint64_t da = umma_desc_sw128(sa);
+                    const uint64_t db = umma_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&ctl->empty[stage]);
+                    if (it == n_iters - 1) umma_commit(&ctl->tmem_full[acc]);
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int z = tile / tiles_per_z;
+            const int t2 = tile - z * tiles_per_z;
+            const int mt = t2 / p.n_tiles;
+            const int nt = t2 - mt * p.n_tiles;
+            const int zb = z / p.nh, zh = z - zb * p.nh;
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            mbar_wait(&ctl->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = quad * 32 + lane;
+            const long long grow = (long long)mt * 128 + row;
+            const bool row_ok = grow < p.m_valid;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
+            int c = 0;
+            for (; c + 32 <= p.BN; c += 32) {
+                uint32_t v[32];
+                DSB_TMEM_LD_32(t_row + c, v);
+                tmem_ld_wait();
+                const int col0 = nt * p.BN + c;
+                if (col0 < p.n_valid)
+                    epilogue_chunk<32>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, z, zb, zh);
+            }
+            if (c < p.BN) {
+                uint32_t v[16];
+                DSB_TMEM_LD_16(t_row + c, v);
+                tmem_ld_wait();
+                const int col0 = nt * p.BN + c;
+                if (col0 < p.n_valid)
+                    epilogue_chunk<16>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, z, zb, zh);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes, const int32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return -1;
+    cuuint64_t gd[5];
+    cuuint64_t gs[4];
+    cuuint32_t bx[5];
+    cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = (cuuint64_t)strides_bytes[i];
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        fprintf(stderr, "[dsb] cuTensorMapEncodeTiled failed: %d (rank %d dims %lld %lld %lld %lld box %d %d %d %d)\n", (int)r, rank,
+                (long long)dims[0], (long long)dims[1], (long long)dims[2], rank > 3 ? (long long)dims[3] : 0LL, box[0], box[1], box[2],
+                rank > 3 ? box[3] : 0);
+        return -2;
+    }
+    return 0;
+}
+
+int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
+    memset(kp, 0, sizeof(*kp));
+    if (d->BN < 16 || d->BN > 256 || (d->BN % 16) != 0) return -10;
+    if (d->a_box[0] != 64 || d->a_box[1] * d->a_box[2] * d->a_box[3] != 128) return -11;
+    if (d->npass != 1 && d->npass != 3) return -12;
+    if (encode_map(&kp->tmA, d->a_ptr, 4, d->a_dims, d->a_strides, d->a_box)) return -1;
+    if (d->a2_c > 0) {
+        int64_t dims2[4] = {d->a2_c, d->a_dims[1], d->a_dims[2], d->a_dims[3]};
+        // aux tensor shares (w,h,n) extents with A; strides follow its own channel count
+        int64_t st2[3] = {d->a2_c * 2, d->a2_c * 2 * d->a_dims[1], d->a2_c * 2 * d->a_dims[1] * d->a_dims[2]};
+        if (encode_map(&kp->tmA2, d->a2_ptr, 4, dims2, st2, d->a_box)) return -2;
+    }
+    int32_t bbox[3] = {64, d->BN, 1};
+    if (encode_map(&kp->tmB, d->b_ptr, 3, d->b_dims, d->b_strides, bbox)) return -3;
+
+    kp->BN = d->BN; kp->m_tiles = d->m_tiles; kp->n_tiles = d->n_tiles; kp->num_z = d->num_z; kp->nh = d->nh > 0 ? d->nh : 1;
+    kp->taps = d->taps; kp->cpb = d->cpb; kp->nkb_main = d->taps * d->cpb; kp->nkb_aux = d->a2_c > 0 ? (int)(d->a2_c / 64) : 0;
+    kp->npass = d->npass; kp->a_mode = d->a_mode; kp->conv_H = d->conv_H; kp->conv_W = d->conv_W;
+    kp->a_plane_n = d->a_plane_n; kp->a2_plane_n = d->a2_plane_n; kp->b_plane_batch = d->b_plane_batch;
+    kp->a_c_per_zh = d->a_c_per_zh; kp->a_n_per_zb = d->a_n_per_zb; kp->a_n_per_zh = d->a_n_per_zh;
+    kp->b_k0 = d->b_k0; kp->b_k_per_zh = d->b_k_per_zh; kp->b_row_per_zh = d->b_row_per_zh;
+    kp->b_z_per_zb = d->b_z_per_zb; kp->b_z_per_zh = d->b_z_per_zh;
+    kp->m_valid = d->m_valid; kp->n_valid = d->n_valid;
+    kp->out_f32 = d->out_f32; kp->out_h16 = reinterpret_cast<__half*>(d->out_h16);
+    kp->o_zb = d->o_zb; kp->o_zh = d->o_zh; kp->ldo = d->ldo; kp->o_plane = d->o_plane;
+    kp->bias_n = d->bias_n; kp->bias_m = d->bias_m; kp->rowvec = d->rowvec; kp->rowvec_stride = d->rowvec_stride;
+    kp->rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+    kp->residual = d->residual; kp->ldr = d->ldr; kp->scale = d->scale;
+    kp->edm_out = d->edm_out; kp->edm_x = d->edm_x; kp->edm_coef = d->edm_coef; kp->edm_coef_stride = d->edm_coef_stride;
+    kp->edm_C = d->edm_C; kp->edm_D = d->edm_D;
+    const int stage_bytes = kATileBytes + d->BN * 128;
+    int ns = (227 * 1024 - 2048) / stage_bytes;
+    if (ns > kMaxStages) ns = kMaxStages;
+    kp->num_stages = ns;
+    return 0;
+}
+
+size_t gemm_params_size() { return sizeof(GemmKernelParams); }
+void gemm_patch_edm(GemmKernelParams* kp, const float* x, float* D) { kp->edm_x = x; kp->edm_D = D; }
+
+static int g_num_sms = 0;
+static bool g_attr_set = false;
+
+int gemm_run(const GemmKernelParams* kp, cudaStream_t stream) {
+    if (!g_attr_set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -20;
+        g_attr_set = true;
+    }
+    const int stage_bytes = kATileBytes + kp->BN * 128;
+    const size_t smem = (size_t)kp->num_stages * stage_bytes + sizeof(SmemCtl) + 1024;
+    const int tiles = kp->num_z * kp->m_tiles * kp->n_tiles;
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    if (grid <= 0) return 0;
+    gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(*kp);
+    return cudaGetLastError() == cudaSuccess ? 0 : -21;
+}
+
+}  // namespace dsb
+
+extern "C" int ds_gemm_launch(const ds_gemm_desc* d, cudaStream_t stream) {
+    dsb::GemmKernelParams kp;
+    int rc = dsb::gemm_build(d, &kp);
+    if (rc) return rc;
+    return dsb::gemm_run(&kp, stream);
+}

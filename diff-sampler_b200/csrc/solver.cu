@@ -1,0 +1,168 @@
+// Solver-side kernels: the fused sigma-scaled update (one HBM pass per step) and the exact
+// per-sample 0.995-quantile used by dynamic thresholding.
+#include "ops.h"
+#include <math.h>
+
+namespace dsb {
+
+__device__ __forceinline__ float4 ld4(const float* p, long long i4) { return __ldcs(reinterpret_cast<const float4*>(p) + i4); }
+__device__ __forceinline__ void st4(float* p, long long i4, float4 v) { __stcs(reinterpret_cast<float4*>(p) + i4, v); }
+
+template <int NH, int MODE>
+__global__ void __launch_bounds__(256) update_kernel(ds_update_desc d, long long n4_total, long long n4_per_sample) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_total; i += stride) {
+        float cx = d.coef[0], c0 = d.coef[1], c1 = d.coef[2], c2 = d.coef[3], c3 = d.coef[4], c4 = d.coef[5];
+        float t = d.t;
+        int b = 0;
+        if (d.coef_dev || d.t_dev || d.thr) b = (int)(i / n4_per_sample);
+        if (d.coef_dev) {
+            cx = d.coef_dev[0 * d.B + b]; c0 = d.coef_dev[1 * d.B + b]; c1 = d.coef_dev[2 * d.B + b];
+            c2 = d.coef_dev[3 * d.B + b]; c3 = d.coef_dev[4 * d.B + b]; c4 = d.coef_dev[5 * d.B + b];
+        }
+        if (d.t_dev) t = d.t_dev[b];
+        const float4 xb = ld4(d.xb, i);
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == DS_M_X0) {
+            m = ld4(d.D, i);
+            if (d.thr) {
+                const float s = d.thr[b];
+                m.x = fminf(fmaxf(m.x, -s), s) / s; m.y = fminf(fmaxf(m.y, -s), s) / s;
+                m.z = fminf(fmaxf(m.z, -s), s) / s; m.w = fminf(fmaxf(m.w, -s), s) / s;
+            }
+        } else if (MODE == DS_M_EPS) {
+            const float4 xs = d.xs ? ld4(d.xs, i) : xb;
+            const float4 D = ld4(d.D, i);
+            m.x = (xs.x - D.x) / t; m.y = (xs.y - D.y) / t; m.z = (xs.z - D.z) / t; m.w = (xs.w - D.w) / t;
+        } else if (MODE == DS_M_DIV) {
+            const float4 xs = d.xs ? ld4(d.xs, i) : xb;
+            m.x = xs.x / t; m.y = xs.y / t; m.z = xs.z / t; m.w = xs.w / t;
+        }
+        float4 o;
+        o.x = cx * xb.x + c0 * m.x; o.y = cx * xb.y + c0 * m.y; o.z = cx * xb.z + c0 * m.z; o.w = cx * xb.w + c0 * m.w;
+        if (NH >= 1) { const float4 h = ld4(d.h[0], i); o.x += c1 * h.x; o.y += c1 * h.y; o.z += c1 * h.z; o.w += c1 * h.w; }
+        if (NH >= 2) { const float4 h = ld4(d.h[1], i); o.x += c2 * h.x; o.y += c2 * h.y; o.z += c2 * h.z; o.w += c2 * h.w; }
+        if (NH >= 3) { const float4 h = ld4(d.h[2], i); o.x += c3 * h.x; o.y += c3 * h.y; o.z += c3 * h.z; o.w += c3 * h.w; }
+        if (NH >= 4) { const float4 h = ld4(d.h[3], i); o.x += c4 * h.x; o.y += c4 * h.y; o.z += c4 * h.z; o.w += c4 * h.w; }
+        if (d.out_x) st4(d.out_x, i, o);
+        if (d.out_m) st4(d.out_m, i, m);
+    }
+}
+
+template <int NH>
+static int launch_update_nh(const ds_update_desc& d, long long n4, long long n4ps, int grid, cudaStream_t s) {
+    switch (d.mode) {
+        case DS_M_X0: update_kernel<NH, DS_M_X0><<<grid, 256, 0, s>>>(d, n4, n4ps); break;
+        case DS_M_EPS: update_kernel<NH, DS_M_EPS><<<grid, 256, 0, s>>>(d, n4, n4ps); break;
+        case DS_M_DIV: update_kernel<NH, DS_M_DIV><<<grid, 256, 0, s>>>(d, n4, n4ps); break;
+        case DS_M_NONE: update_kernel<NH, DS_M_NONE><<<grid, 256, 0, s>>>(d, n4, n4ps); break;
+        default: return -2;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ quantile
+// One CTA per sample.  |x| bit patterns are monotone as uint32, so an MSB-first 8-bit radix select
+// finds the exact k-th order statistic; the (k+1)-th is either equal or the minimum of the larger keys.
+__global__ void __launch_bounds__(256) threshold_kernel(ds_threshold_desc d) {
+    extern __shared__ uint32_t keys[];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_k, s_less;
+    __shared__ uint32_t s_min_above;
+    const int b = blockIdx.x;
+    const int n = d.row_len;
+    const float* x = d.x0 + (long long)b * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = __float_as_uint(fabsf(x[i]));
+    // rank arithmetic in fp32, as torch.quantile does for an fp32 input
+    const float rank = d.q * (float)(n - 1);
+    const float below = floorf(rank);
+    const float w = rank - below;
+    const uint32_t k = (uint32_t)below;
+    if (threadIdx.x == 0) { s_prefix = 0; s_k = k; s_less = 0; s_min_above = 0xFFFFFFFFu; }
+    __syncthreads();
+    uint32_t mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t kk = s_k, acc = 0;
+            int bin = 0;
+            for (; bin < 256; ++bin) {
+                if (acc + hist[bin] > kk) break;
+                acc += hist[bin];
+            }
+            s_k = kk - acc;
+            s_less += acc;
+            s_prefix = prefix | ((uint32_t)bin << shift);
+        }
+        mask |= 0xFFu << shift;
+        __syncthreads();
+    }
+    const uint32_t vk = s_prefix;       // exact k-th smallest key
+    // count of keys == vk and min of keys > vk
+    uint32_t my_eq = 0, my_min = 0xFFFFFFFFu;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t key = keys[i];
+        if (key == vk) ++my_eq;
+        else if (key > vk && key < my_min) my_min = key;
+    }
+    __syncthreads();
+    hist[threadIdx.x] = my_eq;
+    atomicMin(&s_min_above, my_min);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t eq = 0;
+        for (int i = 0; i < 256; ++i) eq += hist[i];
+        const float lo = __uint_as_float(vk);
+        float hi = lo;
+        if ((uint32_t)(k + 1) < (uint32_t)n && !(s_less + eq > k + 1)) hi = __uint_as_float(s_min_above);
+        // torch lerp: a + w*(b-a) for w < 0.5, else b - (b-a)*(1-w)
+        const float diff = hi - lo;
+        const float qv = (w < 0.5f) ? (lo + w * diff) : (hi - diff * (1.0f - w));
+        d.thr[b] = fmaxf(qv, d.floor_val);
+    }
+}
+
+}  // namespace dsb
+
+using namespace dsb;
+
+extern "C" int ds_update_launch(const ds_update_desc* dp, cudaStream_t stream) {
+    const ds_update_desc& d = *dp;
+    if (d.n_per_sample % 4) return -2;
+    const long long n4ps = d.n_per_sample / 4;
+    const long long n4 = n4ps * d.B;
+    if (n4 == 0) return 0;
+    long long blocks = (n4 + 255) / 256;
+    const long long cap = 148LL * 16;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    int rc;
+    switch (d.nhist) {
+        case 0: rc = launch_update_nh<0>(d, n4, n4ps, grid, stream); break;
+        case 1: rc = launch_update_nh<1>(d, n4, n4ps, grid, stream); break;
+        case 2: rc = launch_update_nh<2>(d, n4, n4ps, grid, stream); break;
+        case 3: rc = launch_update_nh<3>(d, n4, n4ps, grid, stream); break;
+        case 4: rc = launch_update_nh<4>(d, n4, n4ps, grid, stream); break;
+        default: return -2;
+    }
+    if (rc) return rc;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+extern "C" int ds_threshold_launch(const ds_threshold_desc* d, cudaStream_t stream) {
+    const size_t smem = (size_t)d->row_len * sizeof(uint32_t);
+    if (smem > 200 * 1024) return -2;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr = true;
+    }
+    threshold_kernel<<<d->B, 256, smem, stream>>>(*d);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}

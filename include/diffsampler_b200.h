@@ -1,0 +1,84 @@
+/*
+ * diffsampler_b200 — C ABI of the B200-native diffusion ODE sampling hot path.
+ *
+ * The reference (zju-pi/diff-sampler) is pure Python/PyTorch: its hot path has no FFI today.  The
+ * boundary it exposes is the Python call surface
+ *     solvers.<name>_sampler(net, latents, ...)          diff-solvers-main/solvers.py:18-821
+ *     solver_utils.get_schedule(...)                      diff-solvers-main/solver_utils.py:6-52
+ *     get_denoised(net, x, t, ...) -> net(x, sigma, ...)  diff-solvers-main/solvers.py:9-14
+ * and the arithmetic underneath it is PyTorch library calls.  This header is the thin C ABI those
+ * Python shims (diff-sampler_b200/solvers.py, net.py) bind with ctypes; every entry point names the
+ * reference code it replaces.  Plain pointers and sizes only — no torch types, no exceptions; every
+ * function returns 0 on success and a negative code on failure (text via ds_last_error()).
+ *
+ * All device pointers are CUDA device addresses on the current device; `stream` is a cudaStream_t
+ * passed as void*.  A handle is bound to one device; calls on one handle must be serialised by the
+ * caller (the reference is single-threaded per process, one process per GPU).
+ */
+#ifndef DIFFSAMPLER_B200_H
+#define DIFFSAMPLER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Library version string, e.g. "diffsampler_b200 0.1 (sm_100a)". */
+const char* ds_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* ds_last_error(void);
+
+/* ---- denoiser network: replaces net(x, sigma, class_labels) ---------------------------------
+ * EDMPrecond.forward + SongUNet/DhariwalUNet.forward, networks_edm.py:482-496, :312-355, :427-453.
+ * `weights` is the packed blob produced by diff-sampler_b200/plan.py (fp16 hi/lo K-major conv
+ * matrices + fp32 vectors); `plan` is an array of ds_plan_op records (csrc/ops.h) lowered for one
+ * batch size.  The library copies the blob to device memory and owns it plus its workspace arena. */
+typedef struct ds_weights ds_weights;
+typedef struct ds_unet ds_unet;
+
+int ds_weights_create(const void* host_blob, size_t bytes, ds_weights** out);
+void ds_weights_destroy(ds_weights* w);
+
+int ds_unet_create(const ds_weights* w, const void* plan_ops, int n_ops, size_t op_size, size_t arena_bytes, ds_unet** out);
+void ds_unet_destroy(ds_unet* u);
+
+/* One denoiser evaluation D = net(x, sigma[, labels]).
+ *   x            [B, C, H, W] fp32 NCHW (not modified)
+ *   sigma        device pointer to 1 or B fp32 values (as lowered in the plan)
+ *   labels       [B, label_dim] fp32 or NULL
+ *   out_D        [B, C, H, W] fp32 NCHW
+ *   out_bottleneck  optional [B, 8*8] channel-mean of the U-Net bottleneck (AMED, solvers_amed.py:7-27) or NULL */
+int ds_unet_forward(ds_unet* u, const float* x, const float* sigma, const float* labels, float* out_D,
+                    float* out_bottleneck, void* stream);
+
+/* Debug/test access to the workspace arena (device -> host copy, synchronises the stream). */
+int ds_unet_debug_read(ds_unet* u, size_t arena_offset, void* host_dst, size_t bytes, void* stream);
+/* Number of kernels launched by the last ds_unet_forward on this handle. */
+int ds_unet_last_launch_count(const ds_unet* u);
+
+/* ---- solver update: replaces the 4-12 elementwise ATen launches per step ------------------------
+ * solvers.py:80-81 (Euler), :163-168 (Heun), :252-258 (DPM-2), :346-352 (iPNDM), :451-477 (iPNDM_v),
+ * :576-585 (DEIS); solver_utils.py:102-163 (DPM-Solver++), :250-285 (UniPC); amed solver_utils.py:90-160.
+ *   m0  = D | clamp(D,-s,s)/s | (xs - D)/t | xs/t | none        (mode 0..3; s = thr[b])
+ *   out = coef[0]*xb + coef[1]*m0 + sum_k coef[2+k]*hist[k]
+ * Coefficients are scalars (coef) or per-sample device vectors coef_dev[6][B] (AMED).  */
+int ds_solver_update(float* out_x, float* out_m, const float* xb, const float* xs, const float* D,
+                     const float* const* hist, int nhist, const float* thr, int mode, float t, const float* t_dev,
+                     const float* coef6, const float* coef_dev, int64_t n_per_sample, int B, void* stream);
+
+/* ---- dynamic thresholding: replaces torch.quantile(|x0|, 0.995) per sample ---------------------
+ * solver_utils.py:77-86.  thr[b] = max(quantile_linear(|x0[b]|, q), floor_val).  Exact selection. */
+int ds_dyn_threshold(const float* x0, float* thr, int B, int row_len, float q, float floor_val, void* stream);
+
+/* ---- kernel-level entry points (used by the parity tests and micro-benchmarks) ------------------
+ * `desc` points to the matching struct of csrc/ops.h with absolute device pointers. */
+int ds_op_launch(int op_type, const void* desc, size_t desc_size, void* stream);
+/* sizeof() of the descriptor structs as compiled (0 = ds_plan_op, else DS_OP_* code); lets bindings verify their mirrors. */
+size_t ds_sizeof(int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
