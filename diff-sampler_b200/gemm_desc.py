@@ -1,0 +1,163 @@
+"""Builders for ds_gemm_desc (csrc/ops.h): how each contraction of the denoiser maps onto the one
+tcgen05 kernel.  Pure integer/shape logic — importable and testable without a GPU.
+
+Pointer arguments are either absolute device addresses (tests) or plan references (plan.py)."""
+from . import _cstructs as S
+
+H16 = 2  # bytes per fp16
+
+
+def pick_bn(n):
+    """N tile: the largest UMMA N (<=256, multiple of 16) among the tilings with the least padding."""
+    best = None
+    for bn in (256, 192, 128, 64, 32, 16):
+        tiles = -(-n // bn)
+        waste = tiles * bn - n
+        key = (waste, -bn)
+        if best is None or key < best[0]:
+            best = (key, bn, tiles)
+    return best[1], best[2]
+
+
+def split_planes_rows(n_valid, bn):
+    tiles = -(-n_valid // bn)
+    return tiles, tiles * bn
+
+
+def conv_box(H, W):
+    """TMA box (64, bw, bh, bn) covering 128 consecutive NHWC pixels."""
+    assert W <= 128 and 128 % W == 0, f'unsupported width {W}'
+    bw = W
+    bh = min(H, 128 // W)
+    bn = 128 // (bw * bh)
+    assert bw * bh * bn == 128
+    return bw, bh, bn
+
+
+def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w_planes=2, a2_ptr=0, C2=0,
+              out_f32=0, out_h16=0, o_planes=2, ldo=None, bias=0, rowvec=0, rowvec_stride=0, residual=0, ldr=None, scale=1.0,
+              edm=None, bn=None):
+    """3x3 (taps=9) or 1x1 (taps=1) convolution over NHWC fp16 planes [a_planes][Bn][H][W][C] with the
+    packed weight matrix [w_planes][Cout_pad][taps*C + C2] (K ordered tap-major, then the aux/skip block).
+    Output rows are NHWC pixels: out[pixel][cout] (+ fused epilogue)."""
+    assert C % 64 == 0 and C2 % 64 == 0
+    if npass == 3:
+        assert a_planes == 2 and w_planes == 2
+    d = S.GemmDesc()
+    bw, bh, bnn = conv_box(H, W)
+    BN, n_tiles = (bn, -(-Cout // bn)) if bn else pick_bn(Cout)
+    cout_pad = n_tiles * BN
+    ktot = taps * C + C2
+    d.a_ptr = a_ptr
+    d.a_dims[:] = [C, W, H, a_planes * Bn]
+    d.a_strides[:] = [C * H16, W * C * H16, H * W * C * H16]
+    d.a_box[:] = [64, bw, bh, bnn]
+    d.a_plane_n = Bn
+    d.a2_ptr = a2_ptr
+    d.a2_c = C2
+    d.a2_plane_n = Bn
+    d.nkb_aux = C2 // 64
+    d.b_ptr = w_ptr
+    d.b_dims[:] = [ktot, cout_pad, w_planes]
+    d.b_strides[:] = [ktot * H16, cout_pad * ktot * H16]
+    d.b_plane_batch = 1
+    d.BN = BN
+    d.m_tiles = -(-(Bn * H * W) // 128)
+    d.n_tiles = n_tiles
+    d.num_z = 1
+    d.nh = 1
+    d.taps = taps
+    d.cpb = C // 64
+    d.npass = npass
+    d.a_mode = 0
+    d.conv_H, d.conv_W = H, W
+    d.m_valid = Bn * H * W
+    d.n_valid = Cout
+    d.out_f32 = out_f32
+    d.out_h16 = out_h16
+    d.ldo = ldo if ldo is not None else Cout
+    d.o_plane = (Bn * H * W * d.ldo) if (out_h16 and o_planes == 2) else 0
+    d.bias_n = bias
+    d.rowvec = rowvec
+    d.rowvec_stride = rowvec_stride
+    d.rows_per_sample = H * W
+    d.residual = residual
+    d.ldr = ldr if ldr is not None else Cout
+    d.scale = scale
+    if edm is not None:
+        d.edm_out = 1
+        d.edm_x, d.edm_coef, d.edm_coef_stride, d.edm_C, d.edm_D = edm
+    return d, dict(BN=BN, n_tiles=n_tiles, cout_pad=cout_pad, ktot=ktot)
+
+
+def rows_gemm(a_ptr, a_rows, a_pitch, a_batches, b_ptr, b_rows, b_pitch, b_batches, K, *, num_z, nh=1, m_valid, n_valid,
+              npass=3, a_planes=2, b_planes=2, a_c_per_zh=0, a_n_per_zb=0, a_n_per_zh=0, b_k0=0, b_k_per_zh=0, b_row_per_zh=0,
+              b_z_per_zb=0, b_z_per_zh=0, out_f32=0, out_h16=0, o_zb=0, o_zh=0, ldo=0, o_plane=0, bias_n=0, bias_m=0,
+              residual=0, ldr=0, scale=1.0, bn=None):
+    """Batched row-major product  D_z[m][n] = sum_k A_z[m][k] * B_z[n][k].
+    A: fp16 planes [a_planes][a_batches][a_rows][a_pitch]; B: fp16 planes [b_planes][b_batches][b_rows][b_pitch].
+    z = zb*nh + zh selects the batch entry / column window of each operand (see csrc/ops.h)."""
+    assert K % 64 == 0
+    d = S.GemmDesc()
+    BN, n_tiles = (bn, -(-n_valid // bn)) if bn else pick_bn(n_valid)
+    d.a_ptr = a_ptr
+    d.a_dims[:] = [a_pitch, a_rows, 1, a_planes * a_batches]
+    d.a_strides[:] = [a_pitch * H16, a_rows * a_pitch * H16, a_rows * a_pitch * H16]
+    d.a_box[:] = [64, 128, 1, 1]
+    d.a_plane_n = a_batches
+    d.b_ptr = b_ptr
+    d.b_dims[:] = [b_pitch, b_rows, b_planes * b_batches]
+    d.b_strides[:] = [b_pitch * H16, b_rows * b_pitch * H16]
+    d.b_plane_batch = b_batches
+    d.BN = BN
+    d.m_tiles = -(-m_valid // 128)
+    d.n_tiles = n_tiles
+    d.num_z = num_z
+    d.nh = nh
+    d.taps = 1
+    d.cpb = K // 64
+    d.npass = npass
+    d.a_mode = 1
+    d.conv_H = d.conv_W = 1
+    d.a_c_per_zh, d.a_n_per_zb, d.a_n_per_zh = a_c_per_zh, a_n_per_zb, a_n_per_zh
+    d.b_k0, d.b_k_per_zh, d.b_row_per_zh, d.b_z_per_zb, d.b_z_per_zh = b_k0, b_k_per_zh, b_row_per_zh, b_z_per_zb, b_z_per_zh
+    d.m_valid, d.n_valid = m_valid, n_valid
+    d.out_f32, d.out_h16 = out_f32, out_h16
+    d.o_zb, d.o_zh, d.ldo, d.o_plane = o_zb, o_zh, ldo, o_plane
+    d.bias_n, d.bias_m = bias_n, bias_m
+    d.rows_per_sample = 1
+    d.residual, d.ldr = residual, ldr
+    d.scale = scale
+    return d, dict(BN=BN, n_tiles=n_tiles)
+
+
+def pack_conv_weight(weight, skip_weight=None, cin_pad=None, bn=None):
+    """torch CPU: Conv2d weight [Cout, Cin, k, k] (+ optional 1x1 skip weight [Cout, C2, 1, 1]) ->
+    fp16 planes [2][Cout_pad][taps*Cin_pad + C2], K ordered (kh, kw, cin) then the skip block."""
+    import torch
+    cout, cin, kh, kw = weight.shape
+    cin_pad = cin_pad or -(-cin // 64) * 64
+    w = torch.zeros(cout, kh, kw, cin_pad, dtype=torch.float32)
+    w[..., :cin] = weight.detach().float().permute(0, 2, 3, 1)
+    w = w.reshape(cout, kh * kw * cin_pad)
+    if skip_weight is not None:
+        c2 = skip_weight.shape[1]
+        c2_pad = -(-c2 // 64) * 64
+        sk = torch.zeros(cout, c2_pad, dtype=torch.float32)
+        sk[:, :c2] = skip_weight.detach().float().reshape(cout, c2)
+        w = torch.cat([w, sk], dim=1)
+    BN, n_tiles = (bn, -(-cout // bn)) if bn else pick_bn(cout)
+    cout_pad = BN * n_tiles
+    wp = torch.zeros(cout_pad, w.shape[1], dtype=torch.float32)
+    wp[:cout] = w
+    hi = wp.half()
+    lo = (wp - hi.float()).half()
+    return torch.stack([hi, lo]).contiguous()
+
+
+def split_planes(x):
+    """fp32 tensor -> stacked fp16 (hi, lo) planes with hi + lo ~= x to ~2^-22."""
+    import torch
+    hi = x.half()
+    lo = (x - hi.float()).half()
+    return torch.stack([hi, lo]).contiguous()

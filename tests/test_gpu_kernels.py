@@ -1,0 +1,371 @@
+"""Kernel-level parity (GPU): each hand-written kernel, called through the C ABI (ds_op_launch /
+ds_solver_update / ds_dyn_threshold), against plain PyTorch fp32/fp64 math on the same inputs."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from diff_sampler_b200 import _lib
+    return _lib
+
+
+def dev():
+    return torch.device('cuda:0')
+
+
+def sync():
+    torch.cuda.synchronize()
+
+
+def planes(x):
+    from diff_sampler_b200.gemm_desc import split_planes
+    return split_planes(x)
+
+
+# --------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize('npass', [1, 3])
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (300, 200, 128), (1000, 384, 320), (64, 64, 64)])
+def test_rows_gemm(lib, npass, M, N, K):
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=dev())
+    Bm = torch.randn(N, K, device=dev())
+    Ap, Bp = planes(A), planes(Bm)
+    out = torch.full((M, N), float('nan'), device=dev())
+    d, _ = G.rows_gemm(Ap.data_ptr(), M, K, 1, Bp.data_ptr(), N, K, 1, K, num_z=1, m_valid=M, n_valid=N, npass=npass,
+                       out_f32=out.data_ptr(), ldo=N)
+    lib.op_launch(d)
+    sync()
+    if npass == 1:
+        ref = Ap[0].double() @ Bp[0].double().t()
+        tol = 1e-4
+    else:
+        ref = A.double() @ Bm.double().t()
+        tol = 2e-5
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f'rows_gemm npass={npass} M{M} N{N} K{K}: max err {err:.3e} (scale {scale:.2f})')
+    assert not torch.isnan(out).any()
+    assert err <= tol * scale
+
+
+@pytest.mark.parametrize('npass', [1, 3])
+@pytest.mark.parametrize('Bn,H,W,Cin,Cout', [(3, 32, 32, 64, 128), (3, 16, 16, 128, 192), (3, 8, 8, 64, 256), (2, 64, 64, 64, 64),
+                                             (5, 8, 8, 128, 3)])
+def test_conv3x3(lib, npass, Bn, H, W, Cin, Cout):
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(1)
+    x = torch.randn(Bn, Cin, H, W, device=dev())
+    w = torch.randn(Cout, Cin, 3, 3, device=dev()) / (3 * Cin ** 0.5)
+    xa = planes(x.permute(0, 2, 3, 1).contiguous())                 # [2][Bn][H][W][C]
+    wp = G.pack_conv_weight(w.cpu()).to(dev())
+    out = torch.full((Bn * H * W, Cout), float('nan'), device=dev())
+    d, info = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=9, npass=npass, out_f32=out.data_ptr())
+    lib.op_launch(d)
+    sync()
+    if npass == 1:
+        ref = F.conv2d(xa[0].permute(0, 3, 1, 2).double(), wp[0][:Cout].double().reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2), padding=1)
+        tol = 1e-4
+    else:
+        ref = F.conv2d(x.double(), w.double(), padding=1)
+        tol = 2e-5
+    ref = ref.permute(0, 2, 3, 1).reshape(Bn * H * W, Cout)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f'conv3x3 npass={npass} {Bn}x{H}x{W} {Cin}->{Cout} BN={info["BN"]}: max err {err:.3e} (scale {scale:.2f})')
+    assert not torch.isnan(out).any()
+    assert err <= tol * scale
+
+
+def test_conv_fused_epilogue(lib):
+    """conv1 of a UNetBlock: 3x3 conv + 1x1 skip appended on K + bias + per-sample embedding + residual, * skip_scale,
+    fp32 and fp16-plane outputs (networks_edm.py:169-171)."""
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(2)
+    Bn, H, W, Cin, C2, Cout = 4, 16, 16, 128, 64, 128
+    x = torch.randn(Bn, Cin, H, W, device=dev())
+    orig = torch.randn(Bn, C2, H, W, device=dev())
+    w = torch.randn(Cout, Cin, 3, 3, device=dev()) / (3 * Cin ** 0.5)
+    ws = torch.randn(Cout, C2, 1, 1, device=dev()) / C2 ** 0.5
+    bias = torch.randn(Cout, device=dev())
+    emb = torch.randn(Bn, Cout, device=dev())
+    res = torch.randn(Bn, Cout, H, W, device=dev())
+    xa = planes(x.permute(0, 2, 3, 1).contiguous())
+    oa = planes(orig.permute(0, 2, 3, 1).contiguous())
+    wp = G.pack_conv_weight(w.cpu(), ws.cpu()).to(dev())
+    res_nhwc = res.permute(0, 2, 3, 1).contiguous()
+    out = torch.full((Bn * H * W, Cout), float('nan'), device=dev())
+    out_h = torch.zeros(2, Bn * H * W, Cout, dtype=torch.float16, device=dev())
+    d, _ = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=9, npass=3, a2_ptr=oa.data_ptr(), C2=C2,
+                       out_f32=out.data_ptr(), out_h16=out_h.data_ptr(), bias=bias.data_ptr(), rowvec=emb.data_ptr(),
+                       rowvec_stride=Cout, residual=res_nhwc.data_ptr(), scale=0.70710678)
+    lib.op_launch(d)
+    sync()
+    ref = F.conv2d(x.double(), w.double(), padding=1) + F.conv2d(orig.double(), ws.double())
+    ref = (ref + bias.double()[None, :, None, None] + emb.double()[:, :, None, None] + res.double()) * 0.70710678
+    ref = ref.permute(0, 2, 3, 1).reshape(Bn * H * W, Cout)
+    err = (out.double() - ref).abs().max().item()
+    errh = ((out_h[0].double() + out_h[1].double()) - ref).abs().max().item()
+    print(f'fused epilogue: f32 err {err:.3e}  h16-planes err {errh:.3e}')
+    assert err < 5e-5 * ref.abs().max().item()
+    assert errh < 5e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize('L,d,nh', [(256, 256, 1), (64, 64, 3), (1024, 64, 2)])
+def test_attention_gemms(lib, L, d, nh):
+    """S = Q K^T / sqrt(d) and O = P V through the batched rows mode (networks_edm.py:108, :176)."""
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(3)
+    Bn = 2
+    Cc = nh * d
+    qk = torch.randn(Bn, L, 2 * Cc, device=dev())          # [b][l][q heads | k heads]
+    vt = torch.randn(Bn, Cc, L, device=dev())              # V^T: [b][head*d + c][l]
+    qkp, vtp = planes(qk), planes(vt)
+    Smat = torch.full((Bn * nh, L, L), float('nan'), device=dev())
+    scale = 1.0 / d ** 0.5
+    dS, _ = G.rows_gemm(qkp.data_ptr(), L, 2 * Cc, Bn, qkp.data_ptr(), L, 2 * Cc, Bn, d, num_z=Bn * nh, nh=nh, m_valid=L, n_valid=L,
+                        a_c_per_zh=d, a_n_per_zb=1, b_k0=Cc, b_k_per_zh=d, b_z_per_zb=1, out_f32=Smat.data_ptr(),
+                        o_zb=nh * L * L, o_zh=L * L, ldo=L, scale=scale)
+    lib.op_launch(dS)
+    sync()
+    q = qk[:, :, :Cc].reshape(Bn, L, nh, d).permute(0, 2, 1, 3).double()
+    k = qk[:, :, Cc:].reshape(Bn, L, nh, d).permute(0, 2, 1, 3).double()
+    refS = (q @ k.transpose(-1, -2) * scale).reshape(Bn * nh, L, L)
+    errS = (Smat.double() - refS).abs().max().item()
+    print(f'QK^T L{L} d{d} nh{nh}: err {errS:.3e}')
+    assert errS < 3e-5 * refS.abs().max().item()
+
+    Pm = torch.softmax(Smat, dim=-1)
+    Pp = planes(Pm)
+    O = torch.zeros(2, Bn, L, Cc, dtype=torch.float16, device=dev())
+    dO, _ = G.rows_gemm(Pp.data_ptr(), L, L, Bn * nh, vtp.data_ptr(), Cc, L, Bn, L, num_z=Bn * nh, nh=nh, m_valid=L, n_valid=d,
+                        a_n_per_zb=nh, a_n_per_zh=1, b_row_per_zh=d, b_z_per_zb=1, out_h16=O.data_ptr(), o_zb=L * Cc, o_zh=d,
+                        ldo=Cc, o_plane=Bn * L * Cc)
+    lib.op_launch(dO)
+    sync()
+    v = vt.reshape(Bn, nh, d, L).double()
+    refO = (Pm.reshape(Bn, nh, L, L).double() @ v.transpose(-1, -2)).permute(0, 2, 1, 3).reshape(Bn, L, Cc)
+    errO = ((O[0].double() + O[1].double()) - refO).abs().max().item()
+    print(f'PV   L{L} d{d} nh{nh}: err {errO:.3e}')
+    assert errO < 3e-5 * max(1.0, refO.abs().max().item())
+
+
+def test_vt_gemm_bias_m(lib):
+    """V^T = Wv . n2^T with the weight as the M operand and a bias along M."""
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(4)
+    Bn, L, Cc = 3, 64, 192
+    Wv = torch.randn(Cc, Cc, device=dev()) / Cc ** 0.5
+    bv = torch.randn(Cc, device=dev())
+    n2 = torch.randn(Bn, L, Cc, device=dev())
+    Wp, n2p = planes(Wv), planes(n2)
+    Vt = torch.zeros(2, Bn, Cc, L, dtype=torch.float16, device=dev())
+    dV, _ = G.rows_gemm(Wp.data_ptr(), Cc, Cc, 1, n2p.data_ptr(), L, Cc, Bn, Cc, num_z=Bn, nh=1, m_valid=Cc, n_valid=L,
+                        b_z_per_zb=1, out_h16=Vt.data_ptr(), o_zb=Cc * L, ldo=L, o_plane=Bn * Cc * L, bias_m=bv.data_ptr())
+    lib.op_launch(dV)
+    sync()
+    ref = (Wv.double() @ n2.double().transpose(1, 2)) + bv.double()[None, :, None]
+    err = ((Vt[0].double() + Vt[1].double()) - ref).abs().max().item()
+    print(f'Vt gemm err {err:.3e}')
+    assert err < 3e-5 * ref.abs().max().item()
+
+
+def test_edm_output_fold(lib):
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(5)
+    Bn, H, W, Cin, Cimg = 3, 16, 16, 128, 3
+    a = torch.randn(Bn, Cin, H, W, device=dev())
+    w = torch.randn(Cimg, Cin, 3, 3, device=dev()) / (3 * Cin ** 0.5)
+    b = torch.randn(Cimg, device=dev())
+    x = torch.randn(Bn, Cimg, H, W, device=dev())
+    coef = torch.rand(Bn, 4, device=dev()) + 0.5
+    xa = planes(a.permute(0, 2, 3, 1).contiguous())
+    wp = G.pack_conv_weight(w.cpu()).to(dev())
+    D = torch.full((Bn, Cimg, H, W), float('nan'), device=dev())
+    d, _ = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cimg, taps=9, npass=3, bias=b.data_ptr(),
+                       edm=(x.data_ptr(), coef.data_ptr(), 4, Cimg, D.data_ptr()))
+    lib.op_launch(d)
+    sync()
+    Fx = F.conv2d(a.double(), w.double(), b.double(), padding=1)
+    ref = coef[:, 0].double()[:, None, None, None] * x.double() + coef[:, 1].double()[:, None, None, None] * Fx
+    err = (D.double() - ref).abs().max().item()
+    print(f'edm fold err {err:.3e}')
+    assert err < 3e-5 * ref.abs().max().item()
+
+
+# --------------------------------------------------------------------------------------------- GroupNorm
+@pytest.mark.parametrize('C0,C1,H,W,resample,ada,silu', [
+    (128, 0, 16, 16, 0, False, True), (256, 128, 8, 8, 0, False, True), (192, 0, 16, 16, 1, True, True),
+    (576, 384, 8, 8, 2, True, True), (256, 0, 32, 32, 0, False, False), (1344, 0, 8, 8, 0, False, True)])
+def test_groupnorm_apply(lib, C0, C1, H, W, resample, ada, silu):
+    from diff_sampler_b200 import _cstructs as S
+    torch.manual_seed(6)
+    Bn, Cc, G = 3, C0 + C1, 32
+    x0 = torch.randn(Bn, H, W, C0, device=dev()) * 1.7 + 0.3
+    x1 = torch.randn(Bn, H, W, C1, device=dev()) * 0.6 - 0.2 if C1 else None
+    gamma = torch.randn(Cc, device=dev())
+    beta = torch.randn(Cc, device=dev())
+    adav = torch.randn(Bn, 2 * Cc, device=dev()) * 0.3 if ada else None
+    sums = torch.zeros(Bn, G, 2, dtype=torch.float64, device=dev())
+    ds = S.GnStatsDesc(src0=x0.data_ptr(), src1=x1.data_ptr() if C1 else 0, C0=C0, C1=C1, HW=H * W, B=Bn, groups=G,
+                       sums=sums.data_ptr())
+    lib.op_launch(ds)
+    Ho, Wo = (H // 2, W // 2) if resample == 1 else ((H * 2, W * 2) if resample == 2 else (H, W))
+    act = torch.zeros(2, Bn, Ho, Wo, Cc, dtype=torch.float16, device=dev())
+    raw = torch.zeros(2, Bn, Ho, Wo, Cc, dtype=torch.float16, device=dev())
+    rawf = torch.zeros(Bn, Ho, Wo, Cc, device=dev())
+    da = S.GnApplyDesc(src0=x0.data_ptr(), src1=x1.data_ptr() if C1 else 0, C0=C0, C1=C1, H=H, W=W, B=Bn, groups=G,
+                       sums=sums.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(), eps=1e-6, silu=int(silu),
+                       ada=adav.data_ptr() if ada else 0, ada_stride=2 * Cc if ada else 0, resample=resample, nplanes=2,
+                       out_act=act.data_ptr(), out_raw=raw.data_ptr(), out_raw_f32=rawf.data_ptr())
+    lib.op_launch(da)
+    sync()
+    xc = torch.cat([x0, x1], dim=-1) if C1 else x0
+    xn = xc.permute(0, 3, 1, 2).double()
+    y = F.group_norm(xn, G, gamma.double(), beta.double(), eps=1e-6)
+    if ada:
+        sc, sh = adav[:, :Cc].double(), adav[:, Cc:].double()
+        y = y * (sc[:, :, None, None] + 1) + sh[:, :, None, None]
+    if silu:
+        y = F.silu(y)
+    r = xn
+    if resample == 1:
+        y, r = F.avg_pool2d(y, 2), F.avg_pool2d(r, 2)
+    elif resample == 2:
+        y, r = F.interpolate(y, scale_factor=2, mode='nearest'), F.interpolate(r, scale_factor=2, mode='nearest')
+    y, r = y.permute(0, 2, 3, 1), r.permute(0, 2, 3, 1)
+    e_act = ((act[0].double() + act[1].double()) - y).abs().max().item()
+    e_raw = ((raw[0].double() + raw[1].double()) - r).abs().max().item()
+    e_rawf = (rawf.double() - r).abs().max().item()
+    print(f'gn C{C0}+{C1} {H}x{W} rs{resample} ada{ada}: act {e_act:.2e} raw {e_raw:.2e} rawf {e_rawf:.2e}')
+    assert e_act < 2e-5 * max(1.0, y.abs().max().item())
+    assert e_raw < 1e-5 and e_rawf < 1e-6
+
+
+def test_softmax(lib):
+    from diff_sampler_b200 import _cstructs as S
+    torch.manual_seed(7)
+    for L in (64, 256, 1024):
+        Sm = torch.randn(37, L, device=dev()) * 4
+        Pm = torch.zeros(2, 37, L, dtype=torch.float16, device=dev())
+        lib.op_launch(S.SoftmaxDesc(S=Sm.data_ptr(), P=Pm.data_ptr(), rows=37, L=L, nplanes=2))
+        sync()
+        ref = torch.softmax(Sm.double(), -1)
+        err = ((Pm[0].double() + Pm[1].double()) - ref).abs().max().item()
+        print(f'softmax L{L}: {err:.2e}')
+        assert err < 2e-6
+
+
+def test_posemb_linear_prep(lib):
+    from diff_sampler_b200 import _cstructs as S
+    torch.manual_seed(8)
+    sig = torch.tensor([80.0, 3.3, 0.002, 0.7], device=dev())
+    nc = 128
+    coef = torch.zeros(4, 4, device=dev())
+    emb = torch.zeros(4, nc, device=dev())
+    lib.op_launch(S.PosembDesc(sigma=sig.data_ptr(), nsig=4, num_channels=nc, endpoint=1, swap_sincos=1, sigma_data=0.5,
+                               coef=coef.data_ptr(), emb=emb.data_ptr()))
+    sync()
+    cn = sig.log() / 4
+    freqs = (1 / 10000) ** (torch.arange(nc // 2, device=dev(), dtype=torch.float32) / (nc // 2 - 1))
+    e = cn.ger(freqs)
+    ref = torch.cat([e.sin(), e.cos()], dim=1)
+    assert (emb - ref).abs().max().item() < 2e-6
+    s2 = sig ** 2 + 0.25
+    refc = torch.stack([0.25 / s2, sig * 0.5 / s2.sqrt(), 1 / s2.sqrt(), cn], dim=1)
+    assert ((coef - refc).abs() / refc.abs().clamp_min(1e-3)).max().item() < 1e-6
+
+    Wt = torch.randn(300, nc, device=dev()) / nc ** 0.5
+    b = torch.randn(300, device=dev())
+    out = torch.zeros(4, 300, device=dev())
+    lib.op_launch(S.LinearDesc(in_=emb.data_ptr(), in_stride=nc, W=Wt.data_ptr(), b=b.data_ptr(), add=0, add_stride=0,
+                               out=out.data_ptr(), n_rows=4, in_f=nc, out_f=300, act=1, in_scale=1.0))
+    sync()
+    refl = F.silu(emb.double() @ Wt.double().t() + b.double())
+    assert (out.double() - refl).abs().max().item() < 1e-5
+
+    x = torch.randn(4, 3, 8, 8, device=dev()) * 10
+    o = torch.zeros(2, 4, 64, 64, dtype=torch.float16, device=dev())
+    lib.op_launch(S.PrepInputDesc(x=x.data_ptr(), coef=coef.data_ptr(), coef_stride=4, B=4, C=3, HW=64, nplanes=2, out=o.data_ptr()))
+    sync()
+    refx = (x * coef[:, 2][:, None, None, None]).permute(0, 2, 3, 1).reshape(4, 64, 3).double()
+    got = o[0].double() + o[1].double()
+    assert (got[:, :, :3] - refx).abs().max().item() < 1e-5
+    assert got[:, :, 3:].abs().max().item() == 0
+
+
+# --------------------------------------------------------------------------------------------- solver
+def _update(lib, out_m, xb, xs, D, hist, thr, mode, t, coef, t_dev=None, coef_dev=None):
+    l = lib.load()
+    out = torch.empty_like(xb)
+    hp = (C.c_void_p * 4)(*[h.data_ptr() for h in hist], *([None] * (4 - len(hist))))
+    cf = (C.c_float * 6)(*coef)
+    B = xb.shape[0]
+    rc = l.ds_solver_update(out.data_ptr(), out_m.data_ptr() if out_m is not None else None, xb.data_ptr(),
+                            xs.data_ptr() if xs is not None else None, D.data_ptr() if D is not None else None, hp, len(hist),
+                            thr.data_ptr() if thr is not None else None, mode, t, t_dev.data_ptr() if t_dev is not None else None,
+                            cf, coef_dev.data_ptr() if coef_dev is not None else None, xb[0].numel(), B, None)
+    lib.check(rc, 'ds_solver_update')
+    sync()
+    return out
+
+
+def test_solver_update_modes(lib):
+    torch.manual_seed(9)
+    B = 5
+    x = torch.randn(B, 3, 32, 32, device=dev()) * 20
+    D = torch.randn(B, 3, 32, 32, device=dev())
+    h = [torch.randn_like(x) for _ in range(3)]
+    t, tn = 12.5, 7.25
+    # Euler (solvers.py:80-81) with the history entry written back
+    m = torch.empty_like(x)
+    out = _update(lib, m, x, None, D, [], None, 1, t, [1.0, tn - t, 0, 0, 0, 0])
+    d_ref = (x - D) / t
+    assert (m - d_ref).abs().max().item() <= 2e-7 * d_ref.abs().max().item()   # torch multiplies by 1/t on CUDA
+    assert (out - (x + (tn - t) * d_ref)).abs().max().item() < 1e-4
+    # iPNDM order 4 (solvers.py:352)
+    hh = tn - t
+    out = _update(lib, m, x, None, D, h, None, 1, t, [1.0, hh * 55 / 24, -hh * 59 / 24, hh * 37 / 24, -hh * 9 / 24, 0])
+    ref = x + hh * (55 * d_ref - 59 * h[0] + 37 * h[1] - 9 * h[2]) / 24
+    assert (out - ref).abs().max().item() < 2e-4
+    # AFS first step (solvers.py:77): d = x / sqrt(1 + t^2)
+    div = (1 + t * t) ** 0.5
+    out = _update(lib, m, x, None, None, [], None, 2, div, [1.0, hh, 0, 0, 0, 0])
+    assert (out - (x + hh * (x / div))).abs().max().item() < 1e-4
+    # x0 mode with dynamic thresholding (solver_utils.py:77-86, :110)
+    thr = torch.rand(B, device=dev()) + 0.5
+    out = _update(lib, m, x, None, D, [], thr, 0, 0.0, [0.3, -0.9, 0, 0, 0, 0])
+    s = thr[:, None, None, None]
+    x0 = torch.clamp(D, -s, s) / s
+    assert torch.equal(m, x0)
+    assert (out - (0.3 * x - 0.9 * x0)).abs().max().item() < 1e-5
+    # per-sample coefficients / divisors (AMED)
+    cd = torch.rand(6, B, device=dev())
+    td = torch.rand(B, device=dev()) + 1
+    out = _update(lib, m, x, None, D, h[:1], None, 1, 0.0, [0] * 6, t_dev=td, coef_dev=cd)
+    dd = (x - D) / td[:, None, None, None]
+    ref = cd[0][:, None, None, None] * x + cd[1][:, None, None, None] * dd + cd[2][:, None, None, None] * h[0]
+    assert (out - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+    # scale-only (x_next = latents * t_steps[0], solvers.py:68)
+    out = _update(lib, None, x, None, None, [], None, 3, 0.0, [80.0, 0, 0, 0, 0, 0])
+    assert torch.equal(out, x * 80.0)
+
+
+@pytest.mark.parametrize('n', [3072, 12288, 16384, 1000])
+def test_dyn_threshold_matches_torch_quantile(lib, n):
+    torch.manual_seed(10)
+    B = 7
+    x0 = torch.randn(B, n, device=dev()) * torch.tensor([0.1, 0.5, 1, 2, 5, 0.01, 30.0], device=dev())[:, None]
+    x0[1, :50] = 0.7           # ties around the selected rank
+    thr = torch.zeros(B, device=dev())
+    lib.check(lib.load().ds_dyn_threshold(x0.data_ptr(), thr.data_ptr(), B, n, 0.995, 1.0, None), 'ds_dyn_threshold')
+    sync()
+    ref = torch.maximum(torch.quantile(x0.abs(), 0.995, dim=1), torch.ones(B, device=dev()))
+    print('thr', thr.tolist(), 'ref', ref.tolist())
+    assert (thr - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
