@@ -199,7 +199,7 @@ def get_deis_coeff_list(t_steps, max_order, N=10000, deis_mode='tab'):
         def I3(a, b, c, s, e, d):                                         # :372-375
             co = (e ** 4 - s ** 4) / 4 - (e ** 3 - s ** 3) * (a + b + c) / 3 + (e ** 2 - s ** 2) * (a * b + a * c + b * c) / 2 - (e - s) * a * b * c
             return co / ((d - a) * (d - b) * (d - c))
-        C = []
+        C, row = [], None
         for i, (tc, tn) in enumerate(zip(t_steps[:-1], t_steps[1:])):
             order = min(i, max_order)
             if order == 0:
@@ -207,12 +207,14 @@ def get_deis_coeff_list(t_steps, max_order, N=10000, deis_mode='tab'):
                 continue
             p = t_steps[[i - k for k in range(order + 1)]]
             if order == 1:
-                C.append([((tn - p[1]) ** 2 - (tc - p[1]) ** 2) / (2 * (tc - p[1])), (tn - tc) ** 2 / (2 * (p[1] - tc))])
+                row = [((tn - p[1]) ** 2 - (tc - p[1]) ** 2) / (2 * (tc - p[1])), (tn - tc) ** 2 / (2 * (p[1] - tc))]
             elif order == 2:
-                C.append([I2(p[1], p[2], tc, tn, tc), I2(tc, p[2], tc, tn, p[1]), I2(tc, p[1], tc, tn, p[2])])
+                row = [I2(p[1], p[2], tc, tn, tc), I2(tc, p[2], tc, tn, p[1]), I2(tc, p[1], tc, tn, p[2])]
             elif order == 3:
-                C.append([I3(p[1], p[2], p[3], tc, tn, tc), I3(tc, p[2], p[3], tc, tn, p[1]), I3(tc, p[1], p[3], tc, tn, p[2]),
-                          I3(tc, p[1], p[2], tc, tn, p[3])])
+                row = [I3(p[1], p[2], p[3], tc, tn, tc), I3(tc, p[2], p[3], tc, tn, p[1]), I3(tc, p[1], p[3], tc, tn, p[2]),
+                       I3(tc, p[1], p[2], tc, tn, p[3])]
+            # order >= 4 has no branch in the reference (:384-399): the previous step's row is appended again
+            C.append(row)
         return C
     return None
 

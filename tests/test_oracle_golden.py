@@ -1,0 +1,132 @@
+"""Pin the oracle (oracle/*.py, the CPU restatement) against golden vectors recorded from the REAL reference
+(tests/golden/ref_core.npz, produced by oracle/gen_golden.py importing /root/reference).  CPU only.
+
+The reference ships no tests of its own; these fixtures are the reference's outputs on seeded
+inputs.  Network outputs and sampler results must match bit-for-bit or to fp32 round-off (the oracle executes the
+same torch CPU ops in the same order); integer outputs (GITS dp lists) must be identical.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import edm_oracle as O
+from oracle import solvers_oracle as SO
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'ref_core.npz')
+
+
+@pytest.fixture(scope='module')
+def gold():
+    d = np.load(GOLD)
+    meta = json.loads(bytes(d['meta_json']).decode())
+    return d, meta
+
+
+SAMPLER_CASES = [
+    ('euler', dict(num_steps=6)),
+    ('euler', dict(num_steps=5, afs=True, denoise_to_zero=True)),
+    ('heun', dict(num_steps=5)),
+    ('dpm_2', dict(num_steps=5, r=0.4)),
+    ('ipndm', dict(num_steps=7, max_order=4)),
+    ('ipndm', dict(num_steps=6, max_order=3, afs=True)),
+    ('ipndm_v', dict(num_steps=7, max_order=4)),
+    ('deis', dict(num_steps=7, max_order=4, deis_mode='tab')),
+    ('deis', dict(num_steps=6, max_order=4, deis_mode='rhoab')),
+    ('dpm_pp', dict(num_steps=7, max_order=3, predict_x0=True)),
+    ('dpm_pp', dict(num_steps=6, max_order=2, predict_x0=False)),
+    ('dpm_pp', dict(num_steps=6, max_order=3, predict_x0=True, afs=True, lower_order_final=False)),
+    ('unipc', dict(num_steps=7, max_order=3, predict_x0=True, variant='bh2')),
+    ('unipc', dict(num_steps=6, max_order=2, predict_x0=False, variant='bh1')),
+    ('unipc', dict(num_steps=6, max_order=3, predict_x0=True, afs=True)),
+]
+
+
+def test_schedules_bit_exact(gold):
+    d, _ = gold
+    for st in ('polynomial', 'logsnr', 'time_uniform'):
+        for n in (4, 6, 7, 11, 18, 61):
+            ref = d[f'sched/{st}/{n}']
+            got = SO.get_schedule(n, 0.002, 80, schedule_type=st, schedule_rho=7).float().numpy()
+            assert np.array_equal(ref, got), (st, n)
+    # known-answer anchor quoted in SURVEY.md section 8(c)
+    ks = SO.get_schedule(6, 0.002, 80).numpy()
+    assert np.allclose(ks, [80, 24.4083, 5.83894, 0.965417, 0.0850872, 0.002], rtol=2e-5)
+
+
+@pytest.mark.parametrize('name', ['tiny_song', 'tiny_adm', 'cifar10'])
+@pytest.mark.parametrize('dz', [0, 1])
+def test_network_init_and_forward(gold, name, dz):
+    d, meta = gold
+    P, S = O.make_net(name, seed=0, dezero=bool(dz))
+    assert O.params_digest(P) == meta[f'digest/{name}/{dz}'], 'parameter init differs from the reference constructors'
+    net = O.OracleNet(P, S)
+    x = O.stacked_randn(range(2), (3, S['img_resolution'], S['img_resolution']))
+    lab = torch.eye(S['label_dim'])[torch.tensor([1, 3])] if S['label_dim'] else None
+    for sigma in (40.0, 1.0):
+        got = net(x * sigma, torch.tensor(sigma), class_labels=lab).numpy()
+        ref = d[f'net/{name}/{dz}/{sigma}']
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), (name, dz, sigma, np.abs(got - ref).max())
+    sig = torch.tensor([3.0, 0.4])
+    got = net(x * sig[:, None, None, None], sig, class_labels=lab).numpy()
+    ref = d[f'net/{name}/{dz}/persample']
+    assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize('name', ['tiny_song', 'tiny_adm'])
+def test_samplers_match_reference(gold, name):
+    d, _ = gold
+    P, S = O.make_net(name, seed=0, dezero=True)
+    net = O.OracleNet(P, S)
+    B = 4
+    lat = O.stacked_randn(range(B), (3, S['img_resolution'], S['img_resolution']))
+    lab = None
+    if S['label_dim']:
+        g = torch.Generator().manual_seed(0)
+        lab = torch.eye(S['label_dim'])[torch.randint(S['label_dim'], (B,), generator=g)]
+    for ci, (solver, kw) in enumerate(SAMPLER_CASES):
+        kw = dict(kw)
+        mode = kw.pop('deis_mode', None)
+        if solver == 'deis':
+            ts = SO.get_schedule(kw['num_steps'], 0.002, 80)
+            kw['coeff_list'] = SO.get_deis_coeff_list(ts, kw['max_order'], deis_mode=mode)
+            ref_c = d[f'deis/{ci}']
+            for row, rr in zip(kw['coeff_list'], ref_c):
+                assert np.allclose([float(c) for c in row], rr[:len(row)], rtol=1e-6, atol=1e-9), (ci, row, rr)
+        got = SO.sample(net, lat, solver, class_labels=lab, sigma_min=0.002, sigma_max=80, schedule_type='polynomial', schedule_rho=7, **kw)
+        ref = d[f'sample/{name}/{ci}']
+        err = np.abs(got.numpy() - ref).max()
+        assert err <= 2e-5 * max(1.0, np.abs(ref).max()), (name, solver, kw, err)
+    rt, re = SO.sample(net, lat, 'euler', class_labels=lab, num_steps=6, return_inters=True, return_eps=True, denoise_to_zero=True)
+    assert rt.shape == d[f'traj/{name}/x'].shape and re.shape == d[f'traj/{name}/eps'].shape
+    assert np.abs(rt.numpy() - d[f'traj/{name}/x']).max() < 1e-4
+    assert np.abs(re.numpy() - d[f'traj/{name}/eps']).max() < 1e-4
+
+
+def test_solver_math(gold):
+    d, _ = gold
+    x0 = torch.from_numpy(d['thr/in'])
+    assert np.array_equal(SO.dynamic_thresholding(x0).numpy(), d['thr/out'])
+    # the sort-based restatement of torch.quantile used to validate the CUDA radix select
+    q = SO.quantile_by_sort(x0.abs().reshape(5, -1), 0.995)
+    assert torch.equal(q, torch.quantile(x0.abs().reshape(5, -1), 0.995, dim=1))
+    x = torch.from_numpy(d['upd/x'])
+    ms = list(torch.from_numpy(d['upd/ms']))
+    ts = [torch.tensor(5.0), torch.tensor(3.0), torch.tensor(2.0)]
+    for order in (1, 2, 3):
+        for px0 in (0, 1):
+            got = SO.dpm_pp_update(x, ms, ts, torch.tensor(1.2), order, predict_x0=bool(px0)).numpy()
+            assert np.abs(got - d[f'upd/dpmpp/{order}/{px0}']).max() < 2e-6
+
+
+def test_gits_dp_and_deviation_bit_exact(gold):
+    d, meta = gold
+    cm = d['gits/cost']
+    for key, ref in meta['gits/dp'].items():
+        ns, coeff = key.split('/')
+        assert SO.dp(cm, int(ns), cm.shape[0], float(coeff)) == ref, key
+    traj = torch.from_numpy(d['gits/traj'])
+    dev = SO.cal_deviation(traj, 3, 8, bs=3).numpy()
+    assert np.abs(dev - d['gits/dev']).max() <= 1e-5 * np.abs(d['gits/dev']).max()
