@@ -45,6 +45,10 @@ struct ds_unet {
     std::vector<std::vector<unsigned char>> gemm_params;   // prebuilt kernel params per op (empty for non-GEMM)
     std::vector<IoFix> fixes;
     int last_launches = 0;
+    // optional per-op timing (bench/profiling only): one event pair per op, read back on demand
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev0, ev1;
+    std::vector<char> ev_used;
 };
 
 template <class F>
@@ -189,6 +193,8 @@ int ds_unet_create(const ds_weights* w, const void* plan_ops, int n_ops, size_t 
 
 void ds_unet_destroy(ds_unet* u) {
     if (!u) return;
+    for (auto e : u->ev0) cudaEventDestroy(e);
+    for (auto e : u->ev1) cudaEventDestroy(e);
     cudaFree(u->arena);
     delete u;
 }
@@ -214,7 +220,9 @@ int ds_unet_forward(ds_unet* u, const float* x, const float* sigma, const float*
             kp = al;
         }
         if (op.type == DS_OP_CHANMEAN && op.u.chanmean.out == nullptr) continue;   // bottleneck tap not requested
+        if (u->profiling) { cudaEventRecord(u->ev0[i], s); u->ev_used[i] = 1; }
         int rc = launch_op(op, kp, s);
+        if (u->profiling) cudaEventRecord(u->ev1[i], s);
         if (rc) {
             char buf[160];
             snprintf(buf, sizeof buf, "ds_unet_forward: op %zu (type %d tag %d) failed rc=%d cuda=%s", i, op.type, op.tag, rc,
@@ -237,6 +245,34 @@ int ds_unet_debug_read(ds_unet* u, size_t arena_offset, void* host_dst, size_t b
 }
 
 int ds_unet_last_launch_count(const ds_unet* u) { return u ? u->last_launches : 0; }
+
+int ds_unet_set_profiling(ds_unet* u, int enable) {
+    if (!u) return fail(-1, "ds_unet_set_profiling: null handle");
+    if (enable && u->ev0.empty()) {
+        u->ev0.resize(u->ops.size());
+        u->ev1.resize(u->ops.size());
+        u->ev_used.assign(u->ops.size(), 0);
+        for (size_t i = 0; i < u->ops.size(); ++i) {
+            cudaEventCreate(&u->ev0[i]);
+            cudaEventCreate(&u->ev1[i]);
+        }
+    }
+    u->profiling = enable != 0;
+    return 0;
+}
+
+int ds_unet_get_profile(ds_unet* u, float* ms_per_op, int n) {
+    if (!u || u->ev0.empty()) return fail(-1, "ds_unet_get_profile: profiling was not enabled");
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail(-2, "ds_unet_get_profile: sync failed");
+    for (int i = 0; i < n && i < (int)u->ops.size(); ++i) {
+        float ms = 0.f;
+        if (u->ev_used[i]) cudaEventElapsedTime(&ms, u->ev0[i], u->ev1[i]);
+        ms_per_op[i] = ms;
+    }
+    return (int)u->ops.size();
+}
+
+int ds_unet_op_type(const ds_unet* u, int i) { return (u && i >= 0 && i < (int)u->ops.size()) ? u->ops[i].type : -1; }
 
 int ds_solver_update(float* out_x, float* out_m, const float* xb, const float* xs, const float* D, const float* const* hist, int nhist,
                      const float* thr, int mode, float t, const float* t_dev, const float* coef6, const float* coef_dev,

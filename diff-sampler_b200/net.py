@@ -102,6 +102,26 @@ class B200Net:
         self.total_launches += self.launches_last_forward
         return out
 
+    def profile_forward(self, x, sigma, class_labels=None):
+        """One forward with per-op CUDA-event timing.  Returns {op_type: (count, total_ms)} (bench.py roofline leg)."""
+        B = x.shape[0]
+        self(x, sigma, class_labels)                                     # make sure the plan exists / warm
+        sig = torch.as_tensor(sigma).reshape(-1)
+        nsig = sig.numel() if sig.numel() == B and B > 1 else 1
+        nlab = 0 if not self.label_dim else (1 if class_labels is None else class_labels.reshape(-1, self.label_dim).shape[0])
+        h, pl = self._plan(B, nsig, nlab)
+        _lib.check(self.lib.ds_unet_set_profiling(h, 1), 'ds_unet_set_profiling')
+        self(x, sigma, class_labels)
+        buf = (C.c_float * pl.n_ops)()
+        n = self.lib.ds_unet_get_profile(h, buf, pl.n_ops)
+        self.lib.ds_unet_set_profiling(h, 0)
+        out = {}
+        for i in range(n):
+            t = self.lib.ds_unet_op_type(h, i)
+            c, ms = out.get(t, (0, 0.0))
+            out[t] = (c + 1, ms + buf[i])
+        return out
+
     def round_sigma(self, sigma):
         return torch.as_tensor(sigma)
 

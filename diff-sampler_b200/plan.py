@@ -17,6 +17,11 @@ from . import gemm_desc as G
 ALIGN = 1024
 
 
+def _groups(c):
+    """GroupNorm group count of the reference: min(32, C // 4)  (networks_edm.py:91)."""
+    return min(32, c // 4)
+
+
 def _align(n, a=ALIGN):
     return (n + a - 1) // a * a
 
@@ -235,7 +240,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
         resample = 1 if b.down else (2 if b.up else 0)
         Mo = B * Ho * Ho
         s0 = stats_slot()
-        emit(lambda R: S.GnStatsDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, HW=Hi * Hi, B=B, groups=32, sums=R('stats', s0)))
+        emit(lambda R: S.GnStatsDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, HW=Hi * Hi, B=B, groups=_groups(cin), sums=R('stats', s0)))
         A.need('act', npl * Mo * max(cin, cout) * H2)
         want_raw = b.skip == 'conv'
         want_rawf = b.skip == 'resample'
@@ -243,7 +248,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
             A.need('raw', npl * Mo * cin * H2)
         if want_rawf:
             A.need('rawf', Mo * cin * F4)
-        emit(lambda R: S.GnApplyDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, H=Hi, W=Hi, B=B, groups=32, sums=R('stats', s0),
+        emit(lambda R: S.GnApplyDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, H=Hi, W=Hi, B=B, groups=_groups(cin), sums=R('stats', s0),
                                      gamma=W(n + '.norm0:g'), beta=W(n + '.norm0:b'), eps=b.eps, silu=1, ada=0, ada_stride=0,
                                      resample=resample, nplanes=npl, out_act=R('act'), out_raw=R('raw') if want_raw else 0,
                                      out_raw_f32=R('rawf') if want_rawf else 0))
@@ -252,8 +257,8 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
                                    bias=W(n + '.conv0:b'), rowvec=0 if b.adaptive_scale else R('aff', b.aff_off * F4),
                                    rowvec_stride=aff_stride)[0])
         s1 = stats_slot()
-        emit(lambda R: S.GnStatsDesc(src0=R('y'), src1=0, C0=cout, C1=0, HW=Ho * Ho, B=B, groups=32, sums=R('stats', s1)))
-        emit(lambda R: S.GnApplyDesc(src0=R('y'), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=32, sums=R('stats', s1),
+        emit(lambda R: S.GnStatsDesc(src0=R('y'), src1=0, C0=cout, C1=0, HW=Ho * Ho, B=B, groups=_groups(cout), sums=R('stats', s1)))
+        emit(lambda R: S.GnApplyDesc(src0=R('y'), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), sums=R('stats', s1),
                                      gamma=W(n + '.norm1:g'), beta=W(n + '.norm1:b'), eps=b.eps, silu=1,
                                      ada=R('aff', b.aff_off * F4) if b.adaptive_scale else 0,
                                      ada_stride=aff_stride if b.adaptive_scale else 0, resample=0, nplanes=npl, out_act=R('act'),
@@ -275,8 +280,8 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
             d = cout // nh
             L = Ho * Ho
             s2 = stats_slot()
-            emit(lambda R: S.GnStatsDesc(src0=R(mid), src1=0, C0=cout, C1=0, HW=L, B=B, groups=32, sums=R('stats', s2)))
-            emit(lambda R: S.GnApplyDesc(src0=R(mid), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=32, sums=R('stats', s2),
+            emit(lambda R: S.GnStatsDesc(src0=R(mid), src1=0, C0=cout, C1=0, HW=L, B=B, groups=_groups(cout), sums=R('stats', s2)))
+            emit(lambda R: S.GnApplyDesc(src0=R(mid), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), sums=R('stats', s2),
                                          gamma=W(n + '.norm2:g'), beta=W(n + '.norm2:b'), eps=b.eps, silu=0, ada=0, ada_stride=0,
                                          resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))
             A.need('qk', npl * B * L * 2 * cout * H2)
@@ -322,8 +327,8 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
     sh = stats_slot()
     A.need('act', npl * B * HW0 * cur_c * H2)
     fin, fin_c = cur, cur_c
-    emit(lambda R: S.GnStatsDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, HW=HW0, B=B, groups=32, sums=R('stats', sh)))
-    emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=32, sums=R('stats', sh),
+    emit(lambda R: S.GnStatsDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, HW=HW0, B=B, groups=_groups(fin_c), sums=R('stats', sh)))
+    emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=_groups(fin_c), sums=R('stats', sh),
                                  gamma=W(spec.head_norm + ':g'), beta=W(spec.head_norm + ':b'), eps=spec.head_eps, silu=1, ada=0,
                                  ada_stride=0, resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))
     emit(lambda R: G.conv_gemm(R('act'), B, R0, R0, fin_c, W(spec.head_conv + ':w'), spec.img_channels, taps=9, npass=npass,

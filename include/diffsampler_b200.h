@@ -58,6 +58,12 @@ int ds_unet_debug_read(ds_unet* u, size_t arena_offset, void* host_dst, size_t b
 /* Number of kernels launched by the last ds_unet_forward on this handle. */
 int ds_unet_last_launch_count(const ds_unet* u);
 
+/* Per-op device timing (bench.py's roofline leg): when enabled, every op of the next forwards is bracketed by CUDA events on
+ * the launch stream; ds_unet_get_profile synchronises and returns the last elapsed ms of each op (returns the op count). */
+int ds_unet_set_profiling(ds_unet* u, int enable);
+int ds_unet_get_profile(ds_unet* u, float* ms_per_op, int n);
+int ds_unet_op_type(const ds_unet* u, int i);
+
 /* ---- solver update: replaces the 4-12 elementwise ATen launches per step ------------------------
  * solvers.py:80-81 (Euler), :163-168 (Heun), :252-258 (DPM-2), :346-352 (iPNDM), :451-477 (iPNDM_v),
  * :576-585 (DEIS); solver_utils.py:102-163 (DPM-Solver++), :250-285 (UniPC); amed solver_utils.py:90-160.
