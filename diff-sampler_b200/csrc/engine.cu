@@ -315,6 +315,14 @@ size_t ds_sizeof(int which) {
     }
 }
 
+int ds_gits_cost(const float* traj, const float* eps, const float* t_steps, double* out, int N, int B, int64_t n_per_sample, void* stream) {
+    ds_gits_cost_desc d;
+    d.traj = traj; d.eps = eps; d.t = t_steps; d.out = out; d.N = N; d.B = B; d.n = n_per_sample;
+    int rc = ds_gits_cost_launch(&d, static_cast<cudaStream_t>(stream));
+    if (rc) return fail(rc, std::string("ds_gits_cost: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
 int ds_op_launch(int op_type, const void* desc, size_t desc_size, void* stream) {
     ds_plan_op op;
     memset(&op, 0, sizeof op);

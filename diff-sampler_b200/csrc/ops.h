@@ -207,6 +207,20 @@ typedef struct ds_threshold_desc {
     float floor_val;        // 1.0
 } ds_threshold_desc;
 
+// GITS cost-matrix reductions (gits-main/gits_utils.py:115-132): for every teacher pair i < j and sample b, with
+//   x_ij = traj[i] + (t[j] - t[i]) * eps[i]      (a single Euler jump i -> j)
+// accumulate  out[i][j][b] = { sum|x_ij - traj[j]|, sum (x_ij - traj[j])^2, sum (c - x_ij)^2, sum (c - x_ij)(c - b0) }
+// where b0 = traj[0], c = traj[N-1] (the chord used by cal_deviation, :237-255).  fp64 accumulators.
+typedef struct ds_gits_cost_desc {
+    const float* traj;      // [N][B][n]
+    const float* eps;       // [N-1][B][n]
+    const float* t;         // [N] device
+    double* out;            // [N][N][B][4]
+    int32_t N, B;
+    int64_t n;
+} ds_gits_cost_desc;
+
+int ds_gits_cost_launch(const ds_gits_cost_desc* d, cudaStream_t stream);
 int ds_update_launch(const ds_update_desc* d, cudaStream_t stream);
 int ds_threshold_launch(const ds_threshold_desc* d, cudaStream_t stream);
 int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream);

@@ -129,9 +129,68 @@ __global__ void __launch_bounds__(256) threshold_kernel(ds_threshold_desc d) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ GITS cost
+// grid (pairs, B); pair p -> (i, j), i < j.  One pass over 5 streams (traj[i], eps[i], traj[j], traj[0], traj[N-1]).
+__global__ void __launch_bounds__(256) gits_cost_kernel(ds_gits_cost_desc d) {
+    // decode the pair index
+    int p = blockIdx.x, i = 0;
+    while (p >= d.N - 1 - i) { p -= d.N - 1 - i; ++i; }
+    const int j = i + 1 + p;
+    const int b = blockIdx.y;
+    const float h = d.t[j] - d.t[i];
+    const long long n4 = d.n / 4;
+    const long long stride = (long long)d.B * d.n;
+    const float4* xi = reinterpret_cast<const float4*>(d.traj + (long long)i * stride + (long long)b * d.n);
+    const float4* di = reinterpret_cast<const float4*>(d.eps + (long long)i * stride + (long long)b * d.n);
+    const float4* xj = reinterpret_cast<const float4*>(d.traj + (long long)j * stride + (long long)b * d.n);
+    const float4* x0 = reinterpret_cast<const float4*>(d.traj + (long long)b * d.n);
+    const float4* xc = reinterpret_cast<const float4*>(d.traj + (long long)(d.N - 1) * stride + (long long)b * d.n);
+    double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+    for (long long k = threadIdx.x; k < n4; k += blockDim.x) {
+        const float4 a = xi[k], dd = di[k], r = xj[k], b0 = x0[k], c = xc[k];
+        const float xs[4] = {a.x + h * dd.x, a.y + h * dd.y, a.z + h * dd.z, a.w + h * dd.w};
+        const float rr[4] = {r.x, r.y, r.z, r.w};
+        const float bb[4] = {b0.x, b0.y, b0.z, b0.w};
+        const float cc[4] = {c.x, c.y, c.z, c.w};
+        float l1 = 0.f, l2 = 0.f, q1 = 0.f, q2 = 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const float e = xs[m] - rr[m];
+            l1 += fabsf(e);
+            l2 += e * e;
+            const float ca = cc[m] - xs[m];
+            q1 += ca * ca;
+            q2 += ca * (cc[m] - bb[m]);
+        }
+        s1 += l1; s2 += l2; s3 += q1; s4 += q2;
+    }
+    __shared__ double red[4][8];
+    double v[4] = {s1, s2, s3, s4};
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[m] += __shfl_xor_sync(0xffffffffu, v[m], o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = v[0]; red[1][warp] = v[1]; red[2][warp] = v[2]; red[3][warp] = v[3]; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double acc = 0;
+        for (int w = 0; w < 8; ++w) acc += red[threadIdx.x][w];
+        d.out[(((long long)i * d.N + j) * d.B + b) * 4 + threadIdx.x] = acc;
+    }
+}
+
 }  // namespace dsb
 
 using namespace dsb;
+
+extern "C" int ds_gits_cost_launch(const ds_gits_cost_desc* d, cudaStream_t stream) {
+    if (d->n % 4 || d->N < 2) return -2;
+    const int pairs = d->N * (d->N - 1) / 2;
+    gits_cost_kernel<<<dim3(pairs, d->B), 256, 0, stream>>>(*d);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 
 extern "C" int ds_update_launch(const ds_update_desc* dp, cudaStream_t stream) {
     const ds_update_desc& d = *dp;

@@ -61,6 +61,9 @@ def expand_dims(v, dims):
 # ---------------------------------------------------------------------------------------------------------------------
 # kernel front-ends
 
+LAUNCHES = [0]      # kernels launched through this module (bench.py's gpu_launches)
+
+
 def _ptr(t):
     return None if t is None else t.data_ptr()
 
@@ -89,6 +92,7 @@ def solver_update(out_x, xb, coef, *, mode=S.DS_M_NONE, D=None, xs=None, hist=()
     rc = lib.ds_solver_update(_ptr(out_x), _ptr(out_m), _ptr(xb), _ptr(xs), _ptr(D), hp, len(hist), _ptr(thr), int(mode), float(t),
                               _ptr(t_dev), cf, _ptr(coef_dev), n, B, _stream(xb))
     _lib.check(rc, 'ds_solver_update')
+    LAUNCHES[0] += 1
     return out_x
 
 
@@ -101,6 +105,7 @@ def dyn_threshold(x0, q=0.995, floor=1.0, out=None):
         out = torch.empty(B, device=x0.device, dtype=torch.float32)
     _lib.check(lib.ds_dyn_threshold(x0.data_ptr(), out.data_ptr(), B, x0[0].numel(), float(q), float(floor), _stream(x0)),
                'ds_dyn_threshold')
+    LAUNCHES[0] += 1
     return out
 
 

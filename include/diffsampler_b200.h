@@ -78,6 +78,12 @@ int ds_solver_update(float* out_x, float* out_m, const float* xb, const float* x
  * solver_utils.py:77-86.  thr[b] = max(quantile_linear(|x0[b]|, q), floor_val).  Exact selection. */
 int ds_dyn_threshold(const float* x0, float* thr, int B, int row_len, float q, float floor_val, void* stream);
 
+/* ---- GITS cost matrix: replaces the O(N_tea^2) loop of tiny reductions --------------------------------
+ * gits-main/gits_utils.py:115-132 (+ cal_deviation :237-255).  For every teacher pair i < j and sample b:
+ *   x_ij = traj[i] + (t[j]-t[i])*eps[i];  out[i][j][b] = { sum|x_ij-traj[j]|, sum(x_ij-traj[j])^2, sum(c-x_ij)^2, sum(c-x_ij)(c-b0) }
+ * with b0 = traj[0], c = traj[N-1].  traj [N][B][n], eps [N-1][B][n] fp32; out [N][N][B][4] fp64 (entries i >= j untouched). */
+int ds_gits_cost(const float* traj, const float* eps, const float* t_steps, double* out, int N, int B, int64_t n_per_sample, void* stream);
+
 /* ---- kernel-level entry points (used by the parity tests and micro-benchmarks) ------------------
  * `desc` points to the matching struct of csrc/ops.h with absolute device pointers. */
 int ds_op_launch(int op_type, const void* desc, size_t desc_size, void* stream);

@@ -130,3 +130,32 @@ def test_gits_dp_and_deviation_bit_exact(gold):
     traj = torch.from_numpy(d['gits/traj'])
     dev = SO.cal_deviation(traj, 3, 8, bs=3).numpy()
     assert np.abs(dev - d['gits/dev']).max() <= 1e-5 * np.abs(d['gits/dev']).max()
+
+
+AMED_CASES = [
+    ('amed', dict(num_steps=4), dict(scale_dir=0.01, scale_time=0.2)),
+    ('euler', dict(num_steps=4, afs=True), dict(scale_dir=0.01, scale_time=0.2)),
+    ('ipndm', dict(num_steps=5, max_order=3), dict(scale_dir=0.01, scale_time=0.2)),
+    ('dpm_2', dict(num_steps=4), dict(scale_dir=0.0, scale_time=0.2)),
+    ('dpm_pp', dict(num_steps=4, max_order=2, predict_x0=False, afs=True), dict(scale_dir=0.01, scale_time=0.2)),
+    ('dpm_pp', dict(num_steps=5, max_order=3, predict_x0=True), dict(scale_dir=0.05, scale_time=0.0)),
+]
+
+
+def load_amed_case(ci):
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_amed.npz'))
+    W = {k[len(f'amed/{ci}/pred/'):]: torch.from_numpy(d[k]) for k in d.files if k.startswith(f'amed/{ci}/pred/')}
+    return W, d[f'amed/{ci}/out']
+
+
+@pytest.mark.parametrize('ci', range(len(AMED_CASES)))
+def test_amed_samplers_match_reference(ci):
+    from oracle import amed_oracle as AO
+    solver, kw, cfg = AMED_CASES[ci]
+    W, ref = load_amed_case(ci)
+    P, S = O.make_net('tiny_song4', seed=0, dezero=True)
+    net = O.OracleNet(P, S)
+    lat = O.stacked_randn(range(3), (3, 16, 16))
+    got = AO.sample_amed(net, lat, solver, W, cfg, **kw).numpy()
+    err = np.abs(got - ref).max()
+    assert err <= 2e-5 * max(1.0, np.abs(ref).max()), (solver, kw, err)
