@@ -107,7 +107,10 @@ def cpu_reference_leg(args, steps, warmup):
     import torch
     from oracle import edm_oracle as O
     from oracle import solvers_oracle as SO
-    cores = os.cpu_count() or 1
+    # thread count: measured on the B200 host (profiles/cpu_thread_sweep.py, 128 logical CPUs): one CIFAR-net forward at batch 8
+    # takes 0.21 s with 16 threads, 0.27 s with 32, 0.59 s with 64 and 4.6 s with 128 (oversubscription), so the baseline uses
+    # the fastest setting rather than every logical CPU.
+    cores = min(os.cpu_count() or 1, int(os.environ.get('DSB_CPU_THREADS', '16')))
     torch.set_num_threads(cores)
     P, S = O.make_net(args.net, seed=0, dezero=True)
     net = O.OracleNet(P, S)

@@ -62,101 +62,112 @@ __global__ void gn_stats_kernel(ds_gn_stats_desc d, int pix_per_cta) {
 }
 
 // ------------------------------------------------------------------------------------------ GN apply
-// grid (chunks, B), block 256. smem: mean[C], a[C] (= rstd*gamma*(1+ada_scale)), b[C] (= beta*(1+ada_scale)+ada_shift)
-__global__ void gn_apply_kernel(ds_gn_apply_desc d, int items_per_cta) {
-    extern __shared__ float sm[];
+// grid (chunks, B); block = nc8 * rows threads.  Thread (c8, prow) owns 8 fixed channels: its normalisation coefficients
+// live in registers (mean, a = rstd*gamma*(1+ada_scale), b = beta*(1+ada_scale)+ada_shift) and it streams over output pixels.
+__device__ __forceinline__ void gn_store_planes(__half* base, long long plane, long long o, const float* v, int nplanes) {
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_h16(v[j], hi[j], lo[j]);
+    *reinterpret_cast<uint4*>(base + o) = *reinterpret_cast<const uint4*>(hi);
+    if (nplanes > 1) *reinterpret_cast<uint4*>(base + plane + o) = *reinterpret_cast<const uint4*>(lo);
+}
+
+template <int RESAMPLE>
+__global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int pix_per_cta, int nc8, int rows) {
     const int C = d.C0 + d.C1;
-    float* s_mean = sm;
-    float* s_a = sm + C;
-    float* s_b = sm + 2 * C;
     const int n = blockIdx.y;
+    const int c8 = threadIdx.x % nc8;
+    const int prow = threadIdx.x / nc8;
+    const int c = c8 * 8;
     const bool norm = d.sums != nullptr;
+    float mean[8], a[8], b[8];
     if (norm) {
         const int cpg = C / d.groups;
         const double cnt = (double)cpg * d.H * d.W;
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const int g = c / cpg;
-            const double s = d.sums[((long long)n * d.groups + g) * 2 + 0];
-            const double q = d.sums[((long long)n * d.groups + g) * 2 + 1];
-            const double mean = s / cnt;
-            double var = q / cnt - mean * mean;
-            if (var < 0.0) var = 0.0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)d.eps));
-            float a = rstd * d.gamma[c];
-            float b = d.beta[c];
-            if (d.ada) {
-                const float sc = d.ada[(long long)n * d.ada_stride + c] + 1.0f;
-                const float sh = d.ada[(long long)n * d.ada_stride + C + c];
-                a *= sc;
-                b = b * sc + sh;
+        int g_prev = -1;
+        float mu_f = 0.f, rstd = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c + j) / cpg;
+            if (g != g_prev) {                 // at most a few distinct groups per 8 channels
+                const double s = d.sums[((long long)n * d.groups + g) * 2 + 0];
+                const double q = d.sums[((long long)n * d.groups + g) * 2 + 1];
+                const double mu = s / cnt;
+                double var = q / cnt - mu * mu;
+                if (var < 0.0) var = 0.0;
+                rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+                mu_f = (float)mu;
+                g_prev = g;
             }
-            s_mean[c] = (float)mean;
-            s_a[c] = a;
-            s_b[c] = b;
+            float aa = rstd * __ldg(d.gamma + c + j);
+            float bb = __ldg(d.beta + c + j);
+            if (d.ada) {
+                const float sc = d.ada[(long long)n * d.ada_stride + c + j] + 1.0f;
+                const float sh = d.ada[(long long)n * d.ada_stride + C + c + j];
+                aa *= sc;
+                bb = bb * sc + sh;
+            }
+            mean[j] = mu_f; a[j] = aa; b[j] = bb;
         }
     }
-    __syncthreads();
-
-    const int Ho = d.resample == 1 ? d.H / 2 : (d.resample == 2 ? d.H * 2 : d.H);
-    const int Wo = d.resample == 1 ? d.W / 2 : (d.resample == 2 ? d.W * 2 : d.W);
-    const int nc8 = C / 8;
-    const long long items = (long long)Ho * Wo * nc8;
-    const long long plane = (long long)d.B * Ho * Wo * C;
-    long long i_begin = (long long)blockIdx.x * items_per_cta;
-    long long i_end = i_begin + items_per_cta;
-    if (i_end > items) i_end = items;
+    const int Ho = RESAMPLE == 1 ? d.H / 2 : (RESAMPLE == 2 ? d.H * 2 : d.H);
+    const int Wo = RESAMPLE == 1 ? d.W / 2 : (RESAMPLE == 2 ? d.W * 2 : d.W);
+    const int npix = Ho * Wo;
+    const long long plane = (long long)d.B * npix * C;
+    const float* base;
+    int pitch, cc;
+    if (c < d.C0) { base = d.src0; pitch = d.C0; cc = c; }
+    else { base = d.src1; pitch = d.C1; cc = c - d.C0; }
+    base += (long long)n * d.H * d.W * pitch + cc;
     __half* oact = reinterpret_cast<__half*>(d.out_act);
     __half* oraw = reinterpret_cast<__half*>(d.out_raw);
-    for (long long it = i_begin + threadIdx.x; it < i_end; it += blockDim.x) {
-        const int c8 = (int)(it % nc8);
-        const int po = (int)(it / nc8);
+    const int p_begin = blockIdx.x * pix_per_cta;
+    int p_end = p_begin + pix_per_cta;
+    if (p_end > npix) p_end = npix;
+    for (int po = p_begin + prow; po < p_end; po += rows) {
         const int ho = po / Wo, wo = po - ho * Wo;
-        const int c = c8 * 8;
-        const float* base;
-        int pitch, cc;
-        if (c < d.C0) { base = d.src0; pitch = d.C0; cc = c; }
-        else { base = d.src1; pitch = d.C1; cc = c - d.C0; }
         float act[8], raw[8];
+        if (RESAMPLE == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { act[j] = 0.f; raw[j] = 0.f; }
-        const int ntap = d.resample == 1 ? 4 : 1;
-        for (int t = 0; t < ntap; ++t) {
-            int hi, wi;
-            if (d.resample == 1) { hi = ho * 2 + (t >> 1); wi = wo * 2 + (t & 1); }
-            else if (d.resample == 2) { hi = ho >> 1; wi = wo >> 1; }
-            else { hi = ho; wi = wo; }
-            const float* src = base + (((long long)n * d.H + hi) * d.W + wi) * pitch + cc;
-            const float4 v0 = *reinterpret_cast<const float4*>(src);
-            const float4 v1 = *reinterpret_cast<const float4*>(src + 4);
-            const float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            const float wgt = d.resample == 1 ? 0.25f : 1.0f;
+            for (int j = 0; j < 8; ++j) { act[j] = 0.f; raw[j] = 0.f; }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                raw[j] += wgt * e[j];
-                if (norm) {
-                    float y = (e[j] - s_mean[c + j]) * s_a[c + j] + s_b[c + j];
-                    if (d.silu) y = silu_f(y);
-                    act[j] += wgt * y;
+            for (int t = 0; t < 4; ++t) {
+                const float* src = base + (long long)((ho * 2 + (t >> 1)) * d.W + wo * 2 + (t & 1)) * pitch;
+                const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src));
+                const float4 v1 = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+                const float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    raw[j] += 0.25f * e[j];
+                    if (norm) {
+                        float y = (e[j] - mean[j]) * a[j] + b[j];
+                        if (d.silu) y = silu_f(y);
+                        act[j] += 0.25f * y;
+                    }
                 }
             }
-        }
-        const long long o = (((long long)n * Ho + ho) * Wo + wo) * C + c;
-        if (oact) {
-            __align__(16) __half hi[8];
-            __align__(16) __half lo[8];
+        } else {
+            const int hi_ = RESAMPLE == 2 ? (ho >> 1) : ho;
+            const int wi_ = RESAMPLE == 2 ? (wo >> 1) : wo;
+            const float* src = base + (long long)(hi_ * d.W + wi_) * pitch;
+            const float4 v0 = __ldcs(reinterpret_cast<const float4*>(src));
+            const float4 v1 = __ldcs(reinterpret_cast<const float4*>(src) + 1);
+            const float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) split_h16(act[j], hi[j], lo[j]);
-            *reinterpret_cast<uint4*>(oact + o) = *reinterpret_cast<const uint4*>(hi);
-            if (d.nplanes > 1) *reinterpret_cast<uint4*>(oact + plane + o) = *reinterpret_cast<const uint4*>(lo);
+            for (int j = 0; j < 8; ++j) {
+                raw[j] = e[j];
+                float y = 0.f;
+                if (norm) {
+                    y = (e[j] - mean[j]) * a[j] + b[j];
+                    if (d.silu) y = silu_f(y);
+                }
+                act[j] = y;
+            }
         }
-        if (oraw) {
-            __align__(16) __half hi[8];
-            __align__(16) __half lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) split_h16(raw[j], hi[j], lo[j]);
-            *reinterpret_cast<uint4*>(oraw + o) = *reinterpret_cast<const uint4*>(hi);
-            if (d.nplanes > 1) *reinterpret_cast<uint4*>(oraw + plane + o) = *reinterpret_cast<const uint4*>(lo);
-        }
+        const long long o = ((long long)n * npix + po) * C + c;
+        if (oact) gn_store_planes(oact, plane, o, act, d.nplanes);
+        if (oraw) gn_store_planes(oraw, plane, o, raw, d.nplanes);
         if (d.out_raw_f32) {
             *reinterpret_cast<float4*>(d.out_raw_f32 + o) = make_float4(raw[0], raw[1], raw[2], raw[3]);
             *reinterpret_cast<float4*>(d.out_raw_f32 + o + 4) = make_float4(raw[4], raw[5], raw[6], raw[7]);
@@ -317,13 +328,22 @@ extern "C" int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream
 extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream) {
     const int C = d->C0 + d->C1;
     if (C % 8 || (d->C0 % 8)) return -2;
+    const int nc8 = C / 8;
+    if (nc8 > 512) return -2;
+    int rows = 256 / nc8;
+    if (rows < 1) rows = 1;
+    const int threads = nc8 * rows;
     const int Ho = d->resample == 1 ? d->H / 2 : (d->resample == 2 ? d->H * 2 : d->H);
     const int Wo = d->resample == 1 ? d->W / 2 : (d->resample == 2 ? d->W * 2 : d->W);
-    const long long items = (long long)Ho * Wo * (C / 8);
-    const int items_per_cta = 256 * 8;
-    const int chunks = (int)((items + items_per_cta - 1) / items_per_cta);
-    const size_t smem = (size_t)3 * C * sizeof(float);
-    gn_apply_kernel<<<dim3(chunks, d->B), 256, smem, stream>>>(*d, items_per_cta);
+    const int npix = Ho * Wo;
+    // ~16 pixels per thread amortise the per-thread coefficient set-up; keep at least ~4 CTAs per SM in flight overall
+    int pix_per_cta = rows * 16;
+    while (pix_per_cta > rows && (long long)((npix + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
+    const int chunks = (npix + pix_per_cta - 1) / pix_per_cta;
+    dim3 grid(chunks, d->B);
+    if (d->resample == 1) gn_apply_kernel<1><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
+    else if (d->resample == 2) gn_apply_kernel<2><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
+    else gn_apply_kernel<0><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
     return ok();
 }
 

@@ -8,12 +8,15 @@ H16 = 2  # bytes per fp16
 
 
 def pick_bn(n):
-    """N tile: the largest UMMA N (<=256, multiple of 16) among the tilings with the least padding."""
+    """N tile (UMMA N, multiple of 16, <= 256): narrow outputs get the smallest covering tile; otherwise the widest of
+    {256, 192, 128, 64} among the tilings with the least padding (wide tiles halve the per-MMA shared-memory traffic)."""
+    for bn in (16, 32, 64):
+        if n <= bn:
+            return bn, 1
     best = None
-    for bn in (256, 192, 128, 64, 32, 16):
+    for bn in (256, 192, 128, 64):
         tiles = -(-n // bn)
-        waste = tiles * bn - n
-        key = (waste, -bn)
+        key = (tiles * bn - n, -bn)
         if best is None or key < best[0]:
             best = (key, bn, tiles)
     return best[1], best[2]

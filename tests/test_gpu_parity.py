@@ -184,3 +184,109 @@ def test_trajectory_and_eps_outputs():
         e1, e2 = (gt.cpu() - rt).abs().max().item(), (ge.cpu() - re).abs().max().item()
         print(f'{solver}: traj err {e1:.3e} eps err {e2:.3e}')
         assert e1 < TOL and e2 < TOL
+
+
+# --------------------------------------------------------------------------------------------- AMED / GITS
+AMED_CASES = [
+    ('amed', 'amed_sampler', dict(num_steps=4), dict(scale_dir=0.01, scale_time=0.2)),
+    ('euler', 'euler_sampler', dict(num_steps=4, afs=True), dict(scale_dir=0.01, scale_time=0.2)),
+    ('ipndm', 'ipndm_sampler', dict(num_steps=5, max_order=3), dict(scale_dir=0.01, scale_time=0.2)),
+    ('dpm_2', 'dpm_2_sampler', dict(num_steps=4), dict(scale_dir=0.0, scale_time=0.2)),
+    ('dpm_pp', 'dpm_pp_sampler', dict(num_steps=4, max_order=2, predict_x0=False, afs=True), dict(scale_dir=0.01, scale_time=0.2)),
+    ('dpm_pp', 'dpm_pp_sampler', dict(num_steps=5, max_order=3, predict_x0=True), dict(scale_dir=0.05, scale_time=0.0)),
+]
+
+
+@pytest.mark.parametrize('ci', range(len(AMED_CASES)))
+def test_amed_sampler_parity(ci):
+    """AMED plug-in samplers (per-sample r / scale_dir / scale_time, second evaluation at per-sample sigma) vs the oracle and
+    vs the REAL reference's recorded output (tests/golden/ref_amed.npz)."""
+    import os
+    import numpy as np
+    from oracle import amed_oracle as AO
+    from oracle import edm_oracle as O
+    from diff_sampler_b200 import solvers_amed
+    from diff_sampler_b200.amed_predictor import AMEDPredictor
+    osolver, fn, kw, cfg = AMED_CASES[ci]
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_amed.npz'))
+    W = {k[len(f'amed/{ci}/pred/'):]: torch.from_numpy(d[k]) for k in d.files if k.startswith(f'amed/{ci}/pred/')}
+    on, P, S = _oracle('tiny_song4')
+    nat = _native(P, S)
+    lat = O.stacked_randn(range(3), (3, 16, 16))
+    ref = AO.sample_amed(on, lat, osolver, W, cfg, **kw)
+    pred = AMEDPredictor(W, **cfg).to(_dev())
+    got = getattr(solvers_amed, fn)(nat, lat.to(_dev()), AMED_predictor=pred, **kw).cpu()
+    e_or = (got - ref).abs().max().item()
+    e_ref = (got - torch.from_numpy(d[f'amed/{ci}/out'])).abs().max().item()
+    print(f'AMED {fn} {kw}: vs oracle {e_or:.3e}, vs recorded reference {e_ref:.3e}')
+    assert e_or < TOL and e_ref < TOL
+
+
+@pytest.mark.parametrize('metric', ['l1', 'l2', 'dev'])
+def test_gits_cost_matrix_and_dp(metric):
+    """One-kernel cost matrix (ds_gits_cost) vs the oracle's pairwise loop; the DP on it returns the same index list."""
+    from oracle import edm_oracle as O
+    from oracle import solvers_oracle as SO
+    from diff_sampler_b200 import gits_utils
+    on, P, S = _oracle('tiny_song')
+    lat = O.stacked_randn(range(4), (3, 16, 16))
+    N = 13
+    ts = SO.get_schedule(N, 0.002, 80)
+    traj, eps = SO.sample(on, lat, 'euler', t_steps=ts, num_steps=N, return_inters=True, return_eps=True)
+    ref = SO.gits_cost_matrix(traj, eps, ts, metric, 3, 16)
+    got = gits_utils.cost_matrix(traj.to(_dev()), eps.to(_dev()), ts.to(_dev()), metric, 3, 16).cpu()
+    err = (got - ref).abs().max().item()
+    print(f'gits cost {metric}: max err {err:.3e} (max {ref.abs().max().item():.3f})')
+    assert err <= 2e-4 * ref.abs().max().item()
+    for ns, coeff in ((5, 1.0), (7, 1.15)):
+        assert gits_utils.dp(got.numpy(), ns, N, coeff) == SO.dp(ref.numpy(), ns, N, coeff)
+
+
+def test_gits_get_dp_list_end_to_end():
+    from diff_sampler_b200 import gits_utils, solver_utils, solvers
+    _, P, S = _oracle('tiny_song')
+    nat = _native(P, S)
+    kw = dict(dataset_name='cifar10', num_warmup=8, max_batch_size=8, sigma_min=0.002, sigma_max=80, num_steps=5, num_steps_tea=11,
+              schedule_type='polynomial', schedule_rho=7, afs=False, metric='dev', coeff=1.15, model_source='edm', solver='dpmpp',
+              solver_tea='euler', max_order=2, deis_mode='tab', prompt=None, guidance_rate=1.0)
+    torch.manual_seed(0)
+    dp_list = gits_utils.get_dp_list(nat, _dev(), **kw)
+    print('dp_list', dp_list)
+    assert dp_list[0] == 0 and dp_list[-1] == 10 and len(dp_list) == 5 and dp_list == sorted(set(dp_list))
+    t_steps = solver_utils.get_schedule(11, 0.002, 80, device=_dev(), dp_list=dp_list)
+    out = solvers.dpm_pp_sampler(nat, torch.randn(4, 3, 16, 16, device=_dev()), num_steps=5, max_order=2, t_steps=t_steps)
+    assert torch.isfinite(out).all()
+
+
+# --------------------------------------------------------------------------------------------- BASELINE-size properties
+def test_fullsize_batch_independence_and_properties():
+    """At the BASELINE size (CIFAR-10 net, batch 512) the oracle is too slow; check size-independent properties instead:
+    a sample's output does not depend on the batch it rides in, the update kernel is linear, thresholding is idempotent."""
+    from diff_sampler_b200 import solver_utils as U
+    from diff_sampler_b200 import _cstructs as S
+    from diff_sampler_b200.net import B200Net
+    net = B200Net.from_config('cifar10', seed=0, dezero=True, device=_dev())
+    g = torch.Generator(device=_dev()).manual_seed(7)
+    x = torch.randn(512, 3, 32, 32, generator=g, device=_dev()) * 5.0
+    sig = torch.tensor(5.0, device=_dev())
+    big = net(x, sig).clone()
+    small = net(x[100:104].contiguous(), sig)
+    e = (big[100:104] - small).abs().max().item()
+    print(f'batch-512 vs batch-4 rows: {e:.3e}')
+    assert e < 2e-5
+    assert torch.isfinite(big).all()
+    # update kernel linearity in (x, D, history) at full size
+    a, b_, h = (torch.randn(512, 3, 32, 32, generator=g, device=_dev()) for _ in range(3))
+    f = lambda X, D, H: U.solver_update(torch.empty_like(X), X, [0.7, -1.3, 0.4], mode=S.DS_M_EPS, D=D, t=3.0, hist=[H])
+    lhs = f(a + 2 * b_, b_ - a, h + a)
+    rhs = f(a, b_, h) + 2 * f(b_, -0.5 * a, 0.5 * a)
+    assert (lhs - rhs).abs().max().item() < 1e-4
+    # dynamic thresholding: s >= 1, |out| <= 1, idempotent, ~0.5% of the entries clipped when s > 1
+    x0 = b_ * 3.0
+    s = U.dyn_threshold(x0)
+    y = U.dynamic_thresholding_fn(x0)
+    assert (s >= 1).all() and y.abs().max().item() <= 1.0 + 1e-6
+    frac = ((x0.abs() > s[:, None, None, None]).float().mean().item())
+    assert abs(frac - 0.005) < 0.001
+    y2 = U.dynamic_thresholding_fn(y)
+    assert (y2 - y).abs().max().item() == 0.0

@@ -1,0 +1,144 @@
+"""Host-side logic of the product (CPU): plan lowering, weight packing, coefficient algebra, schedules, GITS dp —
+checked against the oracle / golden vectors without touching a GPU."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diff_sampler_b200 import _cstructs as S
+from diff_sampler_b200 import edm_nets, gemm_desc as G, gits_utils, plan as planner, solver_utils as U
+from oracle import edm_oracle as O
+from oracle import solvers_oracle as SO
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'ref_core.npz')
+
+
+def test_init_matches_reference_digest():
+    d = np.load(GOLD)
+    meta = json.loads(bytes(d['meta_json']).decode())
+    for name in ('tiny_song', 'tiny_adm', 'cifar10'):
+        params, cfg = edm_nets.init_params(name, seed=0)
+        assert O.params_digest(params) == meta[f'digest/{name}/0']
+        edm_nets.dezero_(params, cfg['kind'], seed=0)
+        assert O.params_digest(params) == meta[f'digest/{name}/1']
+
+
+@pytest.mark.parametrize('name,B', [('tiny_song', 3), ('tiny_adm', 5), ('cifar10', 8), ('ffhq', 2)])
+def test_plan_lowering_invariants(name, B):
+    params, cfg = edm_nets.init_params(name, seed=0)
+    spec = edm_nets.spec_from_params(params, cfg['img_resolution'], cfg['img_channels'], cfg.get('label_dim', 0))
+    assert spec.aff_total == sum(b.aff_width for b in spec.enc + spec.dec)
+    wb, info = planner.pack_weights(spec, params)
+    for nsig in (1, B):
+        pl = planner.compile_plan(spec, wb, info, B, nsig, B if spec.label_dim else 0, npass=3)
+        n_gemm = 0
+        for i in range(pl.n_ops):
+            op = pl.ops_array[i]
+            if op.type == S.DS_OP_GEMM:
+                g = op.u.gemm
+                n_gemm += 1
+                assert g.BN % 16 == 0 and 16 <= g.BN <= 256
+                assert g.a_box[0] == 64 and g.a_box[1] * g.a_box[2] * g.a_box[3] == 128
+                assert g.n_tiles * g.BN >= g.n_valid and g.m_tiles * 128 >= g.m_valid
+                assert (g.a_ptr >> 60) in (S.SPACE_ARENA, S.SPACE_WEIGHTS) and (g.b_ptr >> 60) in (S.SPACE_ARENA, S.SPACE_WEIGHTS)
+                assert all(s % 16 == 0 for s in g.a_strides) and all(s % 16 == 0 for s in g.b_strides)
+        assert n_gemm == pl.meta['n_gemm'] and pl.arena_bytes > 0
+    # every conv of the reference is lowered exactly once: stem + 2 per block + 4 extra per attention block (+1 head)
+    blocks = spec.enc + spec.dec
+    assert pl.meta['n_gemm'] == 1 + 2 * len(blocks) + 5 * sum(1 for b in blocks if b.heads) + 1
+
+
+def test_spec_matches_oracle_structure():
+    for name in ('tiny_song', 'tiny_adm', 'cifar10', 'imagenet64'):
+        P, St = O.make_net(name, seed=0) if name != 'imagenet64' else (None, None)
+        if P is None:
+            continue
+        spec = edm_nets.spec_from_params(P, St['img_resolution'], St['img_channels'], St['label_dim'])
+        for b in spec.enc + spec.dec:
+            ob = St['blocks'][b.name]
+            assert (b.cin, b.cout, b.up, b.down, b.heads) == (ob['cin'], ob['cout'], ob['up'], ob['down'], ob['heads'])
+            assert {None: 'identity', 1: 'conv', 0: 'resample'}[ob['skip_kernel']] == b.skip
+            assert abs(b.skip_scale - float(ob['skip_scale'])) < 1e-7 and b.eps == ob['eps']
+
+
+def test_weight_packing_roundtrip():
+    torch.manual_seed(0)
+    w = torch.randn(70, 40, 3, 3)
+    sk = torch.randn(70, 24, 1, 1)
+    p = G.pack_conv_weight(w, sk)
+    assert p.shape == (2, 128, 9 * 64 + 64) and p.dtype == torch.float16
+    full = p[0].float() + p[1].float()
+    ref = torch.zeros(70, 3, 3, 64)
+    ref[..., :40] = w.permute(0, 2, 3, 1)
+    assert (full[:70, :576] - ref.reshape(70, -1)).abs().max() < 1e-6
+    assert (full[:70, 576:600] - sk.reshape(70, 24)).abs().max() < 1e-6 and full[70:].abs().max() == 0
+    assert G.pick_bn(256) == (256, 1) and G.pick_bn(384) == (192, 2) and G.pick_bn(3) == (16, 1) and G.pick_bn(576) == (192, 3)
+    assert G.conv_box(32, 32) == (32, 4, 1) and G.conv_box(8, 8) == (8, 8, 2) and G.conv_box(64, 64) == (64, 2, 1)
+    # qkv de-interleave ([head][c][q|k|v] rows, networks_edm.py:174)
+    C_, nh = 8, 2
+    wq = torch.arange(3 * C_).float().reshape(3 * C_, 1)
+    bq = torch.arange(3 * C_).float()
+    wqk, bqk, wv, bv = planner._qkv_split(wq, bq, nh)
+    idx = torch.arange(3 * C_).reshape(nh, C_ // nh, 3)
+    assert torch.equal(bqk[:C_], idx[:, :, 0].reshape(-1).float()) and torch.equal(bqk[C_:], idx[:, :, 1].reshape(-1).float())
+    assert torch.equal(bv, idx[:, :, 2].reshape(-1).float())
+
+
+def test_schedules_and_deis_tables_match_reference_golden():
+    d = np.load(GOLD)
+    for st in ('polynomial', 'logsnr', 'time_uniform'):
+        for n in (4, 6, 7, 11, 18, 61):
+            assert np.array_equal(U.get_schedule(n, 0.002, 80, schedule_type=st, schedule_rho=7).float().numpy(), d[f'sched/{st}/{n}'])
+    ts = U.get_schedule(61, 0.002, 80)
+    assert torch.equal(U.get_schedule(61, 0.002, 80, dp_list=[0, 5, 17, 60]), ts[[0, 5, 17, 60]])          # GITS gather
+    for ci, (n, mo, mode) in {7: (7, 4, 'tab'), 8: (6, 4, 'rhoab')}.items():
+        C_ = U.get_deis_coeff_list(U.get_schedule(n, 0.002, 80), mo, deis_mode=mode)
+        for row, rr in zip(C_, d[f'deis/{ci}']):
+            assert np.allclose([float(torch.as_tensor(c).detach()) for c in row], rr[:len(row)], rtol=1e-6, atol=1e-9)
+    with pytest.raises(ValueError):
+        U.get_schedule(5, 0.002, 80, schedule_type='nope')
+
+
+def test_update_coefficients_reproduce_reference_formulas():
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 4, 4)
+    ms = [torch.randn(2, 3, 4, 4) for _ in range(3)]
+    ts = [torch.tensor(5.0), torch.tensor(3.0), torch.tensor(2.0)]
+    t = torch.tensor(1.2)
+    for order in (1, 2, 3):
+        for px0 in (True, False):
+            ref = SO.dpm_pp_update(x, ms, ts, t, order, predict_x0=px0, scale=0.9)
+            c = U.dpm_pp_coefs([float(v) for v in ts], float(t), order, px0, 0.9)
+            got = c[0] * x + c[1] * ms[-1] + c[2] * ms[-2] + c[3] * ms[-3]
+            assert (ref - got).abs().max() < 5e-6
+            for var in ('bh1', 'bh2'):
+                class N:
+                    def __call__(self, xt, tt, cl):
+                        self.xt = xt
+                        return self.D
+                n = N()
+                n.D = torch.randn_like(x) * 0.3
+                xr, mr = SO.unipc_update(x, ms, ts, t, order, variant=var, predict_x0=px0, net=n, use_corrector=True)
+                pred, corr = U.unipc_coefs([float(v) for v in ts], float(t), order, var, px0, True)
+                hist = [ms[-1 - k] for k in range(order)]
+                xp = pred[0] * x + sum(pred[1 + k] * hist[k] for k in range(order))
+                mt = SO.dynamic_thresholding(n.D) if px0 else (n.xt - n.D) / t
+                xc = corr[0] * x + corr[1] * mt + sum(corr[2 + k] * hist[k] for k in range(order))
+                assert (xp - n.xt).abs().max() < 1e-5 and (xc - xr).abs().max() < 2e-5
+    with pytest.raises(ValueError):
+        U.dpm_pp_coefs([1.0], 0.5, 4)
+
+
+def test_gits_dp_bit_exact_vs_reference():
+    d = np.load(GOLD)
+    meta = json.loads(bytes(d['meta_json']).decode())
+    cm = d['gits/cost']
+    for key, ref in meta['gits/dp'].items():
+        ns, coeff = key.split('/')
+        assert gits_utils.dp(cm, int(ns), cm.shape[0], float(coeff)) == ref
+    traj = torch.from_numpy(d['gits/traj'])
+    assert np.abs(gits_utils.cal_deviation(traj, 3, 8, bs=3).numpy() - d['gits/dev']).max() <= 1e-5 * np.abs(d['gits/dev']).max()
+    with pytest.raises(NotImplementedError):
+        gits_utils.get_sampler_fn('nope', 'cpu')
