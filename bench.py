@@ -164,7 +164,19 @@ def main():
     dev = torch.device('cuda', local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints its version banner on stdout at communicator creation; stdout must carry exactly one JSON line.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
@@ -243,6 +255,7 @@ def main():
 
     if rank != 0:
         if world > 1:
+            dist.barrier()                       # stay alive until rank 0 has finished its single-GPU diagnostic legs
             dist.destroy_process_group()
         return
 
@@ -256,7 +269,26 @@ def main():
     if gathered:
         line['allgather_bytes'] = gathered
 
-    if not args.no_extras:
+    try:
+        if not args.no_extras:
+            extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk)
+    except Exception as e:                       # the main measurement above is already complete; report instead of dying
+        line['extras_error'] = repr(e)
+
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_reference_leg(args, 1, 1)
+        line['cpu_baseline'] = dict(value=cb['value'], unit='images/s', cores=cb['cores'], kind='port', sample=cb['sample'])
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk):
+    import torch
+    from diff_sampler_b200 import solver_utils
+    from diff_sampler_b200.net import B200Net
+    if True:
         # ---- roofline of the dominant kernel (tcgen05 GEMM/conv), measured live with CUDA events on the launch stream ---
         x = latents * 2.0
         sig = torch.tensor(2.0, device=dev)
@@ -308,12 +340,6 @@ def main():
                                             note='single tcgen05 pass per product; not the headline because it does not hold 1e-3 on the de-zeroed weight set')
             del net1
 
-    if not args.no_cpu_baseline and world == 1:
-        cb = cpu_reference_leg(args, 1, 1)
-        line['cpu_baseline'] = dict(value=cb['value'], unit='images/s', cores=cb['cores'], kind='port', sample=cb['sample'])
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

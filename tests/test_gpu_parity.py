@@ -104,17 +104,19 @@ def test_reference_init_weights_are_a_vacuous_gate():
     assert err < 1e-5
 
 
-@pytest.mark.parametrize('name', ['cifar10'])
+@pytest.mark.parametrize('name', ['cifar10', 'ffhq', 'imagenet64'])
 def test_fullsize_denoiser_parity(name):
     """BASELINE config net (55.7 M parameters), batch 2, one evaluation at three noise levels."""
     from oracle import edm_oracle as O
     on, P, S = _oracle(name)
     nat = _native(P, S)
     x0 = O.stacked_randn(range(2), (3, S['img_resolution'], S['img_resolution']))
+    lab = _labels(S, 2)
+    labd = None if lab is None else lab.to(_dev())
     for sigma in (40.0, 1.0):
         x = x0 * sigma
-        ref = on(x, torch.tensor(sigma))
-        got = nat(x.to(_dev()), torch.tensor(sigma, device=_dev())).cpu()
+        ref = on(x, torch.tensor(sigma), class_labels=lab)
+        got = nat(x.to(_dev()), torch.tensor(sigma, device=_dev()), class_labels=labd).cpu()
         err = (got - ref).abs().max().item()
         print(f'{name} sigma={sigma}: max-abs err {err:.3e} (max|D| {ref.abs().max().item():.2f})')
         assert err < TOL
