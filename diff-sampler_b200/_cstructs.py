@@ -33,6 +33,7 @@ class GemmDesc(C.Structure):
         ('bias_n', P), ('bias_m', P), ('rowvec', P), ('rowvec_stride', I64), ('rows_per_sample', I32), ('pad0', I32),
         ('residual', P), ('ldr', I64), ('scale', F32),
         ('edm_out', I32), ('edm_x', P), ('edm_coef', P), ('edm_coef_stride', I32), ('edm_C', I32), ('edm_D', P),
+        ('st_sums', P * 2), ('st_cpg', I32 * 2), ('st_choff', I32 * 2), ('st_groups', I32 * 2),
     ]
 
 

@@ -58,7 +58,7 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_GEMM: {
             ds_gemm_desc& g = op.u.gemm;
             P(g.a_ptr); P(g.a2_ptr); P(g.b_ptr); P(g.out_f32); P(g.out_h16); P(g.bias_n); P(g.bias_m); P(g.rowvec);
-            P(g.residual); P(g.edm_x); P(g.edm_coef); P(g.edm_D);
+            P(g.residual); P(g.edm_x); P(g.edm_coef); P(g.edm_D); P(g.st_sums[0]); P(g.st_sums[1]);
             break;
         }
         case DS_OP_GN_STATS: { auto& d = op.u.gn_stats; P(d.src0); P(d.src1); P(d.sums); break; }

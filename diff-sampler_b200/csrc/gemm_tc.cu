@@ -50,6 +50,9 @@ struct alignas(64) GemmKernelParams {
     int edm_coef_stride;
     int edm_C;
     float* edm_D;
+    // fused GroupNorm statistics of the tensor being written (up to two consumers with their own channel grouping)
+    double* st_sums[2];
+    int st_cpg[2], st_choff[2], st_groups[2];
 };
 
 struct SmemCtl {
@@ -64,7 +67,9 @@ template <int W>
 __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const float* v, long long grow_in_z, int col0,
                                                bool row_ok, int z, int zb, int zh) {
     // v[W]: accumulators of this thread's row, columns col0 .. col0+W-1 (tile-local col0 already globalised)
-    if (!row_ok) return;
+    const bool has_stats = p.st_sums[0] != nullptr;      // warp-uniform
+    if (!row_ok && !has_stats) return;
+    if (!row_ok) grow_in_z = 0;                            // keep loads in range; the row's values are zeroed below
     float r[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] = v[j];
@@ -102,6 +107,46 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     }
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] *= p.scale;
+
+    if (has_stats) {
+        // per-(sample, group) sum / sum of squares of the values being written: 32 rows (one warp) belong to one sample,
+        // a group is a run of `cpg` consecutive channels of the consumer's (possibly concatenated) channel axis.
+        const long long n = grow_in_z / p.rows_per_sample;
+#pragma unroll
+        for (int sidx = 0; sidx < 2; ++sidx) {
+            if (!p.st_sums[sidx]) continue;
+            const int cpg = p.st_cpg[sidx];
+            float s1 = 0.f, s2 = 0.f;
+            int g_cur = (p.st_choff[sidx] + col0) / cpg;
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const int g = (p.st_choff[sidx] + col0 + j) / cpg;          // warp-uniform
+                if (g != g_cur) {
+                    float a = s1, b = s2;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+                    if ((threadIdx.x & 31) == 0) {
+                        double* dst = p.st_sums[sidx] + (n * p.st_groups[sidx] + g_cur) * 2;
+                        atomicAdd(dst, (double)a);
+                        atomicAdd(dst + 1, (double)b);
+                    }
+                    s1 = 0.f; s2 = 0.f; g_cur = g;
+                }
+                const float val = (row_ok && (full || col0 + j < p.n_valid)) ? r[j] : 0.f;
+                s1 += val;
+                s2 += val * val;
+            }
+            float a = s1, b = s2;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+            if ((threadIdx.x & 31) == 0) {
+                double* dst = p.st_sums[sidx] + (n * p.st_groups[sidx] + g_cur) * 2;
+                atomicAdd(dst, (double)a);
+                atomicAdd(dst + 1, (double)b);
+            }
+        }
+        if (!row_ok) return;
+    }
 
     if (p.edm_out) {
         // D = c_skip * x + c_out * F, written NCHW (reference: networks_edm.py:488-495)
@@ -392,6 +437,12 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     kp->residual = d->residual; kp->ldr = d->ldr; kp->scale = d->scale;
     kp->edm_out = d->edm_out; kp->edm_x = d->edm_x; kp->edm_coef = d->edm_coef; kp->edm_coef_stride = d->edm_coef_stride;
     kp->edm_C = d->edm_C; kp->edm_D = d->edm_D;
+    for (int k = 0; k < 2; ++k) {
+        kp->st_sums[k] = d->st_sums[k]; kp->st_cpg[k] = d->st_cpg[k] > 0 ? d->st_cpg[k] : 1;
+        kp->st_choff[k] = d->st_choff[k]; kp->st_groups[k] = d->st_groups[k];
+    }
+    if (d->st_sums[1] && !d->st_sums[0]) return -13;
+    if (d->st_sums[0] && (d->a_mode != 0 || (d->conv_H * d->conv_W) % 32 != 0)) return -14;
     const int stage_bytes = kATileBytes + d->BN * 128;
     int ns = (227 * 1024 - 2048) / stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;

@@ -70,6 +70,12 @@ typedef struct ds_gemm_desc {
     int32_t edm_coef_stride;// 0 (one sigma) or 4 (per-sample)
     int32_t edm_C;
     float* edm_D;
+    // fused GroupNorm statistics of the fp32 output (conv mode only): for each consumer k, accumulate per (sample, group)
+    // {sum, sumsq} into st_sums[k][(n*st_groups[k] + g)*2 + {0,1}] with g = (st_choff[k] + channel) / st_cpg[k].
+    double* st_sums[2];
+    int32_t st_cpg[2];
+    int32_t st_choff[2];
+    int32_t st_groups[2];
 } ds_gemm_desc;
 
 int ds_gemm_launch(const ds_gemm_desc* d, cudaStream_t stream);

@@ -154,7 +154,7 @@ class Plan:
         self.meta = meta
 
 
-def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
+def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
     """Lower the forward pass for batch B.  nsig in {1, B}: number of sigma values (embedding rows);
     nlab in {0, 1, B}: rows of class labels supplied."""
     assert nsig in (1, B) and nlab in (0, 1, B)
@@ -170,6 +170,47 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
 
     def emit(builder):
         ops.append((tag[0], builder))
+
+    # Fused GroupNorm statistics: the GEMM that writes an fp32 tensor also accumulates the {sum, sumsq} its consumers need
+    # (at most two: the next block and, for encoder outputs, the decoder block that concatenates it as a skip).
+    prod_of = {}            # buffer name -> index of the op that last wrote it
+    sinks = {}              # producer op index -> [(stats byte offset, cpg, channel offset, groups)]
+
+    def emit_producer(name, build):
+        pid = len(ops)
+        prod_of[name] = pid
+        sinks[pid] = []
+
+        def materialise(R):
+            d = build(R)
+            for k, (slot, cpg, choff, groups) in enumerate(sinks[pid]):
+                d.st_sums[k] = R('stats', slot)
+                d.st_cpg[k], d.st_choff[k], d.st_groups[k] = cpg, choff, groups
+            return d
+        emit(materialise)
+
+    def need_stats(slot, parts, hw):
+        """GroupNorm statistics over the (virtually concatenated) fp32 tensors `parts` = [(buffer, channels), ...] into `slot`.
+        Default: one stand-alone gn_stats launch.  fuse_stats=True: accumulated by the epilogue of the GEMM that writes each part
+        (kept for experiments: on B200 round 1 the extra shuffles + fp64 atomics made the epilogue the critical path —
+        59.7 -> 72.8 ms of GEMM time per CIFAR-10 forward to save a 4.3 ms statistics pass)."""
+        c_total = sum(c for _, c in parts)
+        if not fuse_stats:
+            assert len(parts) <= 2
+            (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
+            emit(lambda R: S.GnStatsDesc(src0=R(n0), src1=R(n1) if n1 else 0, C0=c0, C1=c1, HW=hw, B=B, groups=_groups(c_total),
+                                         sums=R('stats', slot)))
+            return
+        off = 0
+        for name, c in parts:
+            want_stats(name, slot, c_total, off)
+            off += c
+
+    def want_stats(name, slot, c_total, choff):
+        lst = sinks[prod_of[name]]
+        assert len(lst) < 2, f'more than two GroupNorm consumers of {name}'
+        g = _groups(c_total)
+        lst.append((slot, c_total // g, choff, g))
 
     # ---------------- embedding ----------------------------------------------------------------------------------
     A.need('coef', nsig * 4 * F4)
@@ -220,8 +261,8 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
     emit(lambda R: S.PrepInputDesc(x=io(S.DS_IO_X), coef=R('coef'), coef_stride=4 if nsig > 1 else 0, B=B, C=spec.img_channels,
                                    HW=HW0, nplanes=npl, out=R('in_planes')))
     A.need('x:' + spec.stem, B * HW0 * spec.stem_cout * F4)
-    emit(lambda R: G.conv_gemm(R('in_planes'), B, R0, R0, 64, W(spec.stem + ':w'), spec.stem_cout, taps=9, npass=npass,
-                               out_f32=R('x:' + spec.stem), bias=W(spec.stem + ':b'))[0])
+    emit_producer('x:' + spec.stem, lambda R: G.conv_gemm(R('in_planes'), B, R0, R0, 64, W(spec.stem + ':w'), spec.stem_cout, taps=9,
+                                                          npass=npass, out_f32=R('x:' + spec.stem), bias=W(spec.stem + ':b'))[0])
 
     stat_i = [0]
 
@@ -240,7 +281,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
         resample = 1 if b.down else (2 if b.up else 0)
         Mo = B * Ho * Ho
         s0 = stats_slot()
-        emit(lambda R: S.GnStatsDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, HW=Hi * Hi, B=B, groups=_groups(cin), sums=R('stats', s0)))
+        need_stats(s0, [(x0, c0)] + ([(x1, c1)] if x1 else []), Hi * Hi)
         A.need('act', npl * Mo * max(cin, cout) * H2)
         want_raw = b.skip == 'conv'
         want_rawf = b.skip == 'resample'
@@ -253,11 +294,11 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
                                      resample=resample, nplanes=npl, out_act=R('act'), out_raw=R('raw') if want_raw else 0,
                                      out_raw_f32=R('rawf') if want_rawf else 0))
         A.need('y', Mo * cout * F4)
-        emit(lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cin, W(n + '.conv0:w'), cout, taps=9, npass=npass, out_f32=R('y'),
-                                   bias=W(n + '.conv0:b'), rowvec=0 if b.adaptive_scale else R('aff', b.aff_off * F4),
-                                   rowvec_stride=aff_stride)[0])
+        emit_producer('y', lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cin, W(n + '.conv0:w'), cout, taps=9, npass=npass, out_f32=R('y'),
+                                                 bias=W(n + '.conv0:b'), rowvec=0 if b.adaptive_scale else R('aff', b.aff_off * F4),
+                                                 rowvec_stride=aff_stride)[0])
         s1 = stats_slot()
-        emit(lambda R: S.GnStatsDesc(src0=R('y'), src1=0, C0=cout, C1=0, HW=Ho * Ho, B=B, groups=_groups(cout), sums=R('stats', s1)))
+        need_stats(s1, [('y', cout)], Ho * Ho)
         emit(lambda R: S.GnApplyDesc(src0=R('y'), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), sums=R('stats', s1),
                                      gamma=W(n + '.norm1:g'), beta=W(n + '.norm1:b'), eps=b.eps, silu=1,
                                      ada=R('aff', b.aff_off * F4) if b.adaptive_scale else 0,
@@ -272,15 +313,16 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
             res_name = 'rawf'
         else:
             res_name = None
-        emit(lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cout, W(n + '.conv1:w'), cout, taps=9, npass=npass,
-                                   a2_ptr=R('raw') if want_raw else 0, C2=cin if want_raw else 0, out_f32=R(mid),
-                                   bias=W(n + '.conv1:b'), residual=R(res_name) if res_name else 0, ldr=cout, scale=b.skip_scale)[0])
+        emit_producer(mid, lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cout, W(n + '.conv1:w'), cout, taps=9, npass=npass,
+                                                 a2_ptr=R('raw') if want_raw else 0, C2=cin if want_raw else 0, out_f32=R(mid),
+                                                 bias=W(n + '.conv1:b'), residual=R(res_name) if res_name else 0, ldr=cout,
+                                                 scale=b.skip_scale)[0])
         if b.heads:
             nh = b.heads
             d = cout // nh
             L = Ho * Ho
             s2 = stats_slot()
-            emit(lambda R: S.GnStatsDesc(src0=R(mid), src1=0, C0=cout, C1=0, HW=L, B=B, groups=_groups(cout), sums=R('stats', s2)))
+            need_stats(s2, [(mid, cout)], L)
             emit(lambda R: S.GnApplyDesc(src0=R(mid), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), sums=R('stats', s2),
                                          gamma=W(n + '.norm2:g'), beta=W(n + '.norm2:b'), eps=b.eps, silu=0, ada=0, ada_stride=0,
                                          resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))
@@ -301,8 +343,8 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
             emit(lambda R: G.rows_gemm(R('P'), L, L, B * nh, R('vt'), cout, L, B, L, num_z=B * nh, nh=nh, m_valid=L, n_valid=d,
                                        npass=npass, a_n_per_zb=nh, a_n_per_zh=1, b_row_per_zh=d, b_z_per_zb=1, out_h16=R('o'),
                                        o_zb=L * cout, o_zh=d, ldo=cout, o_plane=B * L * cout)[0])
-            emit(lambda R: G.conv_gemm(R('o'), B, Ho, Ho, cout, W(n + '.proj:w'), cout, taps=1, npass=npass, out_f32=R(xout),
-                                       bias=W(n + '.proj:b'), residual=R(mid), ldr=cout, scale=b.skip_scale)[0])
+            emit_producer(xout, lambda R: G.conv_gemm(R('o'), B, Ho, Ho, cout, W(n + '.proj:w'), cout, taps=1, npass=npass, out_f32=R(xout),
+                                                      bias=W(n + '.proj:b'), residual=R(mid), ldr=cout, scale=b.skip_scale)[0])
         if n == spec.bottleneck_block:
             emit(lambda R: S.ChanmeanDesc(src=R(xout), out=io(S.DS_IO_BOTTLENECK), rows=B * Ho * Ho, C=cout))
         return xout
@@ -327,7 +369,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3):
     sh = stats_slot()
     A.need('act', npl * B * HW0 * cur_c * H2)
     fin, fin_c = cur, cur_c
-    emit(lambda R: S.GnStatsDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, HW=HW0, B=B, groups=_groups(fin_c), sums=R('stats', sh)))
+    need_stats(sh, [(fin, fin_c)], HW0)
     emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=_groups(fin_c), sums=R('stats', sh),
                                  gamma=W(spec.head_norm + ':g'), beta=W(spec.head_norm + ':b'), eps=spec.head_eps, silu=1, ada=0,
                                  ada_stride=0, resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))

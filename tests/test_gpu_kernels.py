@@ -369,3 +369,40 @@ def test_dyn_threshold_matches_torch_quantile(lib, n):
     ref = torch.maximum(torch.quantile(x0.abs(), 0.995, dim=1), torch.ones(B, device=dev()))
     print('thr', thr.tolist(), 'ref', ref.tolist())
     assert (thr - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize('Bn,H,W,Cout,cpg1,choff2,ctot2', [(3, 16, 16, 128, 4, 64, 256), (5, 8, 8, 192, 6, 0, 192), (2, 32, 32, 256, 8, 256, 512)])
+def test_conv_epilogue_fused_groupnorm_stats(lib, Bn, H, W, Cout, cpg1, choff2, ctot2):
+    """The GEMM epilogue accumulates the GroupNorm {sum, sumsq} of the tensor it writes, for two consumers with different
+    channel groupings (plain next-block norm; decoder concat where this tensor is one part of a wider channel axis)."""
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(11)
+    Cin = 64
+    x = torch.randn(Bn, Cin, H, W, device=dev())
+    w = torch.randn(Cout, Cin, 3, 3, device=dev()) / (3 * Cin ** 0.5)
+    bias = torch.randn(Cout, device=dev())
+    xa = planes(x.permute(0, 2, 3, 1).contiguous())
+    wp = G.pack_conv_weight(w.cpu()).to(dev())
+    out = torch.zeros(Bn * H * W, Cout, device=dev())
+    g1 = Cout // cpg1
+    g2 = 32
+    cpg2 = ctot2 // g2
+    s1 = torch.zeros(Bn, g1, 2, dtype=torch.float64, device=dev())
+    s2 = torch.zeros(Bn, g2, 2, dtype=torch.float64, device=dev())
+    d, _ = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=9, npass=3, out_f32=out.data_ptr(), bias=bias.data_ptr(),
+                       scale=0.5)
+    d.st_sums[0], d.st_cpg[0], d.st_choff[0], d.st_groups[0] = s1.data_ptr(), cpg1, 0, g1
+    d.st_sums[1], d.st_cpg[1], d.st_choff[1], d.st_groups[1] = s2.data_ptr(), cpg2, choff2, g2
+    lib.op_launch(d)
+    sync()
+    y = out.double().reshape(Bn, H * W, Cout)
+    r1 = torch.stack([y.reshape(Bn, H * W, g1, cpg1).sum(dim=(1, 3)), (y ** 2).reshape(Bn, H * W, g1, cpg1).sum(dim=(1, 3))], dim=-1)
+    assert (s1 - r1).abs().max().item() < 1e-3 * max(1.0, r1.abs().max().item()) * 1e-2
+    r2 = torch.zeros(Bn, g2, 2, dtype=torch.float64, device=dev())
+    for c in range(Cout):
+        g = (choff2 + c) // cpg2
+        r2[:, g, 0] += y[:, :, c].sum(dim=1)
+        r2[:, g, 1] += (y[:, :, c] ** 2).sum(dim=1)
+    err2 = (s2 - r2).abs().max().item()
+    print(f'fused stats: sink1 err {(s1 - r1).abs().max().item():.3e} sink2 err {err2:.3e} (max {r2.abs().max().item():.1f})')
+    assert err2 < 1e-5 * max(1.0, r2.abs().max().item())

@@ -91,6 +91,19 @@ def test_denoiser_parity(name, precision, tol):
     assert err < tol
 
 
+def test_fused_groupnorm_stats_plan_matches():
+    """The optional plan variant that accumulates GroupNorm statistics in the GEMM epilogues gives the same denoiser output."""
+    from oracle import edm_oracle as O
+    from diff_sampler_b200.net import B200Net
+    on, P, S = _oracle('tiny_adm')
+    nat = B200Net(P, S['img_resolution'], S['img_channels'], S['label_dim'], device=_dev(), fuse_stats=True)
+    x = O.stacked_randn(range(3), (3, 16, 16)) * 2.0
+    lab = _labels(S, 3)
+    ref = on(x, torch.tensor(2.0), class_labels=lab)
+    got = nat(x.to(_dev()), torch.tensor(2.0, device=_dev()), class_labels=lab.to(_dev())).cpu()
+    assert (got - ref).abs().max().item() < TOL
+
+
 def test_reference_init_weights_are_a_vacuous_gate():
     """With the reference's own init (init_zero layers ~1e-5) |F_x| ~ 3e-5 and even single-pass fp16 is ~1e-7 off."""
     from oracle import edm_oracle as O
