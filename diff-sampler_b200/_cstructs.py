@@ -8,7 +8,7 @@ I64 = C.c_int64
 F32 = C.c_float
 
 DS_OP_GEMM, DS_OP_GN_STATS, DS_OP_GN_APPLY, DS_OP_SOFTMAX, DS_OP_POSEMB, DS_OP_LINEAR = 1, 2, 3, 4, 5, 6
-DS_OP_PREP_INPUT, DS_OP_CHANMEAN, DS_OP_MEMSET = 7, 8, 9
+DS_OP_PREP_INPUT, DS_OP_CHANMEAN, DS_OP_MEMSET, DS_OP_LAYERNORM, DS_OP_GEGLU = 7, 8, 9, 10, 11
 DS_IO_X, DS_IO_D, DS_IO_SIGMA, DS_IO_LABELS, DS_IO_BOTTLENECK = 0, 1, 2, 3, 4
 DS_M_X0, DS_M_EPS, DS_M_DIV, DS_M_NONE = 0, 1, 2, 3
 
@@ -34,6 +34,7 @@ class GemmDesc(C.Structure):
         ('residual', P), ('ldr', I64), ('scale', F32),
         ('edm_out', I32), ('edm_x', P), ('edm_coef', P), ('edm_coef_stride', I32), ('edm_C', I32), ('edm_D', P),
         ('st_sums', P * 2), ('st_cpg', I32 * 2), ('st_choff', I32 * 2), ('st_groups', I32 * 2),
+        ('tap_dh', I32 * 9), ('tap_dw', I32 * 9), ('tap_cb', I32 * 9), ('pad1', I32),
     ]
 
 
@@ -49,12 +50,12 @@ class GnApplyDesc(C.Structure):
 
 
 class SoftmaxDesc(C.Structure):
-    _fields_ = [('S', P), ('P', P), ('rows', I64), ('L', I32), ('nplanes', I32)]
+    _fields_ = [('S', P), ('P', P), ('rows', I64), ('L', I32), ('nplanes', I32), ('pitch_in', I32), ('pitch_out', I32)]
 
 
 class PosembDesc(C.Structure):
     _fields_ = [('sigma', P), ('nsig', I32), ('num_channels', I32), ('endpoint', I32), ('swap_sincos', I32),
-                ('sigma_data', F32), ('pad0', I32), ('coef', P), ('emb', P)]
+                ('sigma_data', F32), ('mode', I32), ('coef', P), ('emb', P)]
 
 
 class LinearDesc(C.Structure):
@@ -71,6 +72,14 @@ class ChanmeanDesc(C.Structure):
     _fields_ = [('src', P), ('out', P), ('rows', I64), ('C', I32), ('pad0', I32)]
 
 
+class LayernormDesc(C.Structure):
+    _fields_ = [('src', P), ('gamma', P), ('beta', P), ('out', P), ('rows', I64), ('C', I32), ('nplanes', I32), ('eps', F32), ('pad0', I32)]
+
+
+class GegluDesc(C.Structure):
+    _fields_ = [('src', P), ('out', P), ('rows', I64), ('I', I32), ('nplanes', I32)]
+
+
 class MemsetDesc(C.Structure):
     _fields_ = [('ptr', P), ('bytes', I64)]
 
@@ -78,7 +87,7 @@ class MemsetDesc(C.Structure):
 class _OpUnion(C.Union):
     _fields_ = [('gemm', GemmDesc), ('gn_stats', GnStatsDesc), ('gn_apply', GnApplyDesc), ('softmax', SoftmaxDesc),
                 ('posemb', PosembDesc), ('linear', LinearDesc), ('prep_input', PrepInputDesc), ('chanmean', ChanmeanDesc),
-                ('memset', MemsetDesc)]
+                ('memset', MemsetDesc), ('layernorm', LayernormDesc), ('geglu', GegluDesc)]
 
 
 class PlanOp(C.Structure):
@@ -88,13 +97,14 @@ class PlanOp(C.Structure):
 SIZEOF_CHECKS = {
     0: PlanOp, DS_OP_GEMM: GemmDesc, DS_OP_GN_STATS: GnStatsDesc, DS_OP_GN_APPLY: GnApplyDesc, DS_OP_SOFTMAX: SoftmaxDesc,
     DS_OP_POSEMB: PosembDesc, DS_OP_LINEAR: LinearDesc, DS_OP_PREP_INPUT: PrepInputDesc, DS_OP_CHANMEAN: ChanmeanDesc,
-    DS_OP_MEMSET: MemsetDesc,
+    DS_OP_MEMSET: MemsetDesc, DS_OP_LAYERNORM: LayernormDesc, DS_OP_GEGLU: GegluDesc,
 }
 
 UNION_FIELD = {
     DS_OP_GEMM: 'gemm', DS_OP_GN_STATS: 'gn_stats', DS_OP_GN_APPLY: 'gn_apply', DS_OP_SOFTMAX: 'softmax', DS_OP_POSEMB: 'posemb',
     DS_OP_LINEAR: 'linear', DS_OP_PREP_INPUT: 'prep_input', DS_OP_CHANMEAN: 'chanmean', DS_OP_MEMSET: 'memset',
+    DS_OP_LAYERNORM: 'layernorm', DS_OP_GEGLU: 'geglu',
 }
 OP_TYPE_OF = {GemmDesc: DS_OP_GEMM, GnStatsDesc: DS_OP_GN_STATS, GnApplyDesc: DS_OP_GN_APPLY, SoftmaxDesc: DS_OP_SOFTMAX,
               PosembDesc: DS_OP_POSEMB, LinearDesc: DS_OP_LINEAR, PrepInputDesc: DS_OP_PREP_INPUT, ChanmeanDesc: DS_OP_CHANMEAN,
-              MemsetDesc: DS_OP_MEMSET}
+              MemsetDesc: DS_OP_MEMSET, LayernormDesc: DS_OP_LAYERNORM, GegluDesc: DS_OP_GEGLU}

@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
     }
     const int Ho = RESAMPLE == 1 ? d.H / 2 : (RESAMPLE == 2 ? d.H * 2 : d.H);
     const int Wo = RESAMPLE == 1 ? d.W / 2 : (RESAMPLE == 2 ? d.W * 2 : d.W);
-    const int npix = Ho * Wo;
+    const int npix = Ho * Wo;              // RESAMPLE == 3 iterates over INPUT pixels and scatters them into the phase layout
     const long long plane = (long long)d.B * npix * C;
     const float* base;
     int pitch, cc;
@@ -165,7 +165,12 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
                 act[j] = y;
             }
         }
-        const long long o = ((long long)n * npix + po) * C + c;
+        long long o = ((long long)n * npix + po) * C + c;
+        if (RESAMPLE == 3) {
+            // space-to-depth: input pixel (ho, wo) -> output pixel (ho/2, wo/2), channel block ((ho&1)*2 + (wo&1))*C
+            const int h2 = ho >> 1, w2 = wo >> 1, ph = ((ho & 1) << 1) | (wo & 1);
+            o = (((long long)n * (d.H / 2) + h2) * (d.W / 2) + w2) * (4LL * C) + (long long)ph * C + c;
+        }
         if (oact) gn_store_planes(oact, plane, o, act, d.nplanes);
         if (oraw) gn_store_planes(oraw, plane, o, raw, d.nplanes);
         if (d.out_raw_f32) {
@@ -181,39 +186,72 @@ __global__ void softmax_kernel(ds_softmax_desc d) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= d.rows) return;
     const int lane = threadIdx.x & 31;
-    const float* s = d.S + row * d.L;
-    float m = -INFINITY;
-    for (int j = lane * 4; j < d.L; j += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(s + j);
-        m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    const int pin = d.pitch_in ? d.pitch_in : d.L;
+    const int pout = d.pitch_out ? d.pitch_out : d.L;
+    const float* s = d.S + row * pin;
+    __half* P = reinterpret_cast<__half*>(d.P);
+    const long long plane = d.rows * pout;
+    if ((d.L & 3) == 0 && (pin & 3) == 0 && (pout & 3) == 0) {
+        float m = -INFINITY;
+        for (int j = lane * 4; j < d.L; j += 128) {
+            const float4 v = *reinterpret_cast<const float4*>(s + j);
+            m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float sum = 0.f;
+        for (int j = lane * 4; j < d.L; j += 128) {
+            const float4 v = *reinterpret_cast<const float4*>(s + j);
+            sum += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.0f / sum;
+        for (int j = lane * 4; j < d.L; j += 128) {
+            const float4 v = *reinterpret_cast<const float4*>(s + j);
+            const float e[4] = {expf(v.x - m) * inv, expf(v.y - m) * inv, expf(v.z - m) * inv, expf(v.w - m) * inv};
+            __align__(8) __half hi[4];
+            __align__(8) __half lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) split_h16(e[k], hi[k], lo[k]);
+            *reinterpret_cast<uint2*>(P + row * pout + j) = *reinterpret_cast<const uint2*>(hi);
+            if (d.nplanes > 1) *reinterpret_cast<uint2*>(P + plane + row * pout + j) = *reinterpret_cast<const uint2*>(lo);
+        }
+        return;
     }
+    // generic row length (e.g. 77 context tokens): scalar accesses
+    float m = -INFINITY;
+    for (int j = lane; j < d.L; j += 32) m = fmaxf(m, s[j]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     float sum = 0.f;
-    for (int j = lane * 4; j < d.L; j += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(s + j);
-        sum += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
-    }
+    for (int j = lane; j < d.L; j += 32) sum += expf(s[j] - m);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
-    __half* P = reinterpret_cast<__half*>(d.P);
-    const long long plane = d.rows * d.L;
-    for (int j = lane * 4; j < d.L; j += 128) {
-        const float4 v = *reinterpret_cast<const float4*>(s + j);
-        const float e[4] = {expf(v.x - m) * inv, expf(v.y - m) * inv, expf(v.z - m) * inv, expf(v.w - m) * inv};
-        __align__(8) __half hi[4];
-        __align__(8) __half lo[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) split_h16(e[k], hi[k], lo[k]);
-        *reinterpret_cast<uint2*>(P + row * d.L + j) = *reinterpret_cast<const uint2*>(hi);
-        if (d.nplanes > 1) *reinterpret_cast<uint2*>(P + plane + row * d.L + j) = *reinterpret_cast<const uint2*>(lo);
+    for (int j = lane; j < d.L; j += 32) {
+        __half hi, lo;
+        split_h16(expf(s[j] - m) * inv, hi, lo);
+        P[row * pout + j] = hi;
+        if (d.nplanes > 1) P[plane + row * pout + j] = lo;
     }
 }
 
 // ------------------------------------------------------------------------------------------ embedding
 __global__ void posemb_kernel(ds_posemb_desc d) {
     const int n = blockIdx.x;
+    if (d.mode == 1) {
+        // LDM timestep_embedding (util.py:151-171): freqs = exp(-ln(10000) * i / half), [cos | sin]
+        const float t = d.sigma[n];
+        const int half = d.num_channels / 2;
+        for (int i = threadIdx.x; i < half; i += blockDim.x) {
+            const float freq = expf(-logf(10000.0f) * (float)i / (float)half);
+            const float a = t * freq;
+            d.emb[n * d.num_channels + i] = cosf(a);
+            d.emb[n * d.num_channels + half + i] = sinf(a);
+        }
+        return;
+    }
     const float sigma = d.sigma[n];
     const float sd = d.sigma_data;
     const float s2 = sigma * sigma + sd * sd;
@@ -294,6 +332,81 @@ __global__ void prep_input_kernel(ds_prep_input_desc d) {
     if (d.nplanes > 1) *reinterpret_cast<uint4*>(o + (long long)d.B * d.HW * 64 + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// one warp per token row; the row lives in registers (C <= 2048), two-pass mean / variance like torch's layer_norm
+__global__ void layernorm_kernel(ds_layernorm_desc d) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= d.rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* x = d.src + row * d.C;
+    constexpr int MAXV = 16;                                   // float4 per lane: C <= 32*4*16 = 2048
+    float4 v[MAXV];
+    const int nv = d.C / 4;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nv) {
+            v[k] = *reinterpret_cast<const float4*>(x + 4 * j);
+            sum += v[k].x + v[k].y + v[k].z + v[k].w;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)d.C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nv) {
+            const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
+            sq += a * a + b * b + c * c + e * e;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)d.C + d.eps);
+    __half* out = reinterpret_cast<__half*>(d.out);
+    const long long plane = d.rows * d.C;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nv) {
+            const float4 g = *reinterpret_cast<const float4*>(d.gamma + 4 * j);
+            const float4 b = *reinterpret_cast<const float4*>(d.beta + 4 * j);
+            const float y[4] = {(v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y,
+                                (v[k].z - mean) * rstd * g.z + b.z, (v[k].w - mean) * rstd * g.w + b.w};
+            __align__(8) __half hi[4];
+            __align__(8) __half lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_h16(y[q], hi[q], lo[q]);
+            *reinterpret_cast<uint2*>(out + row * d.C + 4 * j) = *reinterpret_cast<const uint2*>(hi);
+            if (d.nplanes > 1) *reinterpret_cast<uint2*>(out + plane + row * d.C + 4 * j) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+}
+
+__global__ void geglu_kernel(ds_geglu_desc d) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 4 outputs
+    const int i4 = d.I / 4;
+    const long long total = d.rows * i4;
+    if (idx >= total) return;
+    const long long row = idx / i4;
+    const int j = (int)(idx - row * i4) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(d.src + row * 2 * d.I + j);
+    const float4 g = *reinterpret_cast<const float4*>(d.src + row * 2 * d.I + d.I + j);
+    const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+    __align__(8) __half hi[4];
+    __align__(8) __half lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float gelu = 0.5f * gv[q] * (1.0f + erff(gv[q] * 0.70710678118654752f));
+        split_h16(av[q] * gelu, hi[q], lo[q]);
+    }
+    __half* out = reinterpret_cast<__half*>(d.out);
+    *reinterpret_cast<uint2*>(out + row * d.I + j) = *reinterpret_cast<const uint2*>(hi);
+    if (d.nplanes > 1) *reinterpret_cast<uint2*>(out + d.rows * d.I + row * d.I + j) = *reinterpret_cast<const uint2*>(lo);
+}
+
 __global__ void chanmean_kernel(ds_chanmean_desc d) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= d.rows) return;
@@ -342,13 +455,27 @@ extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream
     const int chunks = (npix + pix_per_cta - 1) / pix_per_cta;
     dim3 grid(chunks, d->B);
     if (d->resample == 1) gn_apply_kernel<1><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
+    else if (d->resample == 3) gn_apply_kernel<3><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
     else if (d->resample == 2) gn_apply_kernel<2><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
     else gn_apply_kernel<0><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
     return ok();
 }
 
+extern "C" int ds_layernorm_launch(const ds_layernorm_desc* d, cudaStream_t stream) {
+    if (d->C % 4 || d->C > 2048) return -2;
+    const int wpb = 8;
+    layernorm_kernel<<<(unsigned)((d->rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(*d);
+    return ok();
+}
+
+extern "C" int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream) {
+    if (d->I % 4) return -2;
+    const long long total = d->rows * (d->I / 4);
+    geglu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(*d);
+    return ok();
+}
+
 extern "C" int ds_softmax_launch(const ds_softmax_desc* d, cudaStream_t stream) {
-    if (d->L % 4) return -2;
     const int wpb = 8;
     const long long blocks = (d->rows + wpb - 1) / wpb;
     softmax_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(*d);

@@ -73,6 +73,8 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_PREP_INPUT: { auto& d = op.u.prep_input; P(d.x); P(d.coef); P(d.out); break; }
         case DS_OP_CHANMEAN: { auto& d = op.u.chanmean; P(d.src); P(d.out); break; }
         case DS_OP_MEMSET: { auto& d = op.u.memset; P(d.ptr); break; }
+        case DS_OP_LAYERNORM: { auto& d = op.u.layernorm; P(d.src); P(d.gamma); P(d.beta); P(d.out); break; }
+        case DS_OP_GEGLU: { auto& d = op.u.geglu; P(d.src); P(d.out); break; }
         default: break;
     }
 #undef P
@@ -90,6 +92,8 @@ static int launch_op(const ds_plan_op& op, const unsigned char* gemm_kp, cudaStr
         case DS_OP_LINEAR: return ds_linear_launch(&op.u.linear, s);
         case DS_OP_PREP_INPUT: return ds_prep_input_launch(&op.u.prep_input, s);
         case DS_OP_CHANMEAN: return ds_chanmean_launch(&op.u.chanmean, s);
+        case DS_OP_LAYERNORM: return ds_layernorm_launch(&op.u.layernorm, s);
+        case DS_OP_GEGLU: return ds_geglu_launch(&op.u.geglu, s);
         case DS_OP_MEMSET:
             return cudaMemsetAsync(op.u.memset.ptr, 0, (size_t)op.u.memset.bytes, s) == cudaSuccess ? 0 : -1;
         default: return -100;
@@ -311,6 +315,8 @@ size_t ds_sizeof(int which) {
         case DS_OP_PREP_INPUT: return sizeof(ds_prep_input_desc);
         case DS_OP_CHANMEAN: return sizeof(ds_chanmean_desc);
         case DS_OP_MEMSET: return sizeof(ds_memset_desc);
+        case DS_OP_LAYERNORM: return sizeof(ds_layernorm_desc);
+        case DS_OP_GEGLU: return sizeof(ds_geglu_desc);
         default: return 0;
     }
 }

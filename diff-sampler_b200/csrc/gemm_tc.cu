@@ -53,6 +53,7 @@ struct alignas(64) GemmKernelParams {
     // fused GroupNorm statistics of the tensor being written (up to two consumers with their own channel grouping)
     double* st_sums[2];
     int st_cpg[2], st_choff[2], st_groups[2];
+    int tap_dh[9], tap_dw[9], tap_cb[9];
 };
 
 struct SmemCtl {
@@ -280,9 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     const int pb = (pass == 2) ? 1 : 0;
                     if (kb < p.nkb_main) {
                         const int tap = kb / p.cpb;
-                        const int c0 = (kb - tap * p.cpb) * 64;
-                        int dh = 0, dw = 0;
-                        if (p.taps == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+                        const int c0 = (kb - tap * p.cpb) * 64 + p.tap_cb[tap];
+                        const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
                         tma_load_4d(&p.tmA, &ctl->full[stage], sa, c0 + a_c_off, aw0 + dw, ah0 + dh, an0 + pa * p.a_plane_n);
                     } else {
                         const int c0 = (kb - p.nkb_main) * 64;
@@ -441,6 +441,8 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
         kp->st_sums[k] = d->st_sums[k]; kp->st_cpg[k] = d->st_cpg[k] > 0 ? d->st_cpg[k] : 1;
         kp->st_choff[k] = d->st_choff[k]; kp->st_groups[k] = d->st_groups[k];
     }
+    for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = d->tap_dh[t]; kp->tap_dw[t] = d->tap_dw[t]; kp->tap_cb[t] = d->tap_cb[t]; }
+    if (d->taps != 1 && d->taps != 9) return -15;
     if (d->st_sums[1] && !d->st_sums[0]) return -13;
     if (d->st_sums[0] && (d->a_mode != 0 || (d->conv_H * d->conv_W) % 32 != 0)) return -14;
     const int stage_bytes = kATileBytes + d->BN * 128;

@@ -76,6 +76,13 @@ typedef struct ds_gemm_desc {
     int32_t st_cpg[2];
     int32_t st_choff[2];
     int32_t st_groups[2];
+    // conv taps: K block `tap` reads the pixel box shifted by (tap_dh, tap_dw) from channel base tap_cb.  A 3x3 stride-1 conv uses
+    // (kh-1, kw-1, 0); a 3x3 stride-2 conv over a space-to-depth input [B][H/2][W/2][4C] uses shifts in {-1,0} and the phase's
+    // channel base (LDM Downsample, openaimodel.py:134-160).
+    int32_t tap_dh[9];
+    int32_t tap_dw[9];
+    int32_t tap_cb[9];
+    int32_t pad1;
 } ds_gemm_desc;
 
 int ds_gemm_launch(const ds_gemm_desc* d, cudaStream_t stream);
@@ -113,7 +120,7 @@ typedef struct ds_gn_apply_desc {
     int32_t silu;
     const float* ada;       // adaptive [nE][2*C]: scale = ada[c], shift = ada[C + c]; NULL if unused
     int64_t ada_stride;     // elements between samples (0 = broadcast)
-    int32_t resample;       // 0 none, 1 down (2x2 mean), 2 up (nearest x2)
+    int32_t resample;       // 0 none, 1 down (2x2 mean), 2 up (nearest x2), 3 space-to-depth (out [B][H/2][W/2][4C], phase-major)
     int32_t nplanes;        // 1 or 2 (hi / hi+lo)
     void* out_act;          // fp16 [nplanes][B][Ho][Wo][C]; may be NULL
     void* out_raw;          // fp16 planes of the raw input; may be NULL
@@ -125,8 +132,10 @@ typedef struct ds_softmax_desc {
     const float* S;
     void* P;
     int64_t rows;
-    int32_t L;
+    int32_t L;              // valid row length
     int32_t nplanes;
+    int32_t pitch_in;       // elements between rows of S (0 -> L)
+    int32_t pitch_out;      // elements between rows of P (0 -> L)
 } ds_softmax_desc;
 
 // sigma -> EDM coefficients + positional embedding. Reference: networks_edm.py:488-491, :192-198, :315.
@@ -137,7 +146,8 @@ typedef struct ds_posemb_desc {
     int32_t endpoint;       // PositionalEmbedding(endpoint=...)
     int32_t swap_sincos;    // SongUNet swaps to [sin, cos]
     float sigma_data;
-    int32_t pad0;
+    int32_t mode;           // 0: EDM (sigma -> coefficients + embedding of c_noise).  1: LDM timestep_embedding (util.py:151-171):
+                            //    `sigma` holds the timesteps, emb = [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / half); coef untouched
     float* coef;            // [nsig][4] = (c_skip, c_out, c_in, c_noise)
     float* emb;             // [nsig][num_channels]
 } ds_posemb_desc;
@@ -169,6 +179,28 @@ typedef struct ds_prep_input_desc {
     int32_t pad0;
     void* out;              // fp16 [nplanes][B][HW][64]
 } ds_prep_input_desc;
+
+// LayerNorm over the last dim of fp32 [rows][C] -> fp16 hi/lo planes (LDM BasicTransformerBlock.norm1/2/3, attention.py:203-215).
+typedef struct ds_layernorm_desc {
+    const float* src;
+    const float* gamma;
+    const float* beta;
+    void* out;              // fp16 [nplanes][rows][C]
+    int64_t rows;
+    int32_t C;
+    int32_t nplanes;
+    float eps;
+    int32_t pad0;
+} ds_layernorm_desc;
+
+// GEGLU gate: out = x[:, :I] * gelu(x[:, I:]) on fp32 [rows][2I] -> fp16 hi/lo planes [rows][I]  (attention.py:42-44, exact erf GELU).
+typedef struct ds_geglu_desc {
+    const float* src;
+    void* out;
+    int64_t rows;
+    int32_t I;
+    int32_t nplanes;
+} ds_geglu_desc;
 
 // Channel mean of an NHWC fp32 tensor (AMED bottleneck read-out, solvers_amed.py:24,27).
 typedef struct ds_chanmean_desc {
@@ -236,6 +268,8 @@ int ds_posemb_launch(const ds_posemb_desc* d, cudaStream_t stream);
 int ds_linear_launch(const ds_linear_desc* d, cudaStream_t stream);
 int ds_prep_input_launch(const ds_prep_input_desc* d, cudaStream_t stream);
 int ds_chanmean_launch(const ds_chanmean_desc* d, cudaStream_t stream);
+int ds_layernorm_launch(const ds_layernorm_desc* d, cudaStream_t stream);
+int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // Plan records.  The Python plan compiler (diff-sampler_b200/plan.py) lowers one denoiser network at
@@ -243,7 +277,7 @@ int ds_chanmean_launch(const ds_chanmean_desc* d, cudaStream_t stream);
 // and launches them in order.  Pointer fields hold references until resolved:
 //   bits 60..63 = space (0 absolute/NULL, 1 arena, 2 weights, 3 io slot), bits 0..59 = byte offset / slot.
 enum { DS_OP_GEMM = 1, DS_OP_GN_STATS = 2, DS_OP_GN_APPLY = 3, DS_OP_SOFTMAX = 4, DS_OP_POSEMB = 5, DS_OP_LINEAR = 6,
-       DS_OP_PREP_INPUT = 7, DS_OP_CHANMEAN = 8, DS_OP_MEMSET = 9 };
+       DS_OP_PREP_INPUT = 7, DS_OP_CHANMEAN = 8, DS_OP_MEMSET = 9, DS_OP_LAYERNORM = 10, DS_OP_GEGLU = 11 };
 enum { DS_IO_X = 0, DS_IO_D = 1, DS_IO_SIGMA = 2, DS_IO_LABELS = 3, DS_IO_BOTTLENECK = 4, DS_IO_COUNT = 5 };
 
 typedef struct ds_memset_desc {
@@ -264,6 +298,8 @@ typedef struct ds_plan_op {
         ds_prep_input_desc prep_input;
         ds_chanmean_desc chanmean;
         ds_memset_desc memset;
+        ds_layernorm_desc layernorm;
+        ds_geglu_desc geglu;
     } u;
 } ds_plan_op;
 

@@ -39,7 +39,7 @@ def conv_box(H, W):
 
 def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w_planes=2, a2_ptr=0, C2=0,
               out_f32=0, out_h16=0, o_planes=2, ldo=None, bias=0, rowvec=0, rowvec_stride=0, residual=0, ldr=None, scale=1.0,
-              edm=None, bn=None):
+              edm=None, bn=None, s2d=False):
     """3x3 (taps=9) or 1x1 (taps=1) convolution over NHWC fp16 planes [a_planes][Bn][H][W][C] with the
     packed weight matrix [w_planes][Cout_pad][taps*C + C2] (K ordered tap-major, then the aux/skip block).
     Output rows are NHWC pixels: out[pixel][cout] (+ fused epilogue)."""
@@ -52,8 +52,9 @@ def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w
     cout_pad = n_tiles * BN
     ktot = taps * C + C2
     d.a_ptr = a_ptr
-    d.a_dims[:] = [C, W, H, a_planes * Bn]
-    d.a_strides[:] = [C * H16, W * C * H16, H * W * C * H16]
+    cphys = 4 * C if s2d else C          # physical channel extent of the activation tensor
+    d.a_dims[:] = [cphys, W, H, a_planes * Bn]
+    d.a_strides[:] = [cphys * H16, W * cphys * H16, H * W * cphys * H16]
     d.a_box[:] = [64, bw, bh, bnn]
     d.a_plane_n = Bn
     d.a2_ptr = a2_ptr
@@ -74,6 +75,15 @@ def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w
     d.npass = npass
     d.a_mode = 0
     d.conv_H, d.conv_W = H, W
+    if taps == 9:
+        for t in range(9):
+            kh, kw = t // 3, t % 3
+            if s2d:     # stride-2 conv over a space-to-depth input: (shift, phase) of input offset kh-1 in {-1, 0, +1}
+                sh, ph = [(-1, 1), (0, 0), (0, 1)][kh]
+                sw, pw = [(-1, 1), (0, 0), (0, 1)][kw]
+                d.tap_dh[t], d.tap_dw[t], d.tap_cb[t] = sh, sw, (ph * 2 + pw) * C
+            else:
+                d.tap_dh[t], d.tap_dw[t], d.tap_cb[t] = kh - 1, kw - 1, 0
     d.m_valid = Bn * H * W
     d.n_valid = Cout
     d.out_f32 = out_f32
@@ -96,7 +106,7 @@ def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w
 def rows_gemm(a_ptr, a_rows, a_pitch, a_batches, b_ptr, b_rows, b_pitch, b_batches, K, *, num_z, nh=1, m_valid, n_valid,
               npass=3, a_planes=2, b_planes=2, a_c_per_zh=0, a_n_per_zb=0, a_n_per_zh=0, b_k0=0, b_k_per_zh=0, b_row_per_zh=0,
               b_z_per_zb=0, b_z_per_zh=0, out_f32=0, out_h16=0, o_zb=0, o_zh=0, ldo=0, o_plane=0, bias_n=0, bias_m=0,
-              residual=0, ldr=0, scale=1.0, bn=None):
+              residual=0, ldr=0, scale=1.0, bn=None, a_k_valid=None, b_k_valid=None):
     """Batched row-major product  D_z[m][n] = sum_k A_z[m][k] * B_z[n][k].
     A: fp16 planes [a_planes][a_batches][a_rows][a_pitch]; B: fp16 planes [b_planes][b_batches][b_rows][b_pitch].
     z = zb*nh + zh selects the batch entry / column window of each operand (see csrc/ops.h)."""
@@ -104,12 +114,12 @@ def rows_gemm(a_ptr, a_rows, a_pitch, a_batches, b_ptr, b_rows, b_pitch, b_batch
     d = S.GemmDesc()
     BN, n_tiles = (bn, -(-n_valid // bn)) if bn else pick_bn(n_valid)
     d.a_ptr = a_ptr
-    d.a_dims[:] = [a_pitch, a_rows, 1, a_planes * a_batches]
+    d.a_dims[:] = [a_k_valid or a_pitch, a_rows, 1, a_planes * a_batches]       # K beyond the valid extent is zero-filled by TMA
     d.a_strides[:] = [a_pitch * H16, a_rows * a_pitch * H16, a_rows * a_pitch * H16]
     d.a_box[:] = [64, 128, 1, 1]
     d.a_plane_n = a_batches
     d.b_ptr = b_ptr
-    d.b_dims[:] = [b_pitch, b_rows, b_planes * b_batches]
+    d.b_dims[:] = [b_k_valid or b_pitch, b_rows, b_planes * b_batches]
     d.b_strides[:] = [b_pitch * H16, b_rows * b_pitch * H16]
     d.b_plane_batch = b_batches
     d.BN = BN

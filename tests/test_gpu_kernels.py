@@ -406,3 +406,105 @@ def test_conv_epilogue_fused_groupnorm_stats(lib, Bn, H, W, Cout, cpg1, choff2, 
     err2 = (s2 - r2).abs().max().item()
     print(f'fused stats: sink1 err {(s1 - r1).abs().max().item():.3e} sink2 err {err2:.3e} (max {r2.abs().max().item():.1f})')
     assert err2 < 1e-5 * max(1.0, r2.abs().max().item())
+
+
+# --------------------------------------------------------------------------------------------- LDM (Stable Diffusion) building blocks
+def test_layernorm_geglu_softmax_generic(lib):
+    from diff_sampler_b200 import _cstructs as S
+    torch.manual_seed(12)
+    for Cc in (320, 640, 1280):
+        x = torch.randn(50, Cc, device=dev()) * 2 + 0.5
+        g, b = torch.randn(Cc, device=dev()), torch.randn(Cc, device=dev())
+        out = torch.zeros(2, 50, Cc, dtype=torch.float16, device=dev())
+        lib.op_launch(S.LayernormDesc(src=x.data_ptr(), gamma=g.data_ptr(), beta=b.data_ptr(), out=out.data_ptr(), rows=50, C=Cc, nplanes=2, eps=1e-5))
+        sync()
+        ref = F.layer_norm(x.double(), (Cc,), g.double(), b.double(), 1e-5)
+        assert ((out[0].double() + out[1].double()) - ref).abs().max().item() < 2e-5
+    xx = torch.randn(33, 2 * 1280, device=dev()) * 2
+    o = torch.zeros(2, 33, 1280, dtype=torch.float16, device=dev())
+    lib.op_launch(S.GegluDesc(src=xx.data_ptr(), out=o.data_ptr(), rows=33, I=1280, nplanes=2))
+    sync()
+    a, gate = xx.double().chunk(2, dim=-1)
+    assert ((o[0].double() + o[1].double()) - a * F.gelu(gate)).abs().max().item() < 2e-5
+    # softmax over 77 valid keys, input pitch 80, output pitch 128
+    Sm = torch.randn(21, 80, device=dev()) * 3
+    Pm = torch.full((2, 21, 128), 7.0, dtype=torch.float16, device=dev())
+    lib.op_launch(S.SoftmaxDesc(S=Sm.data_ptr(), P=Pm.data_ptr(), rows=21, L=77, nplanes=2, pitch_in=80, pitch_out=128))
+    sync()
+    ref = torch.softmax(Sm[:, :77].double(), -1)
+    assert ((Pm[0, :, :77].double() + Pm[1, :, :77].double()) - ref).abs().max().item() < 2e-6
+    # LDM timestep embedding
+    t = torch.tensor([999.0, 500.5, 3.0], device=dev())
+    emb = torch.zeros(3, 320, device=dev())
+    lib.op_launch(S.PosembDesc(sigma=t.data_ptr(), nsig=3, num_channels=320, endpoint=0, swap_sincos=0, sigma_data=0.5, mode=1, coef=0,
+                               emb=emb.data_ptr()))
+    sync()
+    import math
+    freqs = torch.exp(-math.log(10000) * torch.arange(160, dtype=torch.float32, device=dev()) / 160)
+    args = t[:, None] * freqs[None]
+    refe = torch.cat([args.cos(), args.sin()], dim=-1)
+    assert (emb - refe).abs().max().item() < 2e-4          # arguments up to ~1000 rad: fp32 range reduction differs at the 1e-5 level
+
+
+@pytest.mark.parametrize('Bn,H,Cin,Cout', [(3, 16, 64, 128), (2, 32, 128, 64)])
+def test_stride2_conv_via_space_to_depth(lib, Bn, H, Cin, Cout):
+    """LDM Downsample (3x3, stride 2, pad 1): space-to-depth repack + the same GEMM kernel with per-tap (shift, phase) table."""
+    from diff_sampler_b200 import _cstructs as S
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(13)
+    x = torch.randn(Bn, Cin, H, H, device=dev())
+    w = torch.randn(Cout, Cin, 3, 3, device=dev()) / (3 * Cin ** 0.5)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    s2d = torch.zeros(2, Bn, H // 2, H // 2, 4 * Cin, dtype=torch.float16, device=dev())
+    lib.op_launch(S.GnApplyDesc(src0=xn.data_ptr(), src1=0, C0=Cin, C1=0, H=H, W=H, B=Bn, groups=32, sums=0, gamma=0, beta=0, eps=0, silu=0,
+                                ada=0, ada_stride=0, resample=3, nplanes=2, out_act=0, out_raw=s2d.data_ptr(), out_raw_f32=0))
+    wp = G.pack_conv_weight(w.cpu()).to(dev())
+    Ho = H // 2
+    out = torch.full((Bn * Ho * Ho, Cout), float('nan'), device=dev())
+    d, _ = G.conv_gemm(s2d.data_ptr(), Bn, Ho, Ho, Cin, wp.data_ptr(), Cout, taps=9, npass=3, out_f32=out.data_ptr(), s2d=True)
+    lib.op_launch(d)
+    sync()
+    ref = F.conv2d(x.double(), w.double(), stride=2, padding=1).permute(0, 2, 3, 1).reshape(Bn * Ho * Ho, Cout)
+    err = (out.double() - ref).abs().max().item()
+    print(f'stride-2 conv {Bn}x{H}x{H} {Cin}->{Cout}: err {err:.3e}')
+    assert err < 3e-5 * ref.abs().max().item()
+
+
+def test_cross_attention_gemms_with_77_keys(lib):
+    """S = Q K^T and O = P V with 77 context tokens: K extents that are not multiples of 64 rely on TMA zero fill."""
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(14)
+    Bn, L, nh, d, T = 2, 256, 2, 64, 77
+    Cc = nh * d
+    q = torch.randn(Bn, L, Cc, device=dev())
+    k = torch.randn(Bn, T, Cc, device=dev())
+    vt = torch.zeros(Bn, Cc, 128, device=dev())
+    vt[:, :, :T] = torch.randn(Bn, Cc, T, device=dev())
+    vt[:, :, T:] = float('nan')                         # garbage beyond the valid keys must never be read
+    qp, kp = planes(q), planes(k)
+    vtp = torch.stack([vt.half(), (vt - vt.half().float()).half()])
+    Smat = torch.full((Bn * nh, L, 80), float('nan'), device=dev())
+    dS, _ = G.rows_gemm(qp.data_ptr(), L, Cc, Bn, kp.data_ptr(), T, Cc, Bn, d, num_z=Bn * nh, nh=nh, m_valid=L, n_valid=T,
+                        a_c_per_zh=d, a_n_per_zb=1, b_k_per_zh=d, b_z_per_zb=1, out_f32=Smat.data_ptr(), o_zb=nh * L * 80, o_zh=L * 80,
+                        ldo=80, scale=d ** -0.5)
+    lib.op_launch(dS)
+    sync()
+    qh = q.reshape(Bn, L, nh, d).permute(0, 2, 1, 3).double()
+    kh = k.reshape(Bn, T, nh, d).permute(0, 2, 1, 3).double()
+    refS = (qh @ kh.transpose(-1, -2) * d ** -0.5).reshape(Bn * nh, L, T)
+    assert (Smat[:, :, :T].double() - refS).abs().max().item() < 3e-5 * refS.abs().max().item()
+    Pm = torch.zeros(Bn * nh, L, 128, device=dev())
+    Pm[:, :, :T] = torch.softmax(Smat[:, :, :T], -1)
+    Pm[:, :, T:] = float('nan')
+    Pp = torch.stack([Pm.half(), (Pm - Pm.half().float()).half()])
+    O = torch.zeros(2, Bn, L, Cc, dtype=torch.float16, device=dev())
+    dO, _ = G.rows_gemm(Pp.data_ptr(), L, 128, Bn * nh, vtp.data_ptr(), Cc, 128, Bn, 128, num_z=Bn * nh, nh=nh, m_valid=L, n_valid=d,
+                        a_n_per_zb=nh, a_n_per_zh=1, b_row_per_zh=d, b_z_per_zb=1, out_h16=O.data_ptr(), o_zb=L * Cc, o_zh=d, ldo=Cc,
+                        o_plane=Bn * L * Cc, a_k_valid=T, b_k_valid=T)
+    lib.op_launch(dO)
+    sync()
+    v = vt[:, :, :T].reshape(Bn, nh, d, T).double()
+    refO = (Pm[:, :, :T].reshape(Bn, nh, L, T).double() @ v.transpose(-1, -2)).permute(0, 2, 1, 3).reshape(Bn, L, Cc)
+    got = O[0].double() + O[1].double()
+    assert torch.isfinite(got).all()
+    assert (got - refO).abs().max().item() < 3e-5 * max(1.0, refO.abs().max().item())
