@@ -211,6 +211,73 @@ np.savez_compressed(sys.argv[1], **G)
     return out
 
 
+def ldm_part():
+    """Stable-Diffusion-style eps-net + CFGPrecond from the real reference, loaded with oracle/ldm_oracle.make_params weights."""
+    import types
+    sys.path.insert(0, os.path.join(REF, 'diff-solvers-main'))
+    sys.path.insert(0, ROOT)
+    oc = types.ModuleType('omegaconf')
+    lc = types.ModuleType('omegaconf.listconfig')
+    lc.ListConfig = type('ListConfig', (list,), {})
+    oc.listconfig = lc
+    sys.modules.setdefault('omegaconf', oc)
+    sys.modules.setdefault('omegaconf.listconfig', lc)
+    from models.ldm.modules.diffusionmodules.openaimodel import UNetModel
+    from models.networks_edm import CFGPrecond
+    from oracle import edm_oracle as O
+    from oracle import ldm_oracle as LO
+    G = {}
+    for name in ('tiny_ldm',):
+        P, cfg = LO.make_params(name, seed=0)
+        unet = UNetModel(image_size=32, in_channels=cfg['in_channels'], out_channels=cfg['out_channels'], model_channels=cfg['model_channels'],
+                         attention_resolutions=list(cfg['attention_resolutions']), num_res_blocks=cfg['num_res_blocks'],
+                         channel_mult=list(cfg['channel_mult']), num_heads=cfg['num_heads'], use_spatial_transformer=True,
+                         transformer_depth=1, context_dim=cfg['context_dim'], use_checkpoint=False, legacy=False).eval().requires_grad_(False)
+        sd = unet.state_dict()
+        assert list(sd.keys()) == list(P.keys()), [k for k in sd if k not in P][:5] + [k for k in P if k not in sd][:5]
+        for k in sd:
+            assert tuple(sd[k].shape) == tuple(P[k].shape), (k, sd[k].shape, P[k].shape)
+        unet.load_state_dict(P)
+
+        class Shim(torch.nn.Module):
+            def __init__(self, u):
+                super().__init__()
+                self.u = u
+                self.alphas_cumprod = LO.make_alphas_cumprod()
+
+            def apply_model(self, x, t, cond):
+                return self.u(x, t, context=cond)
+        net = CFGPrecond(Shim(unet), img_resolution=cfg['img_resolution'], img_channels=cfg['in_channels'], guidance_rate=7.5,
+                         guidance_type='classifier-free', label_dim=True).eval()
+        G[f'ldm/{name}/sigma_range'] = np.array([net.sigma_min, net.sigma_max])
+        B = 2
+        R = cfg['img_resolution']
+        x = O.stacked_randn(range(B), (cfg['in_channels'], R, R))
+        g = torch.Generator().manual_seed(5)
+        c = torch.randn(B, 77, cfg['context_dim'], generator=g)
+        uc = torch.randn(B, 77, cfg['context_dim'], generator=g)
+        G[f'ldm/{name}/c'], G[f'ldm/{name}/uc'] = c.numpy(), uc.numpy()
+        with torch.no_grad():
+            for sigma in (10.0, 0.5):
+                G[f'ldm/{name}/D/{sigma}'] = net(x * sigma, torch.tensor([sigma]), condition=c, unconditional_condition=uc).numpy()
+            G[f'ldm/{name}/D/nocfg'] = net(x * 2.0, torch.tensor([2.0]), condition=c, unconditional_condition=None).numpy()
+            sig = torch.tensor([3.0, 0.4])
+            G[f'ldm/{name}/D/persample'] = net(x * sig[:, None, None, None], sig, condition=c, unconditional_condition=uc).numpy()
+            G[f'ldm/{name}/eps'] = unet(x, torch.tensor([500.0, 20.0]), context=c).numpy()
+            sys.path.insert(0, os.path.join(REF, 'diff-solvers-main'))
+            import solver_utils as RU
+            import solvers as RS
+            ts = RU.get_schedule(5, net.sigma_min, net.sigma_max, device=torch.device('cpu'), schedule_type='discrete', schedule_rho=1, net=net)
+            G[f'ldm/{name}/sched_discrete'] = ts.numpy()
+            out = RS.dpm_pp_sampler(net, x, condition=c, unconditional_condition=uc, num_steps=5, sigma_min=net.sigma_min, sigma_max=net.sigma_max,
+                                    schedule_type='discrete', schedule_rho=1, max_order=2, predict_x0=False)
+            G[f'ldm/{name}/sample_dpmpp'] = out.numpy()
+    # known-answer anchor from the reference docs (amed-solver-main/example.ipynb): sigma range of SD
+    out = os.path.join(OUT, 'ref_ldm.npz')
+    np.savez_compressed(out, **G)
+    return out
+
+
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
@@ -220,3 +287,4 @@ if __name__ == '__main__':
     np.savez_compressed(os.path.join(OUT, 'ref_core.npz'), **G)
     print('wrote ref_core.npz with', len(G), 'arrays')
     print('wrote', amed_part())
+    print('wrote', ldm_part())

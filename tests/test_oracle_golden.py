@@ -159,3 +159,32 @@ def test_amed_samplers_match_reference(ci):
     got = AO.sample_amed(net, lat, solver, W, cfg, **kw).numpy()
     err = np.abs(got - ref).max()
     assert err <= 2e-5 * max(1.0, np.abs(ref).max()), (solver, kw, err)
+
+
+def test_ldm_oracle_matches_reference():
+    """Stable-Diffusion-style eps-net + CFGPrecond (tiny config, same structure as v1.5) vs outputs of the real reference classes."""
+    from oracle import ldm_oracle as LO
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_ldm.npz'))
+    P, cfg = LO.make_params('tiny_ldm')
+    net = LO.OracleCFGNet(P, cfg)
+    assert abs(net.sigma_min - 0.0292) < 1e-4 and abs(net.sigma_max - 14.6146) < 1e-3        # amed-solver-main/example.ipynb
+    assert np.allclose([net.sigma_min, net.sigma_max], d['ldm/tiny_ldm/sigma_range'], rtol=1e-6)
+    x = O.stacked_randn(range(2), (4, 16, 16))
+    c, uc = torch.from_numpy(d['ldm/tiny_ldm/c']), torch.from_numpy(d['ldm/tiny_ldm/uc'])
+    with torch.no_grad():
+        for sigma in (10.0, 0.5):
+            got = net(x * sigma, torch.tensor([sigma]), condition=c, unconditional_condition=uc).numpy()
+            ref = d[f'ldm/tiny_ldm/D/{sigma}']
+            assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+        got = net(x * 2.0, torch.tensor([2.0]), condition=c).numpy()
+        assert np.abs(got - d['ldm/tiny_ldm/D/nocfg']).max() <= 1e-5 * np.abs(d['ldm/tiny_ldm/D/nocfg']).max()
+        sig = torch.tensor([3.0, 0.4])
+        got = net(x * sig[:, None, None, None], sig, condition=c, unconditional_condition=uc).numpy()
+        assert np.abs(got - d['ldm/tiny_ldm/D/persample']).max() <= 1e-5 * np.abs(d['ldm/tiny_ldm/D/persample']).max()
+        eps = LO.unet_forward(P, cfg, x, torch.tensor([500.0, 20.0]), c).numpy()
+        assert np.abs(eps - d['ldm/tiny_ldm/eps']).max() <= 1e-5 * np.abs(d['ldm/tiny_ldm/eps']).max()
+        ts = SO.get_schedule(5, net.sigma_min, net.sigma_max, schedule_type='discrete', schedule_rho=1, net=net)
+        assert np.array_equal(ts.numpy(), d['ldm/tiny_ldm/sched_discrete'])
+        out = SO.sample(net, x, 'dpm_pp', condition=c, unconditional_condition=uc, num_steps=5, sigma_min=net.sigma_min,
+                        sigma_max=net.sigma_max, schedule_type='discrete', schedule_rho=1, max_order=2, predict_x0=False).numpy()
+        assert np.abs(out - d['ldm/tiny_ldm/sample_dpmpp']).max() <= 1e-5 * np.abs(d['ldm/tiny_ldm/sample_dpmpp']).max()
