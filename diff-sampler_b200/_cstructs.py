@@ -9,7 +9,7 @@ F32 = C.c_float
 
 DS_OP_GEMM, DS_OP_GN_STATS, DS_OP_GN_APPLY, DS_OP_SOFTMAX, DS_OP_POSEMB, DS_OP_LINEAR = 1, 2, 3, 4, 5, 6
 DS_OP_PREP_INPUT, DS_OP_CHANMEAN, DS_OP_MEMSET, DS_OP_LAYERNORM, DS_OP_GEGLU = 7, 8, 9, 10, 11
-DS_IO_X, DS_IO_D, DS_IO_SIGMA, DS_IO_LABELS, DS_IO_BOTTLENECK = 0, 1, 2, 3, 4
+DS_IO_X, DS_IO_D, DS_IO_SIGMA, DS_IO_LABELS, DS_IO_BOTTLENECK, DS_IO_CTX = 0, 1, 2, 3, 4, 5
 DS_M_X0, DS_M_EPS, DS_M_DIV, DS_M_NONE = 0, 1, 2, 3
 
 SPACE_ABS, SPACE_ARENA, SPACE_WEIGHTS, SPACE_IO = 0, 1, 2, 3
@@ -65,7 +65,7 @@ class LinearDesc(C.Structure):
 
 class PrepInputDesc(C.Structure):
     _fields_ = [('x', P), ('coef', P), ('coef_stride', I32), ('B', I32), ('C', I32), ('HW', I32), ('nplanes', I32),
-                ('pad0', I32), ('out', P)]
+                ('x_batch', I32), ('out', P)]
 
 
 class ChanmeanDesc(C.Structure):

@@ -316,14 +316,16 @@ __global__ void prep_input_kernel(ds_prep_input_desc d) {
     const long long px = idx >> 3;
     const int n = (int)(px / d.HW);
     const int hw = (int)(px - (long long)n * d.HW);
-    const float cin = d.coef[n * d.coef_stride + 2];
+    const int xb = d.x_batch > 0 ? d.x_batch : d.B;
+    const int nx = n % xb;
+    const float cin = d.coef[nx * d.coef_stride + 2];
     __align__(16) __half hi[8];
     __align__(16) __half lo[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c8 * 8 + j;
         float v = 0.f;
-        if (c < d.C) v = cin * d.x[((long long)n * d.C + c) * d.HW + hw];
+        if (c < d.C) v = cin * d.x[((long long)nx * d.C + c) * d.HW + hw];
         split_h16(v, hi[j], lo[j]);
     }
     __half* o = reinterpret_cast<__half*>(d.out);

@@ -203,11 +203,19 @@ void ds_unet_destroy(ds_unet* u) {
     delete u;
 }
 
+int ds_unet_forward_io(ds_unet* u, const void* const* io_in, int n_io, void* stream);
+
 int ds_unet_forward(ds_unet* u, const float* x, const float* sigma, const float* labels, float* out_D, float* out_bottleneck,
                     void* stream) {
+    const void* io[DS_IO_COUNT] = {x, out_D, sigma, labels, out_bottleneck, nullptr};
+    return ds_unet_forward_io(u, io, DS_IO_COUNT, stream);
+}
+
+int ds_unet_forward_io(ds_unet* u, const void* const* io_in, int n_io, void* stream) {
     if (!u) return fail(-1, "ds_unet_forward: null handle");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const void* io[DS_IO_COUNT] = {x, out_D, sigma, labels, out_bottleneck};
+    const void* io[DS_IO_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < n_io && k < DS_IO_COUNT; ++k) io[k] = io_in[k];
     for (const IoFix& fx : u->fixes) {
         if (fx.slot < 0 || fx.slot >= DS_IO_COUNT) return fail(-7, "ds_unet_forward: bad io slot");
         void** field = reinterpret_cast<void**>(reinterpret_cast<char*>(&u->ops[fx.op]) + fx.field_off);

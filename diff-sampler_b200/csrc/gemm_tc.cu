@@ -154,6 +154,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
         const int HW = p.rows_per_sample;
         const long long n = grow_in_z / HW;
         const long long hw = grow_in_z % HW;
+        if (p.edm_out == 2) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const int c = col0 + j;
+                if (c < p.edm_C) p.edm_D[(n * p.edm_C + c) * HW + hw] = r[j];
+            }
+            return;
+        }
         const float cskip = __ldg(p.edm_coef + n * p.edm_coef_stride + 0);
         const float cout = __ldg(p.edm_coef + n * p.edm_coef_stride + 1);
 #pragma unroll

@@ -64,7 +64,7 @@ typedef struct ds_gemm_desc {
     int64_t ldr;
     float scale;
     // EDM output fold (final conv): D[n][c][hw] = cskip[n]*x[n][c][hw] + cout[n]*v   (NCHW fp32)
-    int32_t edm_out;
+    int32_t edm_out;        // 1: EDM combine below; 2: plain NCHW fp32 write of the epilogue value (LDM eps output)
     const float* edm_x;
     const float* edm_coef;  // [nsig][4] = (c_skip, c_out, c_in, c_noise)
     int32_t edm_coef_stride;// 0 (one sigma) or 4 (per-sample)
@@ -176,7 +176,7 @@ typedef struct ds_prep_input_desc {
     int32_t coef_stride;    // 0 or 4
     int32_t B, C, HW;
     int32_t nplanes;
-    int32_t pad0;
+    int32_t x_batch;        // 0 or B: batch of x; sample n reads x[n % x_batch] (classifier-free guidance evaluates [x, x])
     void* out;              // fp16 [nplanes][B][HW][64]
 } ds_prep_input_desc;
 
@@ -278,7 +278,7 @@ int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream);
 //   bits 60..63 = space (0 absolute/NULL, 1 arena, 2 weights, 3 io slot), bits 0..59 = byte offset / slot.
 enum { DS_OP_GEMM = 1, DS_OP_GN_STATS = 2, DS_OP_GN_APPLY = 3, DS_OP_SOFTMAX = 4, DS_OP_POSEMB = 5, DS_OP_LINEAR = 6,
        DS_OP_PREP_INPUT = 7, DS_OP_CHANMEAN = 8, DS_OP_MEMSET = 9, DS_OP_LAYERNORM = 10, DS_OP_GEGLU = 11 };
-enum { DS_IO_X = 0, DS_IO_D = 1, DS_IO_SIGMA = 2, DS_IO_LABELS = 3, DS_IO_BOTTLENECK = 4, DS_IO_COUNT = 5 };
+enum { DS_IO_X = 0, DS_IO_D = 1, DS_IO_SIGMA = 2, DS_IO_LABELS = 3, DS_IO_BOTTLENECK = 4, DS_IO_CTX = 5, DS_IO_COUNT = 6 };
 
 typedef struct ds_memset_desc {
     void* ptr;

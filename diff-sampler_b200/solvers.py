@@ -11,6 +11,7 @@ import math
 import torch
 
 from . import _cstructs as S
+from .ldm_net import B200LDMNet
 from .net import B200Net
 from .solver_utils import *                       # noqa: F401,F403  (the reference does `from solver_utils import *`)
 from .solver_utils import (dpm_pp_coefs, dyn_threshold, get_schedule, solver_update, unipc_coefs)
@@ -21,7 +22,7 @@ _NATIVE_CLASSES = ('SongUNet', 'DhariwalUNet')
 def as_native(net, precision=None):
     """B200Net for `net`: itself, a cached compilation of a reference EDMPrecond module, or — for anything else
     (e.g. CFGPrecond / foreign callables) — the object unchanged (its D(x, sigma) is then consumed by the native update kernels)."""
-    if isinstance(net, B200Net):
+    if isinstance(net, (B200Net, B200LDMNet)):
         return net
     cached = getattr(net, '_b200_native', None)
     if cached is not None:
@@ -88,6 +89,8 @@ class _Loop:
         out = self.D if out is None else out
         if isinstance(net, B200Net):
             return net(x, sig, class_labels=self.kw['class_labels'], out=out)
+        if isinstance(net, B200LDMNet):
+            return net(x, sig, condition=self.kw['condition'], unconditional_condition=self.kw['unconditional_condition'], out=out)
         if hasattr(net, 'guidance_type'):
             r = net(x, sig, condition=self.kw['condition'], unconditional_condition=self.kw['unconditional_condition'])
         else:

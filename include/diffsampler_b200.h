@@ -53,6 +53,11 @@ void ds_unet_destroy(ds_unet* u);
 int ds_unet_forward(ds_unet* u, const float* x, const float* sigma, const float* labels, float* out_D,
                     float* out_bottleneck, void* stream);
 
+/* Same with an explicit io table {x, out_D, sigma_or_timesteps, labels_or_coef, out_bottleneck, context}: used by the latent-diffusion
+ * (CFGPrecond + UNetModel, networks_edm.py:670-696, openaimodel.py:710-741) plans, whose inputs are the timesteps c_noise[Bt], a
+ * coefficient table [B][4] holding c_in, and the text context [Bt, 77, context_dim]; out_D receives eps in NCHW. */
+int ds_unet_forward_io(ds_unet* u, const void* const* io, int n_io, void* stream);
+
 /* Debug/test access to the workspace arena (device -> host copy, synchronises the stream). */
 int ds_unet_debug_read(ds_unet* u, size_t arena_offset, void* host_dst, size_t bytes, void* stream);
 /* Number of kernels launched by the last ds_unet_forward on this handle. */

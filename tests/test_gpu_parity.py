@@ -305,3 +305,97 @@ def test_fullsize_batch_independence_and_properties():
     assert abs(frac - 0.005) < 0.001
     y2 = U.dynamic_thresholding_fn(y)
     assert (y2 - y).abs().max().item() == 0.0
+
+
+# --------------------------------------------------------------------------------------------- latent diffusion (config 5)
+def _ldm_pair(name='tiny_ldm', guidance=7.5, precision='fp16x3'):
+    from oracle import ldm_oracle as LO
+    from diff_sampler_b200.ldm_net import B200LDMNet
+    P, cfg = LO.make_params(name)
+    on = LO.OracleCFGNet(P, cfg, guidance_rate=guidance)
+    nat = B200LDMNet(P, img_resolution=cfg['img_resolution'], img_channels=cfg['in_channels'], num_heads=cfg['num_heads'],
+                     guidance_rate=guidance, precision=precision, device=_dev())
+    return on, nat, cfg
+
+
+def test_ldm_eps_net_blocks_localise():
+    """Per-module activations of the native latent-diffusion eps-net vs the oracle (names the first module that drifts)."""
+    from oracle import edm_oracle as O
+    on, nat, cfg = _ldm_pair()
+    B, R = 2, cfg['img_resolution']
+    x = O.stacked_randn(range(B), (4, R, R)) * 2.0
+    g = torch.Generator().manual_seed(5)
+    c = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    uc = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    on.taps = {}
+    ref = on(x, torch.tensor([2.0]), condition=c, unconditional_condition=uc)
+    got = nat(x.to(_dev()), torch.tensor([2.0], device=_dev()), condition=c.to(_dev()), unconditional_condition=uc.to(_dev()))
+    torch.cuda.synchronize()
+    h, pl = nat._plan(B, 2 * B, 1)
+    worst = 0.0
+    for name, t in on.taps.items():
+        key = 'h:' + name
+        if key not in pl.arena_offsets:
+            continue
+        n, cch, hh, ww = t.shape
+        buf = torch.empty(n * cch * hh * ww)
+        import ctypes as C
+        from diff_sampler_b200 import _lib
+        _lib.check(nat.lib.ds_unet_debug_read(h, pl.arena_offsets[key], buf.data_ptr(), buf.numel() * 4, None), 'debug_read')
+        mine = buf.reshape(n, hh, ww, cch).permute(0, 3, 1, 2)
+        err = (mine - t).abs().max().item()
+        worst = max(worst, err / max(1.0, t.abs().max().item()))
+        print(f'{name:40s} max|ref| {t.abs().max().item():9.3f} err {err:.3e}')
+    e = (got.cpu() - ref).abs().max().item()
+    print(f'tiny_ldm D (cfg 7.5): err {e:.3e} (max|D| {ref.abs().max().item():.2f})')
+    assert worst < 1e-4 and e < TOL * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('guidance', [7.5, 1.0])
+def test_ldm_cfg_denoiser_parity(guidance):
+    from oracle import edm_oracle as O
+    on, nat, cfg = _ldm_pair(guidance=guidance)
+    B, R = 3, cfg['img_resolution']
+    x0 = O.stacked_randn(range(B), (4, R, R))
+    g = torch.Generator().manual_seed(6)
+    c = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    uc = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    cd, ucd = c.to(_dev()), uc.to(_dev())
+    for sigma in (10.0, 0.5):
+        ref = on(x0 * sigma, torch.tensor([sigma]), condition=c, unconditional_condition=uc)
+        got = nat((x0 * sigma).to(_dev()), torch.tensor([sigma], device=_dev()), condition=cd, unconditional_condition=ucd).cpu()
+        err = (got - ref).abs().max().item()
+        print(f'ldm g={guidance} sigma={sigma}: err {err:.3e} (max|D| {ref.abs().max().item():.1f})')
+        assert err < TOL * max(1.0, ref.abs().max().item())
+    sig = torch.tensor([3.0, 0.4, 9.0])
+    ref = on(x0 * sig[:, None, None, None], sig, condition=c, unconditional_condition=uc)
+    got = nat((x0 * sig[:, None, None, None]).to(_dev()), sig.to(_dev()), condition=cd, unconditional_condition=ucd).cpu()
+    err = (got - ref).abs().max().item()
+    print(f'ldm g={guidance} per-sample sigma: err {err:.3e}')
+    assert err < TOL * max(1.0, ref.abs().max().item())
+    # sigma <-> t mapping and the 'discrete' schedule (solver_utils.py:42-48)
+    from oracle import solvers_oracle as SO
+    from diff_sampler_b200 import solver_utils
+    assert abs(nat.sigma_min - on.sigma_min) < 1e-6 and abs(nat.sigma_max - on.sigma_max) < 1e-4
+    ts_ref = SO.get_schedule(6, on.sigma_min, on.sigma_max, schedule_type='discrete', schedule_rho=1, net=on)
+    ts = solver_utils.get_schedule(6, nat.sigma_min, nat.sigma_max, device=_dev(), schedule_type='discrete', schedule_rho=1, net=nat)
+    assert (ts.cpu() - ts_ref).abs().max().item() <= 2e-5 * ts_ref.abs().max().item()
+
+
+def test_ldm_sampler_parity():
+    """BASELINE config-5 shape: DPM-Solver++(2M) eps-mode on the 'discrete' schedule with classifier-free guidance."""
+    from oracle import edm_oracle as O
+    from oracle import solvers_oracle as SO
+    from diff_sampler_b200 import solvers
+    on, nat, cfg = _ldm_pair()
+    B, R = 2, cfg['img_resolution']
+    lat = O.stacked_randn(range(B), (4, R, R))
+    g = torch.Generator().manual_seed(7)
+    c = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    uc = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    kw = dict(num_steps=5, sigma_min=on.sigma_min, sigma_max=on.sigma_max, schedule_type='discrete', schedule_rho=1, max_order=2, predict_x0=False)
+    ref = SO.sample(on, lat, 'dpm_pp', condition=c, unconditional_condition=uc, **kw)
+    got = solvers.dpm_pp_sampler(nat, lat.to(_dev()), condition=c.to(_dev()), unconditional_condition=uc.to(_dev()), **kw).cpu()
+    err = (got - ref).abs().max().item()
+    print(f'ldm dpm_pp(2M) NFE=4 cfg: err {err:.3e} (max|x| {ref.abs().max().item():.1f})')
+    assert err < TOL * max(1.0, ref.abs().max().item())
