@@ -22,8 +22,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-GFLOP_PER_IMG_NFE = {'cifar10': 42.38, 'ffhq': 83.73, 'imagenet64': 219.33}      # BASELINE.md section 2 (2 FLOP per MAC)
-SOLVER_NFE = {'heun': lambda n: 2 * (n - 1), 'euler': lambda n: n - 1, 'ipndm': lambda n: n - 1, 'dpm_pp': lambda n: n - 1}
+GFLOP_PER_IMG_NFE = {'cifar10': 42.38, 'ffhq': 83.73, 'imagenet64': 219.33, 'sd15': 2 * 803.27}      # BASELINE.md section 2 (2 FLOP per MAC; SD: x2 under CFG)
+SOLVER_NFE = {'heun': lambda n: 2 * (n - 1), 'euler': lambda n: n - 1, 'ipndm': lambda n: n - 1, 'dpm_pp': lambda n: n - 1,
+              'amed_dpm_pp': lambda n: 2 * (n - 1) - 1}      # AMED plug-in with AFS: num_steps=4 -> NFE=5 (amed-solver-main/README.md)
 
 
 def parse():
@@ -32,8 +33,8 @@ def parse():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='native', choices=['native', 'reference'])
-    ap.add_argument('--net', default='cifar10')
-    ap.add_argument('--solver', default='heun')
+    ap.add_argument('--net', default='cifar10', help='cifar10 | ffhq | imagenet64 | sd15')
+    ap.add_argument('--solver', default='heun', help='heun | euler | ipndm | dpm_pp | amed_dpm_pp (sd15)')
     ap.add_argument('--num_steps', type=int, default=10)
     ap.add_argument('--batch', type=int, default=512, help='images per GPU per step')
     ap.add_argument('--precision', default='fp16x3', choices=['fp16x3', 'fp16'])
@@ -183,16 +184,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    net = B200Net.from_config(args.net, seed=0, dezero=True, precision=args.precision, device=dev)
-    sampler = getattr(solvers, args.solver + '_sampler')
     B = args.batch
-    shape = (B, net.img_channels, net.img_resolution, net.img_resolution)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    latents = torch.randn(shape, generator=gen, device=dev)
     labels = None
-    if net.label_dim:
-        labels = torch.eye(net.label_dim, device=dev)[torch.randint(net.label_dim, (B,), generator=gen, device=dev)]
-    kw = dict(class_labels=labels, num_steps=args.num_steps, sigma_min=0.002, sigma_max=80, schedule_type='polynomial', schedule_rho=7)
+    if args.net == 'sd15':
+        net, sampler, kw = build_sd15(args, dev, B, gen)
+    else:
+        net = B200Net.from_config(args.net, seed=0, dezero=True, precision=args.precision, device=dev)
+        sampler = getattr(solvers, args.solver + '_sampler')
+    shape = (B, net.img_channels, net.img_resolution, net.img_resolution)
+    latents = torch.randn(shape, generator=gen, device=dev)
+    if args.net != 'sd15':
+        if net.label_dim:
+            labels = torch.eye(net.label_dim, device=dev)[torch.randint(net.label_dim, (B,), generator=gen, device=dev)]
+        kw = dict(class_labels=labels, num_steps=args.num_steps, sigma_min=0.002, sigma_max=80, schedule_type='polynomial', schedule_rho=7)
 
     def run_step():
         return sampler(net, latents, **kw)
@@ -284,12 +289,115 @@ def main():
         dist.destroy_process_group()
 
 
+def build_sd15(args, dev, B, gen):
+    """BASELINE config 5: SD-v1.5-sized eps-net (seeded random weights), CFG 7.5, random [B,77,768] contexts, AMED plug-in on DPM-Solver++(2M),
+    num_steps=4 with AFS => NFE=5, 'discrete' schedule rho=1 (amed-solver-main/launch.sh:57)."""
+    import math
+    import torch
+    from diff_sampler_b200 import solvers, solvers_amed
+    from diff_sampler_b200.amed_predictor import AMEDPredictor
+    from diff_sampler_b200.ldm_net import B200LDMNet
+    shapes = sd15_param_shapes()
+    g = torch.Generator().manual_seed(777)
+    params = {}
+    for k, shp in shapes.items():
+        if len(shp) == 1:
+            v = (torch.rand(shp, generator=g) * 2 - 1) * 0.1
+            params[k] = v + 1.0 if k.endswith('.weight') else v
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            params[k] = (torch.rand(shp, generator=g) * 2 - 1) * math.sqrt(3.0 / fan_in)
+    net = B200LDMNet(params, img_resolution=64, img_channels=4, num_heads=8, guidance_rate=7.5, precision=args.precision, device=dev)
+    c = torch.randn(B, 77, 768, generator=gen, device=dev)
+    uc = torch.randn(B, 77, 768, generator=gen, device=dev)
+    kw = dict(condition=c, unconditional_condition=uc, num_steps=args.num_steps, sigma_min=net.sigma_min, sigma_max=net.sigma_max,
+              schedule_type='discrete', schedule_rho=1)
+    if args.solver == 'amed_dpm_pp':
+        tg = torch.Generator().manual_seed(4242)
+        W = {'map_layer0.weight': torch.randn(8, 8, generator=tg) * 0.3, 'map_layer0.bias': torch.zeros(8),
+             'enc_layer0.weight': torch.randn(128, 64, generator=tg) * 0.1, 'enc_layer0.bias': torch.zeros(128),
+             'enc_layer1.weight': torch.randn(4, 128, generator=tg) * 0.1, 'enc_layer1.bias': torch.zeros(4),
+             'fc_r.weight': torch.randn(1, 20, generator=tg) * 0.2, 'fc_r.bias': torch.zeros(1),
+             'fc_scale_time.weight': torch.randn(1, 20, generator=tg) * 0.2, 'fc_scale_time.bias': torch.zeros(1)}
+        pred = AMEDPredictor(W, scale_dir=0.0, scale_time=0.2).to(dev)
+        kw.update(AMED_predictor=pred, afs=True, max_order=2, predict_x0=False)
+        return net, solvers_amed.dpm_pp_sampler, kw
+    return net, getattr(solvers, args.solver + '_sampler'), kw
+
+
+def sd15_param_shapes():
+    """UNetModel.state_dict() names/shapes for models/ldm/configs/stable-diffusion/v1-inference.yaml:29-44 (859.5 M parameters)."""
+    from collections import OrderedDict
+    mc, mult, nrb, attn_res, heads, ctx = 320, (1, 2, 4, 4), 2, (4, 2, 1), 8, 768
+    ted = mc * 4
+    sh = OrderedDict()
+
+    def lin(n, fi, fo, bias=True):
+        sh[n + '.weight'] = (fo, fi)
+        if bias:
+            sh[n + '.bias'] = (fo,)
+
+    def conv(n, ci, co, k):
+        sh[n + '.weight'] = (co, ci, k, k)
+        sh[n + '.bias'] = (co,)
+
+    def norm(n, c):
+        sh[n + '.weight'] = (c,)
+        sh[n + '.bias'] = (c,)
+
+    def res(n, ci, co):
+        norm(n + '.in_layers.0', ci); conv(n + '.in_layers.2', ci, co, 3); lin(n + '.emb_layers.1', ted, co)
+        norm(n + '.out_layers.0', co); conv(n + '.out_layers.3', co, co, 3)
+        if ci != co:
+            conv(n + '.skip_connection', ci, co, 1)
+
+    def attn(n, ch):
+        t = n + '.transformer_blocks.0'
+        norm(n + '.norm', ch); conv(n + '.proj_in', ch, ch, 1)
+        for a, cd in (('attn1', ch),):
+            lin(f'{t}.{a}.to_q', ch, ch, False); lin(f'{t}.{a}.to_k', cd, ch, False); lin(f'{t}.{a}.to_v', cd, ch, False); lin(f'{t}.{a}.to_out.0', ch, ch)
+        lin(f'{t}.ff.net.0.proj', ch, ch * 8); lin(f'{t}.ff.net.2', ch * 4, ch)
+        lin(f'{t}.attn2.to_q', ch, ch, False); lin(f'{t}.attn2.to_k', ctx, ch, False); lin(f'{t}.attn2.to_v', ctx, ch, False); lin(f'{t}.attn2.to_out.0', ch, ch)
+        for k in (1, 2, 3):
+            norm(f'{t}.norm{k}', ch)
+        conv(n + '.proj_out', ch, ch, 1)
+
+    lin('time_embed.0', mc, ted); lin('time_embed.2', ted, ted)
+    conv('input_blocks.0.0', 4, mc, 3)
+    chans, ch, ds, idx = [mc], mc, 1, 1
+    for level, m in enumerate(mult):
+        for _ in range(nrb):
+            res(f'input_blocks.{idx}.0', ch, m * mc); ch = m * mc
+            if ds in attn_res:
+                attn(f'input_blocks.{idx}.1', ch)
+            chans.append(ch); idx += 1
+        if level != len(mult) - 1:
+            conv(f'input_blocks.{idx}.0.op', ch, ch, 3); chans.append(ch); idx += 1; ds *= 2
+    res('middle_block.0', ch, ch); attn('middle_block.1', ch); res('middle_block.2', ch, ch)
+    idx = 0
+    for level, m in list(enumerate(mult))[::-1]:
+        for i in range(nrb + 1):
+            res(f'output_blocks.{idx}.0', ch + chans.pop(), mc * m); ch = mc * m
+            k = 1
+            if ds in attn_res:
+                attn(f'output_blocks.{idx}.{k}', ch); k += 1
+            if level and i == nrb:
+                conv(f'output_blocks.{idx}.{k}.conv', ch, ch, 3); ds //= 2
+            idx += 1
+    norm('out.0', ch); conv('out.2', mc, 4, 3)
+    return sh
+
+
 def extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk):
     import torch
     from diff_sampler_b200 import solver_utils
     from diff_sampler_b200.net import B200Net
     if True:
         # ---- roofline of the dominant kernel (tcgen05 GEMM/conv), measured live with CUDA events on the launch stream ---
+        if not hasattr(net, 'profile_forward'):
+            return
         x = latents * 2.0
         sig = torch.tensor(2.0, device=dev)
         prof = net.profile_forward(x, sig, labels)

@@ -181,6 +181,74 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
 }
 
 // ------------------------------------------------------------------------------------------ softmax
+// Single-read softmax: the row is held in registers (NV float4 per thread), one HBM read + one write per score.
+//   ROWS_PER_CTA = 8 warps, one warp per row  (L <= 32*4*NV)         -- short rows
+//   ROWS_PER_CTA = 1, 256 threads per row      (L <= 256*4*NV)        -- long rows (4096 keys of the 64x64 SD self-attention)
+template <int NV, bool CTA_ROW>
+__global__ void __launch_bounds__(256) softmax_reg_kernel(ds_softmax_desc d) {
+    __shared__ float red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long row = CTA_ROW ? (long long)blockIdx.x : (long long)blockIdx.x * 8 + warp;
+    if (row >= d.rows) return;                      // whole warp (or CTA) exits together
+    const int tid = CTA_ROW ? threadIdx.x : lane;
+    const int nthr = CTA_ROW ? 256 : 32;
+    const float* s = d.S + row * d.L;
+    float4 v[NV];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int j = (tid + k * nthr) * 4;
+        if (j < d.L) {
+            v[k] = __ldcs(reinterpret_cast<const float4*>(s + j));
+            m = fmaxf(m, fmaxf(fmaxf(v[k].x, v[k].y), fmaxf(v[k].z, v[k].w)));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (CTA_ROW) {
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        m = red[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        __syncthreads();
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int j = (tid + k * nthr) * 4;
+        if (j < d.L) {
+            v[k].x = expf(v[k].x - m); v[k].y = expf(v[k].y - m); v[k].z = expf(v[k].z - m); v[k].w = expf(v[k].w - m);
+            sum += v[k].x + v[k].y + v[k].z + v[k].w;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (CTA_ROW) {
+        if (lane == 0) red[warp] = sum;
+        __syncthreads();
+        sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w];
+    }
+    const float inv = 1.0f / sum;
+    __half* P = reinterpret_cast<__half*>(d.P);
+    const long long plane = d.rows * d.L;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int j = (tid + k * nthr) * 4;
+        if (j < d.L) {
+            const float e[4] = {v[k].x * inv, v[k].y * inv, v[k].z * inv, v[k].w * inv};
+            __align__(8) __half hi[4];
+            __align__(8) __half lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) split_h16(e[q], hi[q], lo[q]);
+            *reinterpret_cast<uint2*>(P + row * d.L + j) = *reinterpret_cast<const uint2*>(hi);
+            if (d.nplanes > 1) *reinterpret_cast<uint2*>(P + plane + row * d.L + j) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+}
+
 // one warp per row
 __global__ void softmax_kernel(ds_softmax_desc d) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -478,6 +546,18 @@ extern "C" int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream) {
 }
 
 extern "C" int ds_softmax_launch(const ds_softmax_desc* d, cudaStream_t stream) {
+    const bool dense = (d->pitch_in == 0 || d->pitch_in == d->L) && (d->pitch_out == 0 || d->pitch_out == d->L) && (d->L % 4 == 0);
+    if (dense && d->L <= 1024) {
+        const unsigned blocks = (unsigned)((d->rows + 7) / 8);
+        if (d->L <= 256) softmax_reg_kernel<2, false><<<blocks, 256, 0, stream>>>(*d);
+        else softmax_reg_kernel<8, false><<<blocks, 256, 0, stream>>>(*d);
+        return ok();
+    }
+    if (dense && d->L <= 8192) {
+        if (d->L <= 4096) softmax_reg_kernel<4, true><<<(unsigned)d->rows, 256, 0, stream>>>(*d);
+        else softmax_reg_kernel<8, true><<<(unsigned)d->rows, 256, 0, stream>>>(*d);
+        return ok();
+    }
     const int wpb = 8;
     const long long blocks = (d->rows + wpb - 1) / wpb;
     softmax_kernel<<<(unsigned)blocks, wpb * 32, 0, stream>>>(*d);

@@ -7,19 +7,38 @@ from . import _cstructs as S
 H16 = 2  # bytes per fp16
 
 
+NUM_SMS = 148
+
+
 def pick_bn(n):
-    """N tile (UMMA N, multiple of 16, <= 256): narrow outputs get the smallest covering tile; otherwise the widest of
-    {256, 192, 128, 64} among the tilings with the least padding (wide tiles halve the per-MMA shared-memory traffic)."""
+    """N tile (UMMA N: any multiple of 16 up to 256): narrow outputs get the smallest covering tile; otherwise the widest tile among
+    the tilings with the least padding (wide tiles lower the per-MMA shared-memory traffic): 320 -> 160x2, 384 -> 192x2, 1344 -> 224x6."""
     for bn in (16, 32, 64):
         if n <= bn:
             return bn, 1
     best = None
-    for bn in (256, 192, 128, 64):
+    for bn in range(256, 63, -16):
         tiles = -(-n // bn)
         key = (tiles * bn - n, -bn)
         if best is None or key < best[0]:
             best = (key, bn, tiles)
     return best[1], best[2]
+
+
+def fill_bn(n, m_tiles, num_z=1):
+    """pick_bn, then — when the problem has fewer tiles than SMs (small batch / low resolution) — narrow the N tile (keeping the same
+    padded width, so packed weights are unchanged) until the persistent grid fills the 148 SMs."""
+    bn, tiles = pick_bn(n)
+    padded = bn * tiles
+    if m_tiles * tiles * num_z >= NUM_SMS or bn <= 64:
+        return bn, tiles
+    for cand in range(bn - 16, 63, -16):
+        if padded % cand:
+            continue
+        if m_tiles * (padded // cand) * num_z >= NUM_SMS:
+            return cand, padded // cand
+    best = [c for c in range(64, bn, 16) if padded % c == 0]
+    return (best[0], padded // best[0]) if best else (bn, tiles)
 
 
 def split_planes_rows(n_valid, bn):
@@ -48,7 +67,7 @@ def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w
         assert a_planes == 2 and w_planes == 2
     d = S.GemmDesc()
     bw, bh, bnn = conv_box(H, W)
-    BN, n_tiles = (bn, -(-Cout // bn)) if bn else pick_bn(Cout)
+    BN, n_tiles = (bn, -(-Cout // bn)) if bn else fill_bn(Cout, -(-(Bn * H * W) // 128))
     cout_pad = n_tiles * BN
     ktot = taps * C + C2
     d.a_ptr = a_ptr
@@ -112,7 +131,7 @@ def rows_gemm(a_ptr, a_rows, a_pitch, a_batches, b_ptr, b_rows, b_pitch, b_batch
     z = zb*nh + zh selects the batch entry / column window of each operand (see csrc/ops.h)."""
     assert K % 64 == 0
     d = S.GemmDesc()
-    BN, n_tiles = (bn, -(-n_valid // bn)) if bn else pick_bn(n_valid)
+    BN, n_tiles = (bn, -(-n_valid // bn)) if bn else fill_bn(n_valid, -(-m_valid // 128), num_z)
     d.a_ptr = a_ptr
     d.a_dims[:] = [a_k_valid or a_pitch, a_rows, 1, a_planes * a_batches]       # K beyond the valid extent is zero-filled by TMA
     d.a_strides[:] = [a_pitch * H16, a_rows * a_pitch * H16, a_rows * a_pitch * H16]

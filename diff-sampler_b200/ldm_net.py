@@ -164,6 +164,24 @@ class B200LDMNet:
                 solver_update(out, x, [0] * 6, mode=S.DS_M_NONE, hist=[F], coef_dev=cd)
         return out
 
+    def profile_call(self, x, sigma, condition, unconditional_condition=None):
+        """One denoiser call with per-op CUDA-event timing -> {op_type: (count, total_ms)} and per-op list [(type, tag, ms)]."""
+        self(x, sigma, condition=condition, unconditional_condition=unconditional_condition)
+        for (h, pl) in self._plans.values():
+            self.lib.ds_unet_set_profiling(h, 1)
+        self(x, sigma, condition=condition, unconditional_condition=unconditional_condition)
+        out, per_op = {}, []
+        for (h, pl) in self._plans.values():
+            buf = (C.c_float * pl.n_ops)()
+            n = self.lib.ds_unet_get_profile(h, buf, pl.n_ops)
+            self.lib.ds_unet_set_profiling(h, 0)
+            for i in range(n):
+                t = self.lib.ds_unet_op_type(h, i)
+                c, ms = out.get(t, (0, 0.0))
+                out[t] = (c + 1, ms + buf[i])
+                per_op.append((t, pl.ops_array[i].tag, buf[i]))
+        return out, per_op
+
     def __del__(self):
         try:
             for h, _ in self._plans.values():

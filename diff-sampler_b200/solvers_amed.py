@@ -12,6 +12,7 @@ import torch
 
 from . import _cstructs as S
 from . import solvers as base
+from .ldm_net import B200LDMNet
 from .net import B200Net
 from .solver_utils import *                        # noqa: F401,F403
 from .solver_utils import dpm_pp_coefs, dyn_threshold, get_schedule, solver_update
@@ -41,12 +42,16 @@ class _Amed(_Loop):
         self.B = self.latents.shape[0]
         self.bott = torch.zeros(self.B, 64, device=self.latents.device)
         self.native = isinstance(self.net, B200Net)
-        self._hooked = None
+        self.native_ldm = isinstance(self.net, B200LDMNet)
 
     def denoise_tap(self, x, i):
         """First evaluation of a step: D(x, t_i) and the channel-mean of the U-Net bottleneck [B, 8, 8]."""
         if self.native:
             D = self.net(x, self.t_dev[i], class_labels=self.kw['class_labels'], out=self.D, bottleneck=self.bott)
+            return D, self.bott.reshape(self.B, 8, 8)
+        if self.native_ldm:       # middle_block read-out, conditional half (solvers_amed.py:12,24-25)
+            D = self.net(x, self.t_dev[i], condition=self.kw['condition'], unconditional_condition=self.kw['unconditional_condition'],
+                         out=self.D, bottleneck=self.bott)
             return D, self.bott.reshape(self.B, 8, 8)
         # foreign torch net: fall back to the reference's forward hook (solvers_amed.py:7-18)
         feats = []

@@ -251,7 +251,7 @@ def test_groupnorm_apply(lib, C0, C1, H, W, resample, ada, silu):
 def test_softmax(lib):
     from diff_sampler_b200 import _cstructs as S
     torch.manual_seed(7)
-    for L in (64, 256, 1024):
+    for L in (64, 256, 1024, 2048, 4096, 8192):
         Sm = torch.randn(37, L, device=dev()) * 4
         Pm = torch.zeros(2, 37, L, dtype=torch.float16, device=dev())
         lib.op_launch(S.SoftmaxDesc(S=Sm.data_ptr(), P=Pm.data_ptr(), rows=37, L=L, nplanes=2))

@@ -399,3 +399,23 @@ def test_ldm_sampler_parity():
     err = (got - ref).abs().max().item()
     print(f'ldm dpm_pp(2M) NFE=4 cfg: err {err:.3e} (max|x| {ref.abs().max().item():.1f})')
     assert err < TOL * max(1.0, ref.abs().max().item())
+
+
+def test_sd15_fullsize_parity():
+    """Full Stable-Diffusion-v1.5-sized eps-net (859.5 M parameters, 4x64x64 latents, 77x768 context) under classifier-free
+    guidance, batch 1: native vs the CPU oracle.  Weights come from the seeded recipe of oracle/ldm_oracle.make_params."""
+    import time
+    from oracle import edm_oracle as O
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    t0 = time.time()
+    on, nat, cfg = _ldm_pair('sd15')
+    x = O.stacked_randn(range(1), (4, 64, 64)) * 3.0
+    g = torch.Generator().manual_seed(8)
+    c = torch.randn(1, 77, 768, generator=g)
+    uc = torch.randn(1, 77, 768, generator=g)
+    got = nat(x.to(_dev()), torch.tensor([3.0], device=_dev()), condition=c.to(_dev()), unconditional_condition=uc.to(_dev())).cpu()
+    t1 = time.time()
+    ref = on(x, torch.tensor([3.0]), condition=c, unconditional_condition=uc)
+    err = (got - ref).abs().max().item()
+    print(f'sd15 cfg 7.5 batch 1: err {err:.3e} (max|D| {ref.abs().max().item():.2f}); build+native {t1 - t0:.0f}s, oracle {time.time() - t1:.0f}s')
+    assert err < TOL * max(1.0, ref.abs().max().item())

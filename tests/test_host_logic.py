@@ -68,13 +68,17 @@ def test_weight_packing_roundtrip():
     w = torch.randn(70, 40, 3, 3)
     sk = torch.randn(70, 24, 1, 1)
     p = G.pack_conv_weight(w, sk)
-    assert p.shape == (2, 128, 9 * 64 + 64) and p.dtype == torch.float16
+    bn, tiles = G.pick_bn(70)
+    assert bn % 16 == 0 and bn * tiles >= 70
+    assert p.shape == (2, bn * tiles, 9 * 64 + 64) and p.dtype == torch.float16
     full = p[0].float() + p[1].float()
     ref = torch.zeros(70, 3, 3, 64)
     ref[..., :40] = w.permute(0, 2, 3, 1)
     assert (full[:70, :576] - ref.reshape(70, -1)).abs().max() < 1e-6
     assert (full[:70, 576:600] - sk.reshape(70, 24)).abs().max() < 1e-6 and full[70:].abs().max() == 0
     assert G.pick_bn(256) == (256, 1) and G.pick_bn(384) == (192, 2) and G.pick_bn(3) == (16, 1) and G.pick_bn(576) == (192, 3)
+    assert G.pick_bn(320) == (160, 2) and G.pick_bn(1344) == (224, 6)
+    assert G.fill_bn(1280, 8) == (64, 20) and G.fill_bn(1280, 2048) == (256, 5)          # few M tiles -> narrower N tiles fill the SMs
     assert G.conv_box(32, 32) == (32, 4, 1) and G.conv_box(8, 8) == (8, 8, 2) and G.conv_box(64, 64) == (64, 2, 1)
     # qkv de-interleave ([head][c][q|k|v] rows, networks_edm.py:174)
     C_, nh = 8, 2
