@@ -253,7 +253,8 @@ def main():
     # ---- finished samples: one NCCL all_gather of the uint8 images (outside the timed region) -------------------------
     gathered = None
     if world > 1:
-        u8 = (images * 127.5 + 128).clip(0, 255).to(torch.uint8)
+        from diff_sampler_b200 import dist_utils
+        u8 = dist_utils.to_uint8_nhwc(images)
         allimg = [torch.empty_like(u8) for _ in range(world)]
         dist.all_gather(allimg, u8)
         gathered = sum(x.numel() for x in allimg)

@@ -337,6 +337,13 @@ int ds_gits_cost(const float* traj, const float* eps, const float* t_steps, doub
     return 0;
 }
 
+int ds_images_to_uint8(const float* images, unsigned char* out, int B, int C, int HW, void* stream) {
+    if (!images || !out) return fail(-1, "ds_images_to_uint8: null argument");
+    int rc = ds_to_uint8_launch(images, out, B, C, HW, static_cast<cudaStream_t>(stream));
+    if (rc) return fail(rc, std::string("ds_images_to_uint8: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
 int ds_op_launch(int op_type, const void* desc, size_t desc_size, void* stream) {
     ds_plan_op op;
     memset(&op, 0, sizeof op);

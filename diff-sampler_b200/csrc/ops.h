@@ -259,6 +259,7 @@ typedef struct ds_gits_cost_desc {
 } ds_gits_cost_desc;
 
 int ds_gits_cost_launch(const ds_gits_cost_desc* d, cudaStream_t stream);
+int ds_to_uint8_launch(const float* x, unsigned char* out, int B, int Cc, int HW, cudaStream_t stream);
 int ds_update_launch(const ds_update_desc* d, cudaStream_t stream);
 int ds_threshold_launch(const ds_threshold_desc* d, cudaStream_t stream);
 int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream);

@@ -181,9 +181,28 @@ __global__ void __launch_bounds__(256) gits_cost_kernel(ds_gits_cost_desc d) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ image epilogue
+// (x * 127.5 + 128).clip(0, 255) -> uint8, NCHW -> NHWC  (sample.py:311): one pass instead of five ATen launches.
+__global__ void to_uint8_nhwc_kernel(const float* x, unsigned char* out, int B, int Cc, int HW) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per (n, pixel)
+    if (idx >= (long long)B * HW) return;
+    const int n = (int)(idx / HW), p = (int)(idx - (long long)n * HW);
+    for (int c = 0; c < Cc; ++c) {
+        float v = x[((long long)n * Cc + c) * HW + p] * 127.5f + 128.0f;
+        v = fminf(fmaxf(v, 0.0f), 255.0f);
+        out[idx * Cc + c] = (unsigned char)v;                                      // truncation, as torch's float -> uint8 cast
+    }
+}
+
 }  // namespace dsb
 
 using namespace dsb;
+
+extern "C" int ds_to_uint8_launch(const float* x, unsigned char* out, int B, int Cc, int HW, cudaStream_t stream) {
+    const long long total = (long long)B * HW;
+    to_uint8_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, out, B, Cc, HW);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 
 extern "C" int ds_gits_cost_launch(const ds_gits_cost_desc* d, cudaStream_t stream) {
     if (d->n % 4 || d->N < 2) return -2;

@@ -37,7 +37,18 @@ def rank_batches(seeds, max_batch_size, world_size, rank):
 
 
 def to_uint8_nhwc(images):
-    """(x * 127.5 + 128).clip(0, 255).uint8, NCHW -> NHWC (sample.py:311)."""
+    """(x * 127.5 + 128).clip(0, 255).uint8, NCHW -> NHWC (sample.py:311).  CUDA tensors go through the one-pass native kernel
+    (ds_images_to_uint8); CPU tensors (tests of the gather logic) use the torch expression."""
+    if images.device.type == 'cuda':
+        import ctypes as C
+        from . import _lib
+        lib = _lib.load()
+        x = images.to(torch.float32).contiguous()
+        B, Cc, H, W = x.shape
+        out = torch.empty(B, H, W, Cc, dtype=torch.uint8, device=x.device)
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        _lib.check(lib.ds_images_to_uint8(x.data_ptr(), out.data_ptr(), B, Cc, H * W, stream), 'ds_images_to_uint8')
+        return out
     return (images * 127.5 + 128).clip(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
 
 

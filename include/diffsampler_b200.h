@@ -89,6 +89,10 @@ int ds_dyn_threshold(const float* x0, float* thr, int B, int row_len, float q, f
  * with b0 = traj[0], c = traj[N-1].  traj [N][B][n], eps [N-1][B][n] fp32; out [N][N][B][4] fp64 (entries i >= j untouched). */
 int ds_gits_cost(const float* traj, const float* eps, const float* t_steps, double* out, int N, int B, int64_t n_per_sample, void* stream);
 
+/* ---- image epilogue: replaces (images * 127.5 + 128).clip(0, 255).to(uint8).permute(0, 2, 3, 1) -------------
+ * sample.py:311.  images [B, C, H*W] fp32 NCHW -> out [B, H*W, C] uint8 NHWC (what is written to PNG / gathered for FID). */
+int ds_images_to_uint8(const float* images, unsigned char* out, int B, int C, int HW, void* stream);
+
 /* ---- kernel-level entry points (used by the parity tests and micro-benchmarks) ------------------
  * `desc` points to the matching struct of csrc/ops.h with absolute device pointers. */
 int ds_op_launch(int op_type, const void* desc, size_t desc_size, void* stream);

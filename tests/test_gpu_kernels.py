@@ -508,3 +508,13 @@ def test_cross_attention_gemms_with_77_keys(lib):
     got = O[0].double() + O[1].double()
     assert torch.isfinite(got).all()
     assert (got - refO).abs().max().item() < 3e-5 * max(1.0, refO.abs().max().item())
+
+
+def test_image_epilogue_uint8_bit_exact(lib):
+    from diff_sampler_b200 import dist_utils
+    torch.manual_seed(15)
+    x = torch.randn(9, 3, 32, 32, device=dev()) * 0.8
+    x[0, 0, 0, :4] = torch.tensor([-1.0, 1.0, 0.99999, -5.0], device=dev())
+    got = dist_utils.to_uint8_nhwc(x)
+    ref = (x * 127.5 + 128).clip(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+    assert torch.equal(got, ref)
