@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--precision', default='fp16x3', choices=['fp16x3', 'fp16'])
     ap.add_argument('--cpu_batch', type=int, default=8, help='batch of the bounded CPU-baseline sample')
     ap.add_argument('--no_cpu_baseline', action='store_true')
+    ap.add_argument('--fuse_stats', type=int, default=0, help='1: GroupNorm statistics accumulated in the GEMM epilogues')
     ap.add_argument('--no_extras', action='store_true', help='skip the roofline / e2e / fp16 legs (timing of the main leg is unchanged)')
     return ap.parse_args()
 
@@ -190,7 +191,7 @@ def main():
     if args.net == 'sd15':
         net, sampler, kw = build_sd15(args, dev, B, gen)
     else:
-        net = B200Net.from_config(args.net, seed=0, dezero=True, precision=args.precision, device=dev)
+        net = B200Net.from_config(args.net, seed=0, dezero=True, precision=args.precision, device=dev, fuse_stats=bool(args.fuse_stats))
         sampler = getattr(solvers, args.solver + '_sampler')
     shape = (B, net.img_channels, net.img_resolution, net.img_resolution)
     latents = torch.randn(shape, generator=gen, device=dev)

@@ -33,7 +33,7 @@ class GemmDesc(C.Structure):
         ('bias_n', P), ('bias_m', P), ('rowvec', P), ('rowvec_stride', I64), ('rows_per_sample', I32), ('pad0', I32),
         ('residual', P), ('ldr', I64), ('scale', F32),
         ('edm_out', I32), ('edm_x', P), ('edm_coef', P), ('edm_coef_stride', I32), ('edm_C', I32), ('edm_D', P),
-        ('st_sums', P * 2), ('st_cpg', I32 * 2), ('st_choff', I32 * 2), ('st_groups', I32 * 2),
+        ('st_part', P * 2), ('st_cpg', I32 * 2), ('st_choff', I32 * 2), ('st_groups', I32 * 2),
         ('tap_dh', I32 * 9), ('tap_dw', I32 * 9), ('tap_cb', I32 * 9), ('pad1', I32),
     ]
 
@@ -46,7 +46,8 @@ class GnStatsDesc(C.Structure):
 class GnApplyDesc(C.Structure):
     _fields_ = [('src0', P), ('src1', P), ('C0', I32), ('C1', I32), ('H', I32), ('W', I32), ('B', I32), ('groups', I32),
                 ('sums', P), ('gamma', P), ('beta', P), ('eps', F32), ('silu', I32), ('ada', P), ('ada_stride', I64),
-                ('resample', I32), ('nplanes', I32), ('out_act', P), ('out_raw', P), ('out_raw_f32', P)]
+                ('resample', I32), ('nplanes', I32), ('out_act', P), ('out_raw', P), ('out_raw_f32', P),
+                ('part0', P), ('part1', P), ('parts_per_sample', I32), ('pad1', I32)]
 
 
 class SoftmaxDesc(C.Structure):

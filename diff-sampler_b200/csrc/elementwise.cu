@@ -80,8 +80,26 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
     const int c8 = threadIdx.x % nc8;
     const int prow = threadIdx.x / nc8;
     const int c = c8 * 8;
-    const bool norm = d.sums != nullptr;
+    const bool norm = d.sums != nullptr || d.part0 != nullptr;
     float mean[8], a[8], b[8];
+    __shared__ double s_grp[64][2];
+    if (d.part0) {
+        // statistics from the producers' slab partials: thread t < 2*groups reduces (group t/2, {sum|sumsq}) over the sample's slabs
+        const int cpg_ = C / d.groups;
+        if ((int)threadIdx.x < 2 * d.groups) {
+            const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
+            double acc = 0.0;
+            const bool in0 = g <= (d.C0 - 1) / cpg_;
+            const bool in1 = d.C1 > 0 && g >= d.C0 / cpg_;
+            const long long base_p = (long long)n * d.parts_per_sample;
+            for (int q = 0; q < d.parts_per_sample; ++q) {
+                if (in0) acc += (double)d.part0[((base_p + q) * d.groups + g) * 2 + k];
+                if (in1) acc += (double)d.part1[((base_p + q) * d.groups + g) * 2 + k];
+            }
+            s_grp[g][k] = acc;
+        }
+        __syncthreads();
+    }
     if (norm) {
         const int cpg = C / d.groups;
         const double cnt = (double)cpg * d.H * d.W;
@@ -91,8 +109,8 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
         for (int j = 0; j < 8; ++j) {
             const int g = (c + j) / cpg;
             if (g != g_prev) {                 // at most a few distinct groups per 8 channels
-                const double s = d.sums[((long long)n * d.groups + g) * 2 + 0];
-                const double q = d.sums[((long long)n * d.groups + g) * 2 + 1];
+                const double s = d.part0 ? s_grp[g][0] : d.sums[((long long)n * d.groups + g) * 2 + 0];
+                const double q = d.part0 ? s_grp[g][1] : d.sums[((long long)n * d.groups + g) * 2 + 1];
                 const double mu = s / cnt;
                 double var = q / cnt - mu * mu;
                 if (var < 0.0) var = 0.0;

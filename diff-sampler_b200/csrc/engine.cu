@@ -58,13 +58,13 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_GEMM: {
             ds_gemm_desc& g = op.u.gemm;
             P(g.a_ptr); P(g.a2_ptr); P(g.b_ptr); P(g.out_f32); P(g.out_h16); P(g.bias_n); P(g.bias_m); P(g.rowvec);
-            P(g.residual); P(g.edm_x); P(g.edm_coef); P(g.edm_D); P(g.st_sums[0]); P(g.st_sums[1]);
+            P(g.residual); P(g.edm_x); P(g.edm_coef); P(g.edm_D); P(g.st_part[0]); P(g.st_part[1]);
             break;
         }
         case DS_OP_GN_STATS: { auto& d = op.u.gn_stats; P(d.src0); P(d.src1); P(d.sums); break; }
         case DS_OP_GN_APPLY: {
             auto& d = op.u.gn_apply;
-            P(d.src0); P(d.src1); P(d.sums); P(d.gamma); P(d.beta); P(d.ada); P(d.out_act); P(d.out_raw); P(d.out_raw_f32);
+            P(d.src0); P(d.src1); P(d.sums); P(d.gamma); P(d.beta); P(d.ada); P(d.out_act); P(d.out_raw); P(d.out_raw_f32); P(d.part0); P(d.part1);
             break;
         }
         case DS_OP_SOFTMAX: { auto& d = op.u.softmax; P(d.S); P(d.P); break; }

@@ -50,8 +50,9 @@ struct alignas(64) GemmKernelParams {
     int edm_coef_stride;
     int edm_C;
     float* edm_D;
-    // fused GroupNorm statistics of the tensor being written (up to two consumers with their own channel grouping)
-    double* st_sums[2];
+    // fused GroupNorm statistics of the tensor being written (up to two consumers with their own channel grouping):
+    // per 32-row slab partial {sum, sumsq} per group, plain stores (no atomics); the consumer adds the slabs of a sample.
+    float* st_part[2];
     int st_cpg[2], st_choff[2], st_groups[2];
     int tap_dh[9], tap_dw[9], tap_cb[9];
 };
@@ -64,21 +65,54 @@ struct SmemCtl {
     uint32_t tmem_base;
 };
 
+// Running GroupNorm-statistics state of one epilogue thread (one row of the tile), carried across the column chunks of a tile so
+// that a group spanning two chunks is reduced once.  Flush = warp reduction over the 32 rows + one plain store by lane 0.
+struct StatCarry {
+    float s1[2], s2[2];
+    int g_cur[2];       // group currently being accumulated (-1: sink unused)
+    int rem[2];         // columns left in that group
+};
+
+__device__ __noinline__ void stat_flush(const GemmKernelParams& p, StatCarry& st, int sidx, long long slab) {
+    float a = st.s1[sidx], b = st.s2[sidx];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        float* dst = p.st_part[sidx] + (slab * p.st_groups[sidx] + st.g_cur[sidx]) * 2;
+        dst[0] = a;
+        dst[1] = b;
+    }
+    st.s1[sidx] = 0.f;
+    st.s2[sidx] = 0.f;
+}
+
 template <int W>
-__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const float* v, long long grow_in_z, int col0,
-                                               bool row_ok, int z, int zb, int zh) {
-    // v[W]: accumulators of this thread's row, columns col0 .. col0+W-1 (tile-local col0 already globalised)
-    const bool has_stats = p.st_sums[0] != nullptr;      // warp-uniform
+__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const float* v, long long grow_in_z, int col0, bool row_ok,
+                                               int zb, int zh, const float4* res_pref, bool res_in_regs, StatCarry& st) {
+    // v[W]: accumulators of this thread's row, columns col0 .. col0+W-1 (col0 is the global column)
+    const bool has_stats = p.st_part[0] != nullptr;      // warp-uniform
     if (!row_ok && !has_stats) return;
+    const long long slab = grow_in_z >> 5;
     if (!row_ok) grow_in_z = 0;                            // keep loads in range; the row's values are zeroed below
     float r[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] = v[j];
     const bool full = (col0 + W <= p.n_valid);
     if (p.bias_n) {
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < W; ++j)
-            if (full || col0 + j < p.n_valid) r[j] += __ldg(p.bias_n + col0 + j);
+            for (int j = 0; j < W; j += 4) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias_n + col0 + j));
+                r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (col0 + j < p.n_valid) r[j] += __ldg(p.bias_n + col0 + j);
+        }
     }
     if (p.bias_m) {
         const float bm = __ldg(p.bias_m + grow_in_z);
@@ -88,62 +122,59 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     if (p.rowvec) {
         const long long s = (p.rowvec_stride == 0) ? 0 : (grow_in_z / p.rows_per_sample) * p.rowvec_stride;
         const float* rv = p.rowvec + s + col0;
-#pragma unroll
-        for (int j = 0; j < W; ++j)
-            if (full || col0 + j < p.n_valid) r[j] += __ldg(rv + j);
-    }
-    if (p.residual) {
-        const float* rs = p.residual + grow_in_z * p.ldr + col0;
         if (full) {
 #pragma unroll
             for (int j = 0; j < W; j += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(rs + j);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(rv + j));
                 r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
             }
         } else {
 #pragma unroll
             for (int j = 0; j < W; ++j)
-                if (col0 + j < p.n_valid) r[j] += rs[j];
+                if (col0 + j < p.n_valid) r[j] += __ldg(rv + j);
+        }
+    }
+    if (p.residual) {
+        if (res_in_regs) {
+#pragma unroll
+            for (int j = 0; j < W; j += 4) {
+                const float4 t = res_pref[j >> 2];
+                r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
+            }
+        } else {
+            const float* rs = p.residual + grow_in_z * p.ldr + col0;
+            if (full) {
+#pragma unroll
+                for (int j = 0; j < W; j += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(rs + j);
+                    r[j] += t.x; r[j + 1] += t.y; r[j + 2] += t.z; r[j + 3] += t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < W; ++j)
+                    if (col0 + j < p.n_valid) r[j] += rs[j];
+            }
         }
     }
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] *= p.scale;
 
     if (has_stats) {
-        // per-(sample, group) sum / sum of squares of the values being written: 32 rows (one warp) belong to one sample,
-        // a group is a run of `cpg` consecutive channels of the consumer's (possibly concatenated) channel axis.
-        const long long n = grow_in_z / p.rows_per_sample;
+        const bool plain = row_ok && full;                 // no masking needed (the common case)
 #pragma unroll
         for (int sidx = 0; sidx < 2; ++sidx) {
-            if (!p.st_sums[sidx]) continue;
+            if (st.g_cur[sidx] < 0) continue;
             const int cpg = p.st_cpg[sidx];
-            float s1 = 0.f, s2 = 0.f;
-            int g_cur = (p.st_choff[sidx] + col0) / cpg;
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                const int g = (p.st_choff[sidx] + col0 + j) / cpg;          // warp-uniform
-                if (g != g_cur) {
-                    float a = s1, b = s2;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-                    if ((threadIdx.x & 31) == 0) {
-                        double* dst = p.st_sums[sidx] + (n * p.st_groups[sidx] + g_cur) * 2;
-                        atomicAdd(dst, (double)a);
-                        atomicAdd(dst + 1, (double)b);
-                    }
-                    s1 = 0.f; s2 = 0.f; g_cur = g;
+                const float val = plain ? r[j] : ((row_ok && col0 + j < p.n_valid) ? r[j] : 0.f);
+                st.s1[sidx] += val;
+                st.s2[sidx] = fmaf(val, val, st.s2[sidx]);
+                if (--st.rem[sidx] == 0) {                  // warp-uniform: group boundary (no per-column division)
+                    stat_flush(p, st, sidx, slab);
+                    ++st.g_cur[sidx];
+                    st.rem[sidx] = cpg;
                 }
-                const float val = (row_ok && (full || col0 + j < p.n_valid)) ? r[j] : 0.f;
-                s1 += val;
-                s2 += val * val;
-            }
-            float a = s1, b = s2;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-            if ((threadIdx.x & 31) == 0) {
-                double* dst = p.st_sums[sidx] + (n * p.st_groups[sidx] + g_cur) * 2;
-                atomicAdd(dst, (double)a);
-                atomicAdd(dst + 1, (double)b);
             }
         }
         if (!row_ok) return;
@@ -350,14 +381,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const long long grow = (long long)mt * 128 + row;
             const bool row_ok = grow < p.m_valid;
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
+            StatCarry st;
+            st.s1[0] = st.s1[1] = st.s2[0] = st.s2[1] = 0.f;
+#pragma unroll
+            for (int sidx = 0; sidx < 2; ++sidx) {
+                st.g_cur[sidx] = -1;
+                st.rem[sidx] = 0;
+                if (p.st_part[sidx]) {
+                    const int c0 = p.st_choff[sidx] + nt * p.BN;          // one division per tile and sink
+                    st.g_cur[sidx] = c0 / p.st_cpg[sidx];
+                    st.rem[sidx] = p.st_cpg[sidx] - (c0 - st.g_cur[sidx] * p.st_cpg[sidx]);
+                }
+            }
+            // residual rows are prefetched one chunk ahead (registers) so their HBM latency overlaps the previous chunk's work
+            const float* res_row = p.residual ? p.residual + (row_ok ? grow : 0) * p.ldr + (long long)nt * p.BN : nullptr;
+            float4 res_next[8];
+            auto prefetch = [&](int cc) {
+                if (res_row && (long long)nt * p.BN + cc + 32 <= p.n_valid) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) res_next[q] = *reinterpret_cast<const float4*>(res_row + cc + 4 * q);
+                }
+            };
+            prefetch(0);
             int c = 0;
             for (; c + 32 <= p.BN; c += 32) {
+                float4 res_cur[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) res_cur[q] = res_next[q];
+                const int col0 = nt * p.BN + c;
+                const bool in_regs = res_row && (col0 + 32 <= p.n_valid);
+                if (c + 64 <= p.BN) prefetch(c + 32);
                 uint32_t v[32];
                 DSB_TMEM_LD_32(t_row + c, v);
                 tmem_ld_wait();
-                const int col0 = nt * p.BN + c;
                 if (col0 < p.n_valid)
-                    epilogue_chunk<32>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, z, zb, zh);
+                    epilogue_chunk<32>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, zb, zh, res_cur, in_regs, st);
             }
             if (c < p.BN) {
                 uint32_t v[16];
@@ -365,7 +423,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 tmem_ld_wait();
                 const int col0 = nt * p.BN + c;
                 if (col0 < p.n_valid)
-                    epilogue_chunk<16>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, z, zb, zh);
+                    epilogue_chunk<16>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, zb, zh, nullptr, false, st);
+            }
+            if (p.st_part[0]) {
+                // a group cut by the end of this tensor's channel range (the rest belongs to the other concat source)
+#pragma unroll
+                for (int sidx = 0; sidx < 2; ++sidx)
+                    if (st.g_cur[sidx] >= 0 && st.rem[sidx] != p.st_cpg[sidx] && st.g_cur[sidx] < p.st_groups[sidx])
+                        stat_flush(p, st, sidx, grow >> 5);
             }
             tc_fence_before();
             __syncwarp();
@@ -446,13 +511,13 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     kp->edm_out = d->edm_out; kp->edm_x = d->edm_x; kp->edm_coef = d->edm_coef; kp->edm_coef_stride = d->edm_coef_stride;
     kp->edm_C = d->edm_C; kp->edm_D = d->edm_D;
     for (int k = 0; k < 2; ++k) {
-        kp->st_sums[k] = d->st_sums[k]; kp->st_cpg[k] = d->st_cpg[k] > 0 ? d->st_cpg[k] : 1;
+        kp->st_part[k] = d->st_part[k]; kp->st_cpg[k] = d->st_cpg[k] > 0 ? d->st_cpg[k] : 1;
         kp->st_choff[k] = d->st_choff[k]; kp->st_groups[k] = d->st_groups[k];
     }
     for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = d->tap_dh[t]; kp->tap_dw[t] = d->tap_dw[t]; kp->tap_cb[t] = d->tap_cb[t]; }
     if (d->taps != 1 && d->taps != 9) return -15;
-    if (d->st_sums[1] && !d->st_sums[0]) return -13;
-    if (d->st_sums[0] && (d->a_mode != 0 || (d->conv_H * d->conv_W) % 32 != 0)) return -14;
+    if (d->st_part[1] && !d->st_part[0]) return -13;
+    if (d->st_part[0] && (d->a_mode != 0 || (d->conv_H * d->conv_W) % 32 != 0 || d->n_tiles != 1 && (d->BN % d->st_cpg[0]) != 0)) return -14;
     const int stage_bytes = kATileBytes + d->BN * 128;
     int ns = (227 * 1024 - 2048) / stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;

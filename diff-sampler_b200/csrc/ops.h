@@ -70,9 +70,10 @@ typedef struct ds_gemm_desc {
     int32_t edm_coef_stride;// 0 (one sigma) or 4 (per-sample)
     int32_t edm_C;
     float* edm_D;
-    // fused GroupNorm statistics of the fp32 output (conv mode only): for each consumer k, accumulate per (sample, group)
-    // {sum, sumsq} into st_sums[k][(n*st_groups[k] + g)*2 + {0,1}] with g = (st_choff[k] + channel) / st_cpg[k].
-    double* st_sums[2];
+    // fused GroupNorm statistics of the fp32 output (conv mode only): for each consumer k, the epilogue stores per 32-row slab
+    // the partial {sum, sumsq} of every group it touches: st_part[k][(row/32 * st_groups[k] + g)*2 + {0,1}],
+    // g = (st_choff[k] + channel) / st_cpg[k].  Plain stores, no atomics; gn_apply adds the slabs of a sample (parts_per_sample).
+    float* st_part[2];
     int32_t st_cpg[2];
     int32_t st_choff[2];
     int32_t st_groups[2];
@@ -125,6 +126,12 @@ typedef struct ds_gn_apply_desc {
     void* out_act;          // fp16 [nplanes][B][Ho][Wo][C]; may be NULL
     void* out_raw;          // fp16 planes of the raw input; may be NULL
     float* out_raw_f32;     // fp32 raw input at output resolution; may be NULL
+    // alternative statistics source (sums == NULL): slab partials written by the producing GEMM epilogues (ds_gemm_desc.st_part),
+    // one buffer per source tensor, `parts_per_sample` = H*W/32 slabs per sample, `groups` columns each.
+    const float* part0;
+    const float* part1;
+    int32_t parts_per_sample;
+    int32_t pad1;
 } ds_gn_apply_desc;
 
 // Row softmax: P = softmax(S) over the last dim, fp32 in, fp16 hi/lo planes out. Reference: networks_edm.py:108.

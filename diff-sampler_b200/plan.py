@@ -171,46 +171,62 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
     def emit(builder):
         ops.append((tag[0], builder))
 
-    # Fused GroupNorm statistics: the GEMM that writes an fp32 tensor also accumulates the {sum, sumsq} its consumers need
-    # (at most two: the next block and, for encoder outputs, the decoder block that concatenates it as a skip).
-    prod_of = {}            # buffer name -> index of the op that last wrote it
-    sinks = {}              # producer op index -> [(stats byte offset, cpg, channel offset, groups)]
+    # Fused GroupNorm statistics (fuse_stats=True): the GEMM that writes an fp32 tensor also stores, per 32-row slab, the partial
+    # {sum, sumsq} of every group its consumers need (at most two consumers: the next block and, for encoder outputs, the decoder block
+    # that concatenates it as a skip); gn_apply adds the slabs of a sample.  No atomics, no separate statistics pass.
+    prod_of = {}            # buffer name -> (op index, Cout, m_tiles) of the GEMM that last wrote it
+    sinks = {}              # producer op index -> [(partial buffer, cpg, channel offset, groups)]
+    stat_src = {}           # stats slot -> ('sums',) | ('parts', [buf0, buf1?], parts_per_sample)
 
-    def emit_producer(name, build):
+    def emit_producer(name, cout, m_rows, build):
         pid = len(ops)
-        prod_of[name] = pid
+        prod_of[name] = (pid, cout, -(-m_rows // 128))
         sinks[pid] = []
 
         def materialise(R):
             d = build(R)
-            for k, (slot, cpg, choff, groups) in enumerate(sinks[pid]):
-                d.st_sums[k] = R('stats', slot)
+            for k, (buf, cpg, choff, groups) in enumerate(sinks[pid]):
+                d.st_part[k] = R(buf)
                 d.st_cpg[k], d.st_choff[k], d.st_groups[k] = cpg, choff, groups
             return d
         emit(materialise)
 
     def need_stats(slot, parts, hw):
-        """GroupNorm statistics over the (virtually concatenated) fp32 tensors `parts` = [(buffer, channels), ...] into `slot`.
-        Default: one stand-alone gn_stats launch.  fuse_stats=True: accumulated by the epilogue of the GEMM that writes each part
-        (kept for experiments: on B200 round 1 the extra shuffles + fp64 atomics made the epilogue the critical path —
-        59.7 -> 72.8 ms of GEMM time per CIFAR-10 forward to save a 4.3 ms statistics pass)."""
+        """GroupNorm statistics over the (virtually concatenated) fp32 tensors `parts` = [(buffer, channels), ...] for `slot`."""
         c_total = sum(c for _, c in parts)
-        if not fuse_stats:
-            assert len(parts) <= 2
-            (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
-            emit(lambda R: S.GnStatsDesc(src0=R(n0), src1=R(n1) if n1 else 0, C0=c0, C1=c1, HW=hw, B=B, groups=_groups(c_total),
-                                         sums=R('stats', slot)))
-            return
+        g = _groups(c_total)
+        cpg = c_total // g
+        fusable = fuse_stats and hw % 32 == 0 and len(parts) <= 2
         off = 0
         for name, c in parts:
-            want_stats(name, slot, c_total, off)
+            if not fusable:
+                break
+            pid, cout, m_tiles = prod_of[name]
+            bn, n_tiles = G.fill_bn(cout, m_tiles)
+            if len(sinks[pid]) >= 2 or (n_tiles > 1 and (bn % cpg or off % cpg)):
+                fusable = False          # a group would straddle two N tiles (e.g. 768 channels in 24-wide groups over 256-wide tiles)
             off += c
+        if not fusable:
+            assert len(parts) <= 2
+            (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
+            emit(lambda R: S.GnStatsDesc(src0=R(n0), src1=R(n1) if n1 else 0, C0=c0, C1=c1, HW=hw, B=B, groups=g, sums=R('stats', slot)))
+            stat_src[slot] = ('sums',)
+            return
+        off, bufs = 0, []
+        for i, (name, c) in enumerate(parts):
+            pid, cout, m_tiles = prod_of[name]
+            buf = A.need(f'part:{slot}:{i}', m_tiles * 4 * g * 2 * F4)
+            sinks[pid].append((buf, cpg, off, g))
+            bufs.append(buf)
+            off += c
+        stat_src[slot] = ('parts', bufs, hw // 32)
 
-    def want_stats(name, slot, c_total, choff):
-        lst = sinks[prod_of[name]]
-        assert len(lst) < 2, f'more than two GroupNorm consumers of {name}'
-        g = _groups(c_total)
-        lst.append((slot, c_total // g, choff, g))
+    def stat_args(R, slot):
+        src = stat_src[slot]
+        if src[0] == 'sums':
+            return dict(sums=R('stats', slot), part0=0, part1=0, parts_per_sample=0)
+        bufs = src[1]
+        return dict(sums=0, part0=R(bufs[0]), part1=R(bufs[1]) if len(bufs) > 1 else 0, parts_per_sample=src[2])
 
     # ---------------- embedding ----------------------------------------------------------------------------------
     A.need('coef', nsig * 4 * F4)
@@ -261,7 +277,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
     emit(lambda R: S.PrepInputDesc(x=io(S.DS_IO_X), coef=R('coef'), coef_stride=4 if nsig > 1 else 0, B=B, C=spec.img_channels,
                                    HW=HW0, nplanes=npl, out=R('in_planes')))
     A.need('x:' + spec.stem, B * HW0 * spec.stem_cout * F4)
-    emit_producer('x:' + spec.stem, lambda R: G.conv_gemm(R('in_planes'), B, R0, R0, 64, W(spec.stem + ':w'), spec.stem_cout, taps=9,
+    emit_producer('x:' + spec.stem, spec.stem_cout, B * HW0, lambda R: G.conv_gemm(R('in_planes'), B, R0, R0, 64, W(spec.stem + ':w'), spec.stem_cout, taps=9,
                                                           npass=npass, out_f32=R('x:' + spec.stem), bias=W(spec.stem + ':b'))[0])
 
     stat_i = [0]
@@ -289,17 +305,17 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
             A.need('raw', npl * Mo * cin * H2)
         if want_rawf:
             A.need('rawf', Mo * cin * F4)
-        emit(lambda R: S.GnApplyDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, H=Hi, W=Hi, B=B, groups=_groups(cin), sums=R('stats', s0),
+        emit(lambda R: S.GnApplyDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, H=Hi, W=Hi, B=B, groups=_groups(cin), **stat_args(R, s0),
                                      gamma=W(n + '.norm0:g'), beta=W(n + '.norm0:b'), eps=b.eps, silu=1, ada=0, ada_stride=0,
                                      resample=resample, nplanes=npl, out_act=R('act'), out_raw=R('raw') if want_raw else 0,
                                      out_raw_f32=R('rawf') if want_rawf else 0))
         A.need('y', Mo * cout * F4)
-        emit_producer('y', lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cin, W(n + '.conv0:w'), cout, taps=9, npass=npass, out_f32=R('y'),
+        emit_producer('y', cout, Mo, lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cin, W(n + '.conv0:w'), cout, taps=9, npass=npass, out_f32=R('y'),
                                                  bias=W(n + '.conv0:b'), rowvec=0 if b.adaptive_scale else R('aff', b.aff_off * F4),
                                                  rowvec_stride=aff_stride)[0])
         s1 = stats_slot()
         need_stats(s1, [('y', cout)], Ho * Ho)
-        emit(lambda R: S.GnApplyDesc(src0=R('y'), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), sums=R('stats', s1),
+        emit(lambda R: S.GnApplyDesc(src0=R('y'), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), **stat_args(R, s1),
                                      gamma=W(n + '.norm1:g'), beta=W(n + '.norm1:b'), eps=b.eps, silu=1,
                                      ada=R('aff', b.aff_off * F4) if b.adaptive_scale else 0,
                                      ada_stride=aff_stride if b.adaptive_scale else 0, resample=0, nplanes=npl, out_act=R('act'),
@@ -313,7 +329,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
             res_name = 'rawf'
         else:
             res_name = None
-        emit_producer(mid, lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cout, W(n + '.conv1:w'), cout, taps=9, npass=npass,
+        emit_producer(mid, cout, Mo, lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cout, W(n + '.conv1:w'), cout, taps=9, npass=npass,
                                                  a2_ptr=R('raw') if want_raw else 0, C2=cin if want_raw else 0, out_f32=R(mid),
                                                  bias=W(n + '.conv1:b'), residual=R(res_name) if res_name else 0, ldr=cout,
                                                  scale=b.skip_scale)[0])
@@ -323,7 +339,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
             L = Ho * Ho
             s2 = stats_slot()
             need_stats(s2, [(mid, cout)], L)
-            emit(lambda R: S.GnApplyDesc(src0=R(mid), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), sums=R('stats', s2),
+            emit(lambda R: S.GnApplyDesc(src0=R(mid), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), **stat_args(R, s2),
                                          gamma=W(n + '.norm2:g'), beta=W(n + '.norm2:b'), eps=b.eps, silu=0, ada=0, ada_stride=0,
                                          resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))
             A.need('qk', npl * B * L * 2 * cout * H2)
@@ -343,7 +359,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
             emit(lambda R: G.rows_gemm(R('P'), L, L, B * nh, R('vt'), cout, L, B, L, num_z=B * nh, nh=nh, m_valid=L, n_valid=d,
                                        npass=npass, a_n_per_zb=nh, a_n_per_zh=1, b_row_per_zh=d, b_z_per_zb=1, out_h16=R('o'),
                                        o_zb=L * cout, o_zh=d, ldo=cout, o_plane=B * L * cout)[0])
-            emit_producer(xout, lambda R: G.conv_gemm(R('o'), B, Ho, Ho, cout, W(n + '.proj:w'), cout, taps=1, npass=npass, out_f32=R(xout),
+            emit_producer(xout, cout, Mo, lambda R: G.conv_gemm(R('o'), B, Ho, Ho, cout, W(n + '.proj:w'), cout, taps=1, npass=npass, out_f32=R(xout),
                                                       bias=W(n + '.proj:b'), residual=R(mid), ldr=cout, scale=b.skip_scale)[0])
         if n == spec.bottleneck_block:
             emit(lambda R: S.ChanmeanDesc(src=R(xout), out=io(S.DS_IO_BOTTLENECK), rows=B * Ho * Ho, C=cout))
@@ -370,7 +386,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
     A.need('act', npl * B * HW0 * cur_c * H2)
     fin, fin_c = cur, cur_c
     need_stats(sh, [(fin, fin_c)], HW0)
-    emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=_groups(fin_c), sums=R('stats', sh),
+    emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=_groups(fin_c), **stat_args(R, sh),
                                  gamma=W(spec.head_norm + ':g'), beta=W(spec.head_norm + ':b'), eps=spec.head_eps, silu=1, ada=0,
                                  ada_stride=0, resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))
     emit(lambda R: G.conv_gemm(R('act'), B, R0, R0, fin_c, W(spec.head_conv + ':w'), spec.img_channels, taps=9, npass=npass,

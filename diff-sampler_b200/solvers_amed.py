@@ -175,7 +175,7 @@ def euler_sampler(net, latents, class_labels=None, condition=None, unconditional
 @torch.no_grad()
 def ipndm_sampler(net, latents, class_labels=None, condition=None, unconditional_condition=None, num_steps=None, sigma_min=0.002,
                   sigma_max=80, schedule_type='polynomial', schedule_rho=7, afs=False, denoise_to_zero=False, return_inters=False,
-                  AMED_predictor=None, step_idx=None, train=False, buffer_model=[], max_order=4, **kwargs):
+                  AMED_predictor=None, train=False, max_order=4, buffer_model=[], **kwargs):
     """AMED plug-in for iPNDM.  Reference: solvers_amed.py:262-396.  Both legs use the Adams-Bashforth weights of the
     current history length; the intermediate d enters the history as well."""
     assert max_order >= 1 and max_order <= 4

@@ -146,3 +146,41 @@ def test_gits_dp_bit_exact_vs_reference():
     assert np.abs(gits_utils.cal_deviation(traj, 3, 8, bs=3).numpy() - d['gits/dev']).max() <= 1e-5 * np.abs(d['gits/dev']).max()
     with pytest.raises(NotImplementedError):
         gits_utils.get_sampler_fn('nope', 'cpu')
+
+
+def test_public_surface_matches_reference_signatures():
+    """Drop-in check: every function of the reference's solvers / solver_utils / solvers_amed / gits_utils surface exists here with
+    the same parameter names, order and defaults (signatures recorded from the real reference into tests/golden/ref_signatures.json;
+    the product may only ADD trailing keyword parameters, e.g. `dp_list`, `scale`, `t_steps`)."""
+    import inspect
+    import importlib
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'ref_signatures.json')))
+    modmap = {'solvers': 'diff_sampler_b200.solvers', 'solver_utils': 'diff_sampler_b200.solver_utils',
+              'solvers_amed': 'diff_sampler_b200.solvers_amed', 'gits_utils': 'diff_sampler_b200.gits_utils',
+              'amed.solver_utils': 'diff_sampler_b200.solver_utils', 'gits.solver_utils': 'diff_sampler_b200.solver_utils'}
+    checked = 0
+    for key, params in ref.items():
+        modname, fn = key.rsplit('.', 1)
+        mod = importlib.import_module(modmap[modname])
+        assert hasattr(mod, fn), f'{key} missing'
+        mine = list(inspect.signature(getattr(mod, fn)).parameters.items())
+        mine_named = [(n, p) for n, p in mine if p.kind not in (inspect.Parameter.VAR_KEYWORD, inspect.Parameter.VAR_POSITIONAL)]
+        ref_named = [r for r in params if 'VAR_' not in r[1]]
+        ref_has_kwargs = any('VAR_KEYWORD' in r[1] for r in params)
+        assert len(mine_named) >= len(ref_named), key
+        for (n, p), (rn, _, rd) in zip(mine_named, ref_named):
+            assert n == rn, f'{key}: parameter {n} != reference {rn}'
+            md = None if p.default is inspect._empty else repr(p.default)
+            if rd is not None and md is not None:
+                assert md == rd or (rd in ('[]',) and md == rd) or float_eq(md, rd), f'{key}.{n}: default {md} != reference {rd}'
+        if ref_has_kwargs:
+            assert any(p.kind == inspect.Parameter.VAR_KEYWORD for _, p in mine), f'{key} must swallow **kwargs (sample.py passes the whole CLI dict)'
+        checked += 1
+    assert checked >= 30
+
+
+def float_eq(a, b):
+    try:
+        return float(a) == float(b)
+    except ValueError:
+        return False
