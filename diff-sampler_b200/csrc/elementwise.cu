@@ -38,8 +38,9 @@ __global__ void gn_stats_kernel(ds_gn_stats_desc d, int pix_per_cta) {
         const int gB = (c + 3) / cpg;
         const int nA = (gA == gB) ? 4 : ((gA + 1) * cpg - c);   // channels of this float4 that belong to group A
         float sA = 0.f, qA = 0.f, sB = 0.f, qB = 0.f;
+#pragma unroll 8
         for (int p = p_begin + threadIdx.y; p < p_end; p += blockDim.y) {
-            const float4 v = *reinterpret_cast<const float4*>(base + ((long long)n * d.HW + p) * pitch + cc);
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(base + ((long long)n * d.HW + p) * pitch + cc));
             const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -554,8 +555,9 @@ extern "C" int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream
     int bx = ncol4 < 256 ? ncol4 : 256;
     // keep bx a divisor-friendly size; columns loop with stride bx anyway
     int by = 256 / bx; if (by < 1) by = 1;
-    int pix_per_cta = 64;
-    if (pix_per_cta < by) pix_per_cta = by;
+    int pix_per_cta = 8 * by;                  // 8 loads in flight per thread
+    if (pix_per_cta < 64) pix_per_cta = 64;
+    while (pix_per_cta > 64 && (long long)((d->HW + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
     const int chunks = (d->HW + pix_per_cta - 1) / pix_per_cta;
     gn_stats_kernel<<<dim3(chunks, d->B), dim3(bx, by), 0, stream>>>(*d, pix_per_cta);
     return ok();
