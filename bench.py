@@ -40,7 +40,7 @@ def parse():
     ap.add_argument('--precision', default='fp16x3', choices=['fp16x3', 'fp16'])
     ap.add_argument('--cpu_batch', type=int, default=8, help='batch of the bounded CPU-baseline sample')
     ap.add_argument('--no_cpu_baseline', action='store_true')
-    ap.add_argument('--fuse_stats', type=int, default=0, help='1: GroupNorm statistics accumulated in the GEMM epilogues')
+    ap.add_argument('--fuse_stats', type=int, default=1, help='1 (default): GroupNorm statistics from the GEMM epilogues; 0: separate gn_stats pass')
     ap.add_argument('--no_extras', action='store_true', help='skip the roofline / e2e / fp16 legs (timing of the main leg is unchanged)')
     return ap.parse_args()
 

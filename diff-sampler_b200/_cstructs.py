@@ -8,7 +8,7 @@ I64 = C.c_int64
 F32 = C.c_float
 
 DS_OP_GEMM, DS_OP_GN_STATS, DS_OP_GN_APPLY, DS_OP_SOFTMAX, DS_OP_POSEMB, DS_OP_LINEAR = 1, 2, 3, 4, 5, 6
-DS_OP_PREP_INPUT, DS_OP_CHANMEAN, DS_OP_MEMSET, DS_OP_LAYERNORM, DS_OP_GEGLU = 7, 8, 9, 10, 11
+DS_OP_PREP_INPUT, DS_OP_CHANMEAN, DS_OP_MEMSET, DS_OP_LAYERNORM, DS_OP_GEGLU, DS_OP_GN_FINALIZE = 7, 8, 9, 10, 11, 12
 DS_IO_X, DS_IO_D, DS_IO_SIGMA, DS_IO_LABELS, DS_IO_BOTTLENECK, DS_IO_CTX = 0, 1, 2, 3, 4, 5
 DS_M_X0, DS_M_EPS, DS_M_DIV, DS_M_NONE = 0, 1, 2, 3
 
@@ -33,7 +33,7 @@ class GemmDesc(C.Structure):
         ('bias_n', P), ('bias_m', P), ('rowvec', P), ('rowvec_stride', I64), ('rows_per_sample', I32), ('pad0', I32),
         ('residual', P), ('ldr', I64), ('scale', F32),
         ('edm_out', I32), ('edm_x', P), ('edm_coef', P), ('edm_coef_stride', I32), ('edm_C', I32), ('edm_D', P),
-        ('st_part', P * 2), ('st_cpg', I32 * 2), ('st_choff', I32 * 2), ('st_groups', I32 * 2),
+        ('st_quads', P),
         ('tap_dh', I32 * 9), ('tap_dw', I32 * 9), ('tap_cb', I32 * 9), ('pad1', I32),
     ]
 
@@ -46,8 +46,7 @@ class GnStatsDesc(C.Structure):
 class GnApplyDesc(C.Structure):
     _fields_ = [('src0', P), ('src1', P), ('C0', I32), ('C1', I32), ('H', I32), ('W', I32), ('B', I32), ('groups', I32),
                 ('sums', P), ('gamma', P), ('beta', P), ('eps', F32), ('silu', I32), ('ada', P), ('ada_stride', I64),
-                ('resample', I32), ('nplanes', I32), ('out_act', P), ('out_raw', P), ('out_raw_f32', P),
-                ('part0', P), ('part1', P), ('parts_per_sample', I32), ('pad1', I32)]
+                ('resample', I32), ('nplanes', I32), ('out_act', P), ('out_raw', P), ('out_raw_f32', P)]
 
 
 class SoftmaxDesc(C.Structure):
@@ -81,6 +80,11 @@ class GegluDesc(C.Structure):
     _fields_ = [('src', P), ('out', P), ('rows', I64), ('I', I32), ('nplanes', I32)]
 
 
+class GnFinalizeDesc(C.Structure):
+    _fields_ = [('quads0', P), ('quads1', P), ('C0', I32), ('C1', I32), ('slabs_per_sample', I32), ('B', I32), ('groups', I32),
+                ('pad0', I32), ('sums', P)]
+
+
 class MemsetDesc(C.Structure):
     _fields_ = [('ptr', P), ('bytes', I64)]
 
@@ -88,7 +92,7 @@ class MemsetDesc(C.Structure):
 class _OpUnion(C.Union):
     _fields_ = [('gemm', GemmDesc), ('gn_stats', GnStatsDesc), ('gn_apply', GnApplyDesc), ('softmax', SoftmaxDesc),
                 ('posemb', PosembDesc), ('linear', LinearDesc), ('prep_input', PrepInputDesc), ('chanmean', ChanmeanDesc),
-                ('memset', MemsetDesc), ('layernorm', LayernormDesc), ('geglu', GegluDesc)]
+                ('memset', MemsetDesc), ('layernorm', LayernormDesc), ('geglu', GegluDesc), ('gn_finalize', GnFinalizeDesc)]
 
 
 class PlanOp(C.Structure):
@@ -98,14 +102,14 @@ class PlanOp(C.Structure):
 SIZEOF_CHECKS = {
     0: PlanOp, DS_OP_GEMM: GemmDesc, DS_OP_GN_STATS: GnStatsDesc, DS_OP_GN_APPLY: GnApplyDesc, DS_OP_SOFTMAX: SoftmaxDesc,
     DS_OP_POSEMB: PosembDesc, DS_OP_LINEAR: LinearDesc, DS_OP_PREP_INPUT: PrepInputDesc, DS_OP_CHANMEAN: ChanmeanDesc,
-    DS_OP_MEMSET: MemsetDesc, DS_OP_LAYERNORM: LayernormDesc, DS_OP_GEGLU: GegluDesc,
+    DS_OP_MEMSET: MemsetDesc, DS_OP_LAYERNORM: LayernormDesc, DS_OP_GEGLU: GegluDesc, DS_OP_GN_FINALIZE: GnFinalizeDesc,
 }
 
 UNION_FIELD = {
     DS_OP_GEMM: 'gemm', DS_OP_GN_STATS: 'gn_stats', DS_OP_GN_APPLY: 'gn_apply', DS_OP_SOFTMAX: 'softmax', DS_OP_POSEMB: 'posemb',
     DS_OP_LINEAR: 'linear', DS_OP_PREP_INPUT: 'prep_input', DS_OP_CHANMEAN: 'chanmean', DS_OP_MEMSET: 'memset',
-    DS_OP_LAYERNORM: 'layernorm', DS_OP_GEGLU: 'geglu',
+    DS_OP_LAYERNORM: 'layernorm', DS_OP_GEGLU: 'geglu', DS_OP_GN_FINALIZE: 'gn_finalize',
 }
 OP_TYPE_OF = {GemmDesc: DS_OP_GEMM, GnStatsDesc: DS_OP_GN_STATS, GnApplyDesc: DS_OP_GN_APPLY, SoftmaxDesc: DS_OP_SOFTMAX,
               PosembDesc: DS_OP_POSEMB, LinearDesc: DS_OP_LINEAR, PrepInputDesc: DS_OP_PREP_INPUT, ChanmeanDesc: DS_OP_CHANMEAN,
-              MemsetDesc: DS_OP_MEMSET, LayernormDesc: DS_OP_LAYERNORM, GegluDesc: DS_OP_GEGLU}
+              MemsetDesc: DS_OP_MEMSET, LayernormDesc: DS_OP_LAYERNORM, GegluDesc: DS_OP_GEGLU, GnFinalizeDesc: DS_OP_GN_FINALIZE}

@@ -62,6 +62,32 @@ __global__ void gn_stats_kernel(ds_gn_stats_desc d, int pix_per_cta) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ GN statistics from quad partials
+// One CTA per sample.  Step 1: thread t owns the (quad, sum|sumsq) column t of the concatenated partial row (C/2 columns) and adds
+// it over the sample's slabs in fp64 (coalesced along t).  Step 2: thread j < 2*groups adds the cpg/4 quads of its group.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(ds_gn_finalize_desc d) {
+    extern __shared__ double s_cols[];
+    const int n = blockIdx.x;
+    const int w0 = d.C0 / 2, w1 = d.C1 / 2;           // floats per partial row of each source
+    for (int t = threadIdx.x; t < w0 + w1; t += blockDim.x) {
+        const float* src = (t < w0) ? d.quads0 + (long long)n * d.slabs_per_sample * w0 + t
+                                    : d.quads1 + (long long)n * d.slabs_per_sample * w1 + (t - w0);
+        const int pitch = (t < w0) ? w0 : w1;
+        double acc = 0.0;
+#pragma unroll 8
+        for (int sl = 0; sl < d.slabs_per_sample; ++sl) acc += (double)__ldg(src + (long long)sl * pitch);
+        s_cols[t] = acc;
+    }
+    __syncthreads();
+    const int qpg = (d.C0 + d.C1) / d.groups / 4;     // quads per group
+    for (int j = threadIdx.x; j < 2 * d.groups; j += blockDim.x) {
+        const int g = j >> 1, k = j & 1;
+        double acc = 0.0;
+        for (int q = g * qpg; q < (g + 1) * qpg; ++q) acc += s_cols[2 * q + k];
+        d.sums[((long long)n * d.groups + g) * 2 + k] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ GN apply
 // grid (chunks, B); block = nc8 * rows threads.  Thread (c8, prow) owns 8 fixed channels: its normalisation coefficients
 // live in registers (mean, a = rstd*gamma*(1+ada_scale), b = beta*(1+ada_scale)+ada_shift) and it streams over output pixels.
@@ -81,26 +107,8 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
     const int c8 = threadIdx.x % nc8;
     const int prow = threadIdx.x / nc8;
     const int c = c8 * 8;
-    const bool norm = d.sums != nullptr || d.part0 != nullptr;
+    const bool norm = d.sums != nullptr;
     float mean[8], a[8], b[8];
-    __shared__ double s_grp[64][2];
-    if (d.part0) {
-        // statistics from the producers' slab partials: thread t < 2*groups reduces (group t/2, {sum|sumsq}) over the sample's slabs
-        const int cpg_ = C / d.groups;
-        if ((int)threadIdx.x < 2 * d.groups) {
-            const int g = threadIdx.x >> 1, k = threadIdx.x & 1;
-            double acc = 0.0;
-            const bool in0 = g <= (d.C0 - 1) / cpg_;
-            const bool in1 = d.C1 > 0 && g >= d.C0 / cpg_;
-            const long long base_p = (long long)n * d.parts_per_sample;
-            for (int q = 0; q < d.parts_per_sample; ++q) {
-                if (in0) acc += (double)d.part0[((base_p + q) * d.groups + g) * 2 + k];
-                if (in1) acc += (double)d.part1[((base_p + q) * d.groups + g) * 2 + k];
-            }
-            s_grp[g][k] = acc;
-        }
-        __syncthreads();
-    }
     if (norm) {
         const int cpg = C / d.groups;
         const double cnt = (double)cpg * d.H * d.W;
@@ -110,8 +118,8 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
         for (int j = 0; j < 8; ++j) {
             const int g = (c + j) / cpg;
             if (g != g_prev) {                 // at most a few distinct groups per 8 channels
-                const double s = d.part0 ? s_grp[g][0] : d.sums[((long long)n * d.groups + g) * 2 + 0];
-                const double q = d.part0 ? s_grp[g][1] : d.sums[((long long)n * d.groups + g) * 2 + 1];
+                const double s = d.sums[((long long)n * d.groups + g) * 2 + 0];
+                const double q = d.sums[((long long)n * d.groups + g) * 2 + 1];
                 const double mu = s / cnt;
                 double var = q / cnt - mu * mu;
                 if (var < 0.0) var = 0.0;
@@ -560,6 +568,13 @@ extern "C" int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream
     while (pix_per_cta > 64 && (long long)((d->HW + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
     const int chunks = (d->HW + pix_per_cta - 1) / pix_per_cta;
     gn_stats_kernel<<<dim3(chunks, d->B), dim3(bx, by), 0, stream>>>(*d, pix_per_cta);
+    return ok();
+}
+
+extern "C" int ds_gn_finalize_launch(const ds_gn_finalize_desc* d, cudaStream_t stream) {
+    const int C = d->C0 + d->C1;
+    if (d->C0 % 4 || d->C1 % 4 || d->groups <= 0 || C % d->groups || (C / d->groups) % 4 || (d->C1 > 0 && !d->quads1)) return -2;
+    gn_finalize_kernel<<<d->B, 256, (size_t)(C / 2) * sizeof(double), stream>>>(*d);
     return ok();
 }
 

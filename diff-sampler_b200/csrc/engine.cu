@@ -58,13 +58,13 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_GEMM: {
             ds_gemm_desc& g = op.u.gemm;
             P(g.a_ptr); P(g.a2_ptr); P(g.b_ptr); P(g.out_f32); P(g.out_h16); P(g.bias_n); P(g.bias_m); P(g.rowvec);
-            P(g.residual); P(g.edm_x); P(g.edm_coef); P(g.edm_D); P(g.st_part[0]); P(g.st_part[1]);
+            P(g.residual); P(g.edm_x); P(g.edm_coef); P(g.edm_D); P(g.st_quads);
             break;
         }
         case DS_OP_GN_STATS: { auto& d = op.u.gn_stats; P(d.src0); P(d.src1); P(d.sums); break; }
         case DS_OP_GN_APPLY: {
             auto& d = op.u.gn_apply;
-            P(d.src0); P(d.src1); P(d.sums); P(d.gamma); P(d.beta); P(d.ada); P(d.out_act); P(d.out_raw); P(d.out_raw_f32); P(d.part0); P(d.part1);
+            P(d.src0); P(d.src1); P(d.sums); P(d.gamma); P(d.beta); P(d.ada); P(d.out_act); P(d.out_raw); P(d.out_raw_f32);
             break;
         }
         case DS_OP_SOFTMAX: { auto& d = op.u.softmax; P(d.S); P(d.P); break; }
@@ -75,6 +75,7 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_MEMSET: { auto& d = op.u.memset; P(d.ptr); break; }
         case DS_OP_LAYERNORM: { auto& d = op.u.layernorm; P(d.src); P(d.gamma); P(d.beta); P(d.out); break; }
         case DS_OP_GEGLU: { auto& d = op.u.geglu; P(d.src); P(d.out); break; }
+        case DS_OP_GN_FINALIZE: { auto& d = op.u.gn_finalize; P(d.quads0); P(d.quads1); P(d.sums); break; }
         default: break;
     }
 #undef P
@@ -94,6 +95,7 @@ static int launch_op(const ds_plan_op& op, const unsigned char* gemm_kp, cudaStr
         case DS_OP_CHANMEAN: return ds_chanmean_launch(&op.u.chanmean, s);
         case DS_OP_LAYERNORM: return ds_layernorm_launch(&op.u.layernorm, s);
         case DS_OP_GEGLU: return ds_geglu_launch(&op.u.geglu, s);
+        case DS_OP_GN_FINALIZE: return ds_gn_finalize_launch(&op.u.gn_finalize, s);
         case DS_OP_MEMSET:
             return cudaMemsetAsync(op.u.memset.ptr, 0, (size_t)op.u.memset.bytes, s) == cudaSuccess ? 0 : -1;
         default: return -100;
@@ -325,6 +327,7 @@ size_t ds_sizeof(int which) {
         case DS_OP_MEMSET: return sizeof(ds_memset_desc);
         case DS_OP_LAYERNORM: return sizeof(ds_layernorm_desc);
         case DS_OP_GEGLU: return sizeof(ds_geglu_desc);
+        case DS_OP_GN_FINALIZE: return sizeof(ds_gn_finalize_desc);
         default: return 0;
     }
 }

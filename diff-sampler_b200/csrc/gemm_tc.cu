@@ -52,8 +52,7 @@ struct alignas(64) GemmKernelParams {
     float* edm_D;
     // fused GroupNorm statistics of the tensor being written (up to two consumers with their own channel grouping):
     // per 32-row slab partial {sum, sumsq} per group, plain stores (no atomics); the consumer adds the slabs of a sample.
-    float* st_part[2];
-    int st_cpg[2], st_choff[2], st_groups[2];
+    float* st_quads;
     int tap_dh[9], tap_dw[9], tap_cb[9];
 };
 
@@ -65,38 +64,32 @@ struct SmemCtl {
     uint32_t tmem_base;
 };
 
-// Running GroupNorm-statistics state of one epilogue thread (one row of the tile), carried across the column chunks of a tile so
-// that a group spanning two chunks is reduced once.  Flush = warp reduction over the 32 rows + one plain store by lane 0.
-struct StatCarry {
-    float s1[2], s2[2];
-    int g_cur[2];       // group currently being accumulated (-1: sink unused)
-    int rem[2];         // columns left in that group
-};
-
-__device__ __noinline__ void stat_flush(const GemmKernelParams& p, StatCarry& st, int sidx, long long slab) {
-    float a = st.s1[sidx], b = st.s2[sidx];
+// Sum NV per-lane values over the 32 lanes of a warp with NV-ish shuffles instead of 5*NV: at every butterfly level each lane
+// keeps one half of its values and hands the other half to its partner, so the value count halves while the lane span doubles.
+// On return v[0] of lane L is the full sum of value index (L >> (5 - log2 NV)) (NV = 16: L >> 1; NV = 8: L >> 2).
+template <int NV>
+__device__ __forceinline__ void warp_sum_multi(float (&v)[NV], int lane) {
+    static_assert(NV == 16 || NV == 8, "NV");
+    int off = 16;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b += __shfl_xor_sync(0xffffffffu, b, o);
+    for (int n = NV / 2; n >= 1; n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const float send = up ? v[i] : v[i + n];
+            const float keep = up ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+        off >>= 1;
     }
-    if ((threadIdx.x & 31) == 0) {
-        float* dst = p.st_part[sidx] + (slab * p.st_groups[sidx] + st.g_cur[sidx]) * 2;
-        dst[0] = a;
-        dst[1] = b;
-    }
-    st.s1[sidx] = 0.f;
-    st.s2[sidx] = 0.f;
+    for (; off >= 1; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
 }
 
 template <int W>
 __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const float* v, long long grow_in_z, int col0, bool row_ok,
-                                               int zb, int zh, const float4* res_pref, bool res_in_regs, StatCarry& st) {
+                                               int zb, int zh, const float4* res_pref, bool res_in_regs) {
     // v[W]: accumulators of this thread's row, columns col0 .. col0+W-1 (col0 is the global column)
-    const bool has_stats = p.st_part[0] != nullptr;      // warp-uniform
-    if (!row_ok && !has_stats) return;
-    const long long slab = grow_in_z >> 5;
-    if (!row_ok) grow_in_z = 0;                            // keep loads in range; the row's values are zeroed below
+    if (!row_ok) return;                                   // warp-uniform whenever statistics are fused (m_valid % 32 == 0)
     float r[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] = v[j];
@@ -159,25 +152,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] *= p.scale;
 
-    if (has_stats) {
-        const bool plain = row_ok && full;                 // no masking needed (the common case)
+    if (p.st_quads) {
+        // GroupNorm partials of this 32-row slab: per channel quad {sum, sumsq}, reduced over the warp's 32 rows
+        float q[W / 2];
 #pragma unroll
-        for (int sidx = 0; sidx < 2; ++sidx) {
-            if (st.g_cur[sidx] < 0) continue;
-            const int cpg = p.st_cpg[sidx];
-#pragma unroll
-            for (int j = 0; j < W; ++j) {
-                const float val = plain ? r[j] : ((row_ok && col0 + j < p.n_valid) ? r[j] : 0.f);
-                st.s1[sidx] += val;
-                st.s2[sidx] = fmaf(val, val, st.s2[sidx]);
-                if (--st.rem[sidx] == 0) {                  // warp-uniform: group boundary (no per-column division)
-                    stat_flush(p, st, sidx, slab);
-                    ++st.g_cur[sidx];
-                    st.rem[sidx] = cpg;
-                }
-            }
+        for (int j = 0; j < W; j += 4) {
+            q[j / 2] = (r[j] + r[j + 1]) + (r[j + 2] + r[j + 3]);
+            q[j / 2 + 1] = fmaf(r[j], r[j], r[j + 1] * r[j + 1]) + fmaf(r[j + 2], r[j + 2], r[j + 3] * r[j + 3]);
         }
-        if (!row_ok) return;
+        const int lane = threadIdx.x & 31;
+        warp_sum_multi<W / 2>(q, lane);
+        constexpr int kShift = (W == 32) ? 1 : 2;            // lane L holds value L >> kShift = 2 * quad + {0: sum, 1: sumsq}
+        const int vi = lane >> kShift;
+        if ((lane & ((1 << kShift) - 1)) == 0 && col0 + 4 * (vi >> 1) < p.n_valid)
+            p.st_quads[((grow_in_z >> 5) * (long long)(p.n_valid >> 2)) * 2 + (col0 >> 1) + vi] = q[0];
     }
 
     if (p.edm_out) {
@@ -381,18 +369,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const long long grow = (long long)mt * 128 + row;
             const bool row_ok = grow < p.m_valid;
             const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
-            StatCarry st;
-            st.s1[0] = st.s1[1] = st.s2[0] = st.s2[1] = 0.f;
-#pragma unroll
-            for (int sidx = 0; sidx < 2; ++sidx) {
-                st.g_cur[sidx] = -1;
-                st.rem[sidx] = 0;
-                if (p.st_part[sidx]) {
-                    const int c0 = p.st_choff[sidx] + nt * p.BN;          // one division per tile and sink
-                    st.g_cur[sidx] = c0 / p.st_cpg[sidx];
-                    st.rem[sidx] = p.st_cpg[sidx] - (c0 - st.g_cur[sidx] * p.st_cpg[sidx]);
-                }
-            }
             // residual rows are prefetched one chunk ahead (registers) so their HBM latency overlaps the previous chunk's work
             const float* res_row = p.residual ? p.residual + (row_ok ? grow : 0) * p.ldr + (long long)nt * p.BN : nullptr;
             float4 res_next[8];
@@ -415,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 DSB_TMEM_LD_32(t_row + c, v);
                 tmem_ld_wait();
                 if (col0 < p.n_valid)
-                    epilogue_chunk<32>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, zb, zh, res_cur, in_regs, st);
+                    epilogue_chunk<32>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, zb, zh, res_cur, in_regs);
             }
             if (c < p.BN) {
                 uint32_t v[16];
@@ -423,14 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 tmem_ld_wait();
                 const int col0 = nt * p.BN + c;
                 if (col0 < p.n_valid)
-                    epilogue_chunk<16>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, zb, zh, nullptr, false, st);
-            }
-            if (p.st_part[0]) {
-                // a group cut by the end of this tensor's channel range (the rest belongs to the other concat source)
-#pragma unroll
-                for (int sidx = 0; sidx < 2; ++sidx)
-                    if (st.g_cur[sidx] >= 0 && st.rem[sidx] != p.st_cpg[sidx] && st.g_cur[sidx] < p.st_groups[sidx])
-                        stat_flush(p, st, sidx, grow >> 5);
+                    epilogue_chunk<16>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, zb, zh, nullptr, false);
             }
             tc_fence_before();
             __syncwarp();
@@ -510,14 +479,11 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     kp->residual = d->residual; kp->ldr = d->ldr; kp->scale = d->scale;
     kp->edm_out = d->edm_out; kp->edm_x = d->edm_x; kp->edm_coef = d->edm_coef; kp->edm_coef_stride = d->edm_coef_stride;
     kp->edm_C = d->edm_C; kp->edm_D = d->edm_D;
-    for (int k = 0; k < 2; ++k) {
-        kp->st_part[k] = d->st_part[k]; kp->st_cpg[k] = d->st_cpg[k] > 0 ? d->st_cpg[k] : 1;
-        kp->st_choff[k] = d->st_choff[k]; kp->st_groups[k] = d->st_groups[k];
-    }
+    kp->st_quads = d->st_quads;
     for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = d->tap_dh[t]; kp->tap_dw[t] = d->tap_dw[t]; kp->tap_cb[t] = d->tap_cb[t]; }
     if (d->taps != 1 && d->taps != 9) return -15;
-    if (d->st_part[1] && !d->st_part[0]) return -13;
-    if (d->st_part[0] && (d->a_mode != 0 || (d->conv_H * d->conv_W) % 32 != 0 || d->n_tiles != 1 && (d->BN % d->st_cpg[0]) != 0)) return -14;
+    // fused statistics: whole 32-row slabs (row validity is then warp-uniform), whole channel quads, one z slice, fp32 output
+    if (d->st_quads && (d->num_z != 1 || d->m_valid % 32 != 0 || d->n_valid % 4 != 0 || d->edm_out != 0)) return -14;
     const int stage_bytes = kATileBytes + d->BN * 128;
     int ns = (227 * 1024 - 2048) / stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;

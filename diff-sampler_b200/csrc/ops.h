@@ -70,13 +70,12 @@ typedef struct ds_gemm_desc {
     int32_t edm_coef_stride;// 0 (one sigma) or 4 (per-sample)
     int32_t edm_C;
     float* edm_D;
-    // fused GroupNorm statistics of the fp32 output (conv mode only): for each consumer k, the epilogue stores per 32-row slab
-    // the partial {sum, sumsq} of every group it touches: st_part[k][(row/32 * st_groups[k] + g)*2 + {0,1}],
-    // g = (st_choff[k] + channel) / st_cpg[k].  Plain stores, no atomics; gn_apply adds the slabs of a sample (parts_per_sample).
-    float* st_part[2];
-    int32_t st_cpg[2];
-    int32_t st_choff[2];
-    int32_t st_groups[2];
+    // fused GroupNorm statistics of the fp32 output (conv mode, m_valid % 32 == 0, n_valid % 4 == 0): the epilogue stores, per
+    // 32-row slab and per channel QUAD (4 consecutive channels), the partial {sum, sumsq}:
+    //   st_quads[((row/32) * (n_valid/4) + channel/4) * 2 + {0,1}]
+    // Plain coalesced stores, no atomics, independent of how consumers group the channels (every GroupNorm here has groups that
+    // are unions of quads); ds_gn_finalize adds the slabs of a sample and the quads of a group into the fp64 sums gn_apply reads.
+    float* st_quads;
     // conv taps: K block `tap` reads the pixel box shifted by (tap_dh, tap_dw) from channel base tap_cb.  A 3x3 stride-1 conv uses
     // (kh-1, kw-1, 0); a 3x3 stride-2 conv over a space-to-depth input [B][H/2][W/2][4C] uses shifts in {-1,0} and the phase's
     // channel base (LDM Downsample, openaimodel.py:134-160).
@@ -126,13 +125,21 @@ typedef struct ds_gn_apply_desc {
     void* out_act;          // fp16 [nplanes][B][Ho][Wo][C]; may be NULL
     void* out_raw;          // fp16 planes of the raw input; may be NULL
     float* out_raw_f32;     // fp32 raw input at output resolution; may be NULL
-    // alternative statistics source (sums == NULL): slab partials written by the producing GEMM epilogues (ds_gemm_desc.st_part),
-    // one buffer per source tensor, `parts_per_sample` = H*W/32 slabs per sample, `groups` columns each.
-    const float* part0;
-    const float* part1;
-    int32_t parts_per_sample;
-    int32_t pad1;
 } ds_gn_apply_desc;
+
+// GroupNorm statistics from the quad partials written by the producing GEMM epilogues (ds_gemm_desc.st_quads) of the one or two
+// (virtually concatenated) source tensors: sums[n][g] = {sum, sumsq} (fp64) over the sample's slabs and the group's quads.
+// Replaces the ds_gn_stats pass over the tensor itself (reads B*HW*C/64 floats instead of B*HW*C).
+typedef struct ds_gn_finalize_desc {
+    const float* quads0;    // [B * slabs_per_sample][C0/4][2]
+    const float* quads1;    // [B * slabs_per_sample][C1/4][2]; NULL when C1 == 0
+    int32_t C0, C1;
+    int32_t slabs_per_sample;   // H*W / 32
+    int32_t B;
+    int32_t groups;         // (C0 + C1) / groups must be a multiple of 4
+    int32_t pad0;
+    double* sums;           // [B][groups][2], overwritten
+} ds_gn_finalize_desc;
 
 // Row softmax: P = softmax(S) over the last dim, fp32 in, fp16 hi/lo planes out. Reference: networks_edm.py:108.
 typedef struct ds_softmax_desc {
@@ -271,6 +278,7 @@ int ds_update_launch(const ds_update_desc* d, cudaStream_t stream);
 int ds_threshold_launch(const ds_threshold_desc* d, cudaStream_t stream);
 int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream);
 int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream);
+int ds_gn_finalize_launch(const ds_gn_finalize_desc* d, cudaStream_t stream);
 int ds_softmax_launch(const ds_softmax_desc* d, cudaStream_t stream);
 int ds_posemb_launch(const ds_posemb_desc* d, cudaStream_t stream);
 int ds_linear_launch(const ds_linear_desc* d, cudaStream_t stream);
@@ -285,7 +293,8 @@ int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream);
 // and launches them in order.  Pointer fields hold references until resolved:
 //   bits 60..63 = space (0 absolute/NULL, 1 arena, 2 weights, 3 io slot), bits 0..59 = byte offset / slot.
 enum { DS_OP_GEMM = 1, DS_OP_GN_STATS = 2, DS_OP_GN_APPLY = 3, DS_OP_SOFTMAX = 4, DS_OP_POSEMB = 5, DS_OP_LINEAR = 6,
-       DS_OP_PREP_INPUT = 7, DS_OP_CHANMEAN = 8, DS_OP_MEMSET = 9, DS_OP_LAYERNORM = 10, DS_OP_GEGLU = 11 };
+       DS_OP_PREP_INPUT = 7, DS_OP_CHANMEAN = 8, DS_OP_MEMSET = 9, DS_OP_LAYERNORM = 10, DS_OP_GEGLU = 11,
+       DS_OP_GN_FINALIZE = 12 };
 enum { DS_IO_X = 0, DS_IO_D = 1, DS_IO_SIGMA = 2, DS_IO_LABELS = 3, DS_IO_BOTTLENECK = 4, DS_IO_CTX = 5, DS_IO_COUNT = 6 };
 
 typedef struct ds_memset_desc {
@@ -308,6 +317,7 @@ typedef struct ds_plan_op {
         ds_memset_desc memset;
         ds_layernorm_desc layernorm;
         ds_geglu_desc geglu;
+        ds_gn_finalize_desc gn_finalize;
     } u;
 } ds_plan_op;
 

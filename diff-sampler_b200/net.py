@@ -19,7 +19,7 @@ PRECISIONS = {'fp16x3': 3, 'fp16': 1}
 
 class B200Net:
     def __init__(self, params, img_resolution, img_channels, label_dim=0, sigma_min=0.002, sigma_max=80.0, sigma_data=0.5,
-                 precision='fp16x3', device='cuda', fuse_stats=False):
+                 precision='fp16x3', device='cuda', fuse_stats=True):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.DsError('B200Net needs a CUDA device (no CPU fallback)')

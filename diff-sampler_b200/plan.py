@@ -154,7 +154,7 @@ class Plan:
         self.meta = meta
 
 
-def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
+def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True):
     """Lower the forward pass for batch B.  nsig in {1, B}: number of sigma values (embedding rows);
     nlab in {0, 1, B}: rows of class labels supplied."""
     assert nsig in (1, B) and nlab in (0, 1, B)
@@ -171,62 +171,47 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=False):
     def emit(builder):
         ops.append((tag[0], builder))
 
-    # Fused GroupNorm statistics (fuse_stats=True): the GEMM that writes an fp32 tensor also stores, per 32-row slab, the partial
-    # {sum, sumsq} of every group its consumers need (at most two consumers: the next block and, for encoder outputs, the decoder block
-    # that concatenates it as a skip); gn_apply adds the slabs of a sample.  No atomics, no separate statistics pass.
-    prod_of = {}            # buffer name -> (op index, Cout, m_tiles) of the GEMM that last wrote it
-    sinks = {}              # producer op index -> [(partial buffer, cpg, channel offset, groups)]
-    stat_src = {}           # stats slot -> ('sums',) | ('parts', [buf0, buf1?], parts_per_sample)
+    # Fused GroupNorm statistics (fuse_stats=True): the GEMM that writes an fp32 tensor also stores, per 32-row slab and channel
+    # quad, the partial {sum, sumsq} (ds_gemm_desc.st_quads); a tiny ds_gn_finalize per GroupNorm folds slabs and quads into the
+    # fp64 sums gn_apply reads.  The partials are independent of the consumer's grouping, so one buffer per tensor serves both the
+    # next block and the decoder block that concatenates it as a skip.  No atomics, no pass over the tensor itself.
+    prod_of = {}            # buffer name -> (op index of the GEMM that wrote it, Cout, rows)
+    quads_of = {}           # producer op index -> arena name of its quad-partial buffer
 
     def emit_producer(name, cout, m_rows, build):
         pid = len(ops)
-        prod_of[name] = (pid, cout, -(-m_rows // 128))
-        sinks[pid] = []
+        prod_of[name] = (pid, cout, m_rows)
 
         def materialise(R):
             d = build(R)
-            for k, (buf, cpg, choff, groups) in enumerate(sinks[pid]):
-                d.st_part[k] = R(buf)
-                d.st_cpg[k], d.st_choff[k], d.st_groups[k] = cpg, choff, groups
+            if pid in quads_of:
+                d.st_quads = R(quads_of[pid])
             return d
         emit(materialise)
 
     def need_stats(slot, parts, hw):
         """GroupNorm statistics over the (virtually concatenated) fp32 tensors `parts` = [(buffer, channels), ...] for `slot`."""
+        assert len(parts) <= 2
         c_total = sum(c for _, c in parts)
         g = _groups(c_total)
         cpg = c_total // g
-        fusable = fuse_stats and hw % 32 == 0 and len(parts) <= 2
-        off = 0
-        for name, c in parts:
-            if not fusable:
-                break
-            pid, cout, m_tiles = prod_of[name]
-            bn, n_tiles = G.fill_bn(cout, m_tiles)
-            if len(sinks[pid]) >= 2 or (n_tiles > 1 and (bn % cpg or off % cpg)):
-                fusable = False          # a group would straddle two N tiles (e.g. 768 channels in 24-wide groups over 256-wide tiles)
-            off += c
+        (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
+        fusable = (fuse_stats and hw % 32 == 0 and cpg % 4 == 0 and all(c % 4 == 0 for _, c in parts)
+                   and all(name in prod_of and prod_of[name][1] == c for name, c in parts))
         if not fusable:
-            assert len(parts) <= 2
-            (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
             emit(lambda R: S.GnStatsDesc(src0=R(n0), src1=R(n1) if n1 else 0, C0=c0, C1=c1, HW=hw, B=B, groups=g, sums=R('stats', slot)))
-            stat_src[slot] = ('sums',)
             return
-        off, bufs = 0, []
-        for i, (name, c) in enumerate(parts):
-            pid, cout, m_tiles = prod_of[name]
-            buf = A.need(f'part:{slot}:{i}', m_tiles * 4 * g * 2 * F4)
-            sinks[pid].append((buf, cpg, off, g))
-            bufs.append(buf)
-            off += c
-        stat_src[slot] = ('parts', bufs, hw // 32)
+        bufs = []
+        for name, c in parts:
+            pid, cout, m_rows = prod_of[name]
+            if pid not in quads_of:
+                quads_of[pid] = A.need('quads:' + name, (m_rows // 32) * (cout // 4) * 2 * F4)
+            bufs.append(quads_of[pid])
+        emit(lambda R: S.GnFinalizeDesc(quads0=R(bufs[0]), quads1=R(bufs[1]) if len(bufs) > 1 else 0, C0=c0, C1=c1,
+                                        slabs_per_sample=hw // 32, B=B, groups=g, sums=R('stats', slot)))
 
     def stat_args(R, slot):
-        src = stat_src[slot]
-        if src[0] == 'sums':
-            return dict(sums=R('stats', slot), part0=0, part1=0, parts_per_sample=0)
-        bufs = src[1]
-        return dict(sums=0, part0=R(bufs[0]), part1=R(bufs[1]) if len(bufs) > 1 else 0, parts_per_sample=src[2])
+        return dict(sums=R('stats', slot))
 
     # ---------------- embedding ----------------------------------------------------------------------------------
     A.need('coef', nsig * 4 * F4)

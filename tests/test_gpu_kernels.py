@@ -371,10 +371,12 @@ def test_dyn_threshold_matches_torch_quantile(lib, n):
     assert (thr - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize('Bn,H,W,Cout,cpg1,choff2,ctot2', [(3, 16, 16, 128, 4, 64, 256), (5, 8, 8, 192, 6, 0, 192), (2, 32, 32, 256, 8, 256, 512)])
-def test_conv_epilogue_fused_groupnorm_stats(lib, Bn, H, W, Cout, cpg1, choff2, ctot2):
-    """The GEMM epilogue stores, per 32-row slab, the GroupNorm {sum, sumsq} partials of the tensor it writes, for two consumers with
-    different channel groupings (plain next-block norm; decoder concat where this tensor is one part of a wider channel axis)."""
+@pytest.mark.parametrize('Bn,H,W,Cout,groups_cat', [(3, 16, 16, 128, 32), (5, 8, 8, 192, 32), (2, 32, 32, 256, 32), (2, 8, 8, 48, 12)])
+def test_conv_epilogue_fused_groupnorm_stats(lib, Bn, H, W, Cout, groups_cat):
+    """The GEMM epilogue stores, per 32-row slab and channel quad, the {sum, sumsq} partials of the tensor it writes; ds_gn_finalize
+    folds them into the per-(sample, group) sums gn_apply reads -- for the tensor alone and as one part of a decoder concat (where a
+    group may straddle the two sources, e.g. 192 + 192 channels in 12-wide groups)."""
+    from diff_sampler_b200 import _cstructs as S
     from diff_sampler_b200 import gemm_desc as G
     torch.manual_seed(11)
     Cin = 64
@@ -385,34 +387,56 @@ def test_conv_epilogue_fused_groupnorm_stats(lib, Bn, H, W, Cout, cpg1, choff2, 
     wp = G.pack_conv_weight(w.cpu()).to(dev())
     M = Bn * H * W
     out = torch.zeros(M, Cout, device=dev())
-    g1 = Cout // cpg1
-    g2 = 32
-    cpg2 = ctot2 // g2
-    slabs = -(-M // 128) * 4
-    s1 = torch.full((slabs, g1, 2), float('nan'), device=dev())
-    s2 = torch.full((slabs, g2, 2), float('nan'), device=dev())
-    bn_full, _ = G.pick_bn(Cout)          # one N tile per row of groups (a group must not straddle two N tiles)
+    slabs = M // 32
+    quads = torch.full((slabs, Cout // 4, 2), float('nan'), device=dev())
     d, _ = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=9, npass=3, out_f32=out.data_ptr(), bias=bias.data_ptr(),
-                       scale=0.5, bn=bn_full)
-    d.st_part[0], d.st_cpg[0], d.st_choff[0], d.st_groups[0] = s1.data_ptr(), cpg1, 0, g1
-    d.st_part[1], d.st_cpg[1], d.st_choff[1], d.st_groups[1] = s2.data_ptr(), cpg2, choff2, g2
+                       scale=0.5)
+    d.st_quads = quads.data_ptr()
     lib.op_launch(d)
     sync()
     y = out.double()
-    pad = torch.zeros(slabs * 32, Cout, dtype=torch.float64, device=dev())
-    pad[:M] = y
-    ys = pad.reshape(slabs, 32, Cout)
-    r1 = torch.stack([ys.reshape(slabs, 32, g1, cpg1).sum(dim=(1, 3)), (ys ** 2).reshape(slabs, 32, g1, cpg1).sum(dim=(1, 3))], dim=-1)
-    e1 = (s1.double() - r1).abs().max().item()
-    glo, ghi = choff2 // cpg2, (choff2 + Cout - 1) // cpg2
-    r2 = torch.zeros(slabs, g2, 2, dtype=torch.float64, device=dev())
-    for c in range(Cout):
-        g = (choff2 + c) // cpg2
-        r2[:, g, 0] += ys[:, :, c].sum(dim=1)
-        r2[:, g, 1] += (ys[:, :, c] ** 2).sum(dim=1)
-    e2 = (s2[:, glo:ghi + 1].double() - r2[:, glo:ghi + 1]).abs().max().item()
-    print(f'fused stats partials: sink1 err {e1:.3e} sink2 err {e2:.3e} (max {r2.abs().max().item():.1f})')
+    ys = y.reshape(slabs, 32, Cout // 4, 4)
+    rq = torch.stack([ys.sum(dim=(1, 3)), (ys ** 2).sum(dim=(1, 3))], dim=-1)
+    eq = (quads.double() - rq).abs().max().item()
+    assert eq < 1e-4 * max(1.0, rq.abs().max().item()), eq
+    # finalize: the tensor alone (groups = min(32, C/4) as the EDM nets use) ...
+    g1 = min(32, Cout // 4)
+    while (Cout // g1) % 4:
+        g1 //= 2
+    sums = torch.full((Bn, g1, 2), float('nan'), dtype=torch.float64, device=dev())
+    lib.op_launch(S.GnFinalizeDesc(quads0=quads.data_ptr(), quads1=0, C0=Cout, C1=0, slabs_per_sample=H * W // 32, B=Bn, groups=g1,
+                                   sums=sums.data_ptr()))
+    yb = y.reshape(Bn, H * W, g1, Cout // g1)
+    r1 = torch.stack([yb.sum(dim=(1, 3)), (yb ** 2).sum(dim=(1, 3))], dim=-1)
+    # ... and as the first half of a concat [this tensor | this tensor again]
+    sums2 = torch.full((Bn, groups_cat, 2), float('nan'), dtype=torch.float64, device=dev())
+    lib.op_launch(S.GnFinalizeDesc(quads0=quads.data_ptr(), quads1=quads.data_ptr(), C0=Cout, C1=Cout, slabs_per_sample=H * W // 32, B=Bn,
+                                   groups=groups_cat, sums=sums2.data_ptr()))
+    sync()
+    yc = torch.cat([y, y], dim=1).reshape(Bn, H * W, groups_cat, 2 * Cout // groups_cat)
+    r2 = torch.stack([yc.sum(dim=(1, 3)), (yc ** 2).sum(dim=(1, 3))], dim=-1)
+    e1 = (sums - r1).abs().max().item()
+    e2 = (sums2 - r2).abs().max().item()
+    print(f'fused stats: quad partials err {eq:.3e}, finalize err {e1:.3e} / concat {e2:.3e} (max {r2.abs().max().item():.1f})')
     assert e1 < 1e-4 * max(1.0, r1.abs().max().item()) and e2 < 1e-4 * max(1.0, r2.abs().max().item())
+
+
+def test_fused_stats_rejects_partial_slabs(lib):
+    """st_quads needs whole 32-row slabs (here M = 2*4*4 = 32 is fine, 3*4*4 = 48 is not): rc -14, surfaced as DsError."""
+    from diff_sampler_b200 import gemm_desc as G
+    for Bn, ok_ in ((2, True), (3, False)):
+        x = planes(torch.randn(Bn, 4, 4, 64, device=dev()))
+        wp = G.pack_conv_weight(torch.randn(64, 64, 3, 3)).to(dev())
+        out = torch.zeros(Bn * 16, 64, device=dev())
+        quads = torch.zeros(Bn * 16 // 32 + 1, 16, 2, device=dev())
+        d, _ = G.conv_gemm(x.data_ptr(), Bn, 4, 4, 64, wp.data_ptr(), 64, taps=9, npass=3, out_f32=out.data_ptr())
+        d.st_quads = quads.data_ptr()
+        if ok_:
+            lib.op_launch(d)
+        else:
+            with pytest.raises(lib.DsError):
+                lib.op_launch(d)
+    sync()
 
 
 # --------------------------------------------------------------------------------------------- LDM (Stable Diffusion) building blocks

@@ -91,12 +91,14 @@ def test_denoiser_parity(name, precision, tol):
     assert err < tol
 
 
-def test_fused_groupnorm_stats_plan_matches():
-    """The optional plan variant that accumulates GroupNorm statistics in the GEMM epilogues gives the same denoiser output."""
+@pytest.mark.parametrize('fuse', [True, False])
+def test_fused_groupnorm_stats_plan_matches(fuse):
+    """The plan with GroupNorm statistics taken from the GEMM epilogues (default) and the one with the separate gn_stats pass give the
+    same denoiser output."""
     from oracle import edm_oracle as O
     from diff_sampler_b200.net import B200Net
     on, P, S = _oracle('tiny_adm')
-    nat = B200Net(P, S['img_resolution'], S['img_channels'], S['label_dim'], device=_dev(), fuse_stats=True)
+    nat = B200Net(P, S['img_resolution'], S['img_channels'], S['label_dim'], device=_dev(), fuse_stats=fuse)
     x = O.stacked_randn(range(3), (3, 16, 16)) * 2.0
     lab = _labels(S, 3)
     ref = on(x, torch.tensor(2.0), class_labels=lab)
