@@ -18,6 +18,10 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp);
 int gemm_run(const GemmKernelParams* kp, cudaStream_t stream);
 size_t gemm_params_size();
 void gemm_patch_edm(GemmKernelParams* kp, const float* x, float* D);
+struct AttnKernelParams;
+int attn_build(const ds_attn_desc* d, AttnKernelParams* kp);
+int attn_run(const AttnKernelParams* kp, cudaStream_t stream);
+size_t attn_params_size();
 }  // namespace dsb
 
 static thread_local std::string g_err;
@@ -42,7 +46,7 @@ struct ds_unet {
     void* arena = nullptr;
     size_t arena_bytes = 0;
     std::vector<ds_plan_op> ops;
-    std::vector<std::vector<unsigned char>> gemm_params;   // prebuilt kernel params per op (empty for non-GEMM)
+    std::vector<std::vector<unsigned char>> gemm_params;   // prebuilt kernel params (tensor maps) per GEMM / attention op, else empty
     std::vector<IoFix> fixes;
     int last_launches = 0;
     // optional per-op timing (bench/profiling only): one event pair per op, read back on demand
@@ -76,6 +80,7 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_LAYERNORM: { auto& d = op.u.layernorm; P(d.src); P(d.gamma); P(d.beta); P(d.out); break; }
         case DS_OP_GEGLU: { auto& d = op.u.geglu; P(d.src); P(d.out); break; }
         case DS_OP_GN_FINALIZE: { auto& d = op.u.gn_finalize; P(d.quads0); P(d.quads1); P(d.sums); break; }
+        case DS_OP_ATTN: { auto& d = op.u.attn; P(d.q); P(d.k); P(d.vt); P(d.out); break; }
         default: break;
     }
 #undef P
@@ -96,6 +101,9 @@ static int launch_op(const ds_plan_op& op, const unsigned char* gemm_kp, cudaStr
         case DS_OP_LAYERNORM: return ds_layernorm_launch(&op.u.layernorm, s);
         case DS_OP_GEGLU: return ds_geglu_launch(&op.u.geglu, s);
         case DS_OP_GN_FINALIZE: return ds_gn_finalize_launch(&op.u.gn_finalize, s);
+        case DS_OP_ATTN:
+            if (gemm_kp) return dsb::attn_run(reinterpret_cast<const dsb::AttnKernelParams*>(gemm_kp), s);
+            return ds_attn_launch(&op.u.attn, s);
         case DS_OP_MEMSET:
             return cudaMemsetAsync(op.u.memset.ptr, 0, (size_t)op.u.memset.bytes, s) == cudaSuccess ? 0 : -1;
         default: return -100;
@@ -180,15 +188,18 @@ int ds_unet_create(const ds_weights* w, const void* plan_ops, int n_ops, size_t 
         return fail(-5, buf);
     }
     for (int i = 0; i < n_ops; ++i) {
-        if (u->ops[i].type != DS_OP_GEMM) continue;
-        u->gemm_params[i].resize(dsb::gemm_params_size() + 64);
+        const int type = u->ops[i].type;
+        if (type != DS_OP_GEMM && type != DS_OP_ATTN) continue;
+        u->gemm_params[i].resize((type == DS_OP_GEMM ? dsb::gemm_params_size() : dsb::attn_params_size()) + 64);
         // keep 64-byte alignment for the embedded CUtensorMaps
         unsigned char* p = u->gemm_params[i].data();
         unsigned char* al = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 63) & ~uintptr_t(63));
-        int rc = dsb::gemm_build(&u->ops[i].u.gemm, reinterpret_cast<dsb::GemmKernelParams*>(al));
+        int rc = type == DS_OP_GEMM ? dsb::gemm_build(&u->ops[i].u.gemm, reinterpret_cast<dsb::GemmKernelParams*>(al))
+                                    : dsb::attn_build(&u->ops[i].u.attn, reinterpret_cast<dsb::AttnKernelParams*>(al));
         if (rc) {
             char buf[96];
-            snprintf(buf, sizeof buf, "ds_unet_create: gemm_build failed (rc %d) for op %d tag %d", rc, i, u->ops[i].tag);
+            snprintf(buf, sizeof buf, "ds_unet_create: %s failed (rc %d) for op %d tag %d", type == DS_OP_GEMM ? "gemm_build" : "attn_build", rc, i,
+                     u->ops[i].tag);
             ds_unet_destroy(u);
             return fail(-6, buf);
         }
@@ -227,10 +238,11 @@ int ds_unet_forward_io(ds_unet* u, const void* const* io_in, int n_io, void* str
     for (size_t i = 0; i < u->ops.size(); ++i) {
         ds_plan_op& op = u->ops[i];
         const unsigned char* kp = nullptr;
-        if (op.type == DS_OP_GEMM) {
+        if (op.type == DS_OP_GEMM || op.type == DS_OP_ATTN) {
             unsigned char* p = u->gemm_params[i].data();
             unsigned char* al = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 63) & ~uintptr_t(63));
-            if (op.u.gemm.edm_out) dsb::gemm_patch_edm(reinterpret_cast<dsb::GemmKernelParams*>(al), op.u.gemm.edm_x, op.u.gemm.edm_D);
+            if (op.type == DS_OP_GEMM && op.u.gemm.edm_out)
+                dsb::gemm_patch_edm(reinterpret_cast<dsb::GemmKernelParams*>(al), op.u.gemm.edm_x, op.u.gemm.edm_D);
             kp = al;
         }
         if (op.type == DS_OP_CHANMEAN && op.u.chanmean.out == nullptr) continue;   // bottleneck tap not requested
@@ -328,6 +340,7 @@ size_t ds_sizeof(int which) {
         case DS_OP_LAYERNORM: return sizeof(ds_layernorm_desc);
         case DS_OP_GEGLU: return sizeof(ds_geglu_desc);
         case DS_OP_GN_FINALIZE: return sizeof(ds_gn_finalize_desc);
+        case DS_OP_ATTN: return sizeof(ds_attn_desc);
         default: return 0;
     }
 }

@@ -429,7 +429,7 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int encode_map(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes, const int32_t* box) {
+int encode_map(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes, const int32_t* box) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return -1;
     cuuint64_t gd[5];

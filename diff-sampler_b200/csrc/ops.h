@@ -141,6 +141,20 @@ typedef struct ds_gn_finalize_desc {
     double* sums;           // [B][groups][2], overwritten
 } ds_gn_finalize_desc;
 
+// Fused softmax attention, head dim padded to 64 (attention.cu): out[b][l][h*64 + c] = sum_k softmax_k(scale * q_l . k_k) v_k[c].
+// All operands are fp16 hi/lo planes, plane p of a [B]-batched tensor at batch index p*B + b.
+// Reference: networks_edm.py:105-118, :174-178; ldm/modules/attention.py:152-196.
+typedef struct ds_attn_desc {
+    const void* q;          // [2][B][L][q_pitch]; head h reads channels q_c0 + h*64 ..
+    const void* k;          // [2][B][Lk][k_pitch]; head h reads channels k_c0 + h*64 ..
+    const void* vt;         // [2][B][nh*64][vt_pitch]: V transposed, keys contiguous (Lk <= vt_pitch valid)
+    void* out;              // [2][B][L][o_pitch]
+    int32_t B, nh, L, Lk;
+    int32_t q_pitch, q_c0, k_pitch, k_c0, vt_pitch, o_pitch;
+    int32_t nplanes;        // must be 2
+    float scale;            // > 0
+} ds_attn_desc;
+
 // Row softmax: P = softmax(S) over the last dim, fp32 in, fp16 hi/lo planes out. Reference: networks_edm.py:108.
 typedef struct ds_softmax_desc {
     const float* S;
@@ -279,6 +293,7 @@ int ds_threshold_launch(const ds_threshold_desc* d, cudaStream_t stream);
 int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream);
 int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream);
 int ds_gn_finalize_launch(const ds_gn_finalize_desc* d, cudaStream_t stream);
+int ds_attn_launch(const ds_attn_desc* d, cudaStream_t stream);
 int ds_softmax_launch(const ds_softmax_desc* d, cudaStream_t stream);
 int ds_posemb_launch(const ds_posemb_desc* d, cudaStream_t stream);
 int ds_linear_launch(const ds_linear_desc* d, cudaStream_t stream);
@@ -294,7 +309,7 @@ int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream);
 //   bits 60..63 = space (0 absolute/NULL, 1 arena, 2 weights, 3 io slot), bits 0..59 = byte offset / slot.
 enum { DS_OP_GEMM = 1, DS_OP_GN_STATS = 2, DS_OP_GN_APPLY = 3, DS_OP_SOFTMAX = 4, DS_OP_POSEMB = 5, DS_OP_LINEAR = 6,
        DS_OP_PREP_INPUT = 7, DS_OP_CHANMEAN = 8, DS_OP_MEMSET = 9, DS_OP_LAYERNORM = 10, DS_OP_GEGLU = 11,
-       DS_OP_GN_FINALIZE = 12 };
+       DS_OP_GN_FINALIZE = 12, DS_OP_ATTN = 13 };
 enum { DS_IO_X = 0, DS_IO_D = 1, DS_IO_SIGMA = 2, DS_IO_LABELS = 3, DS_IO_BOTTLENECK = 4, DS_IO_CTX = 5, DS_IO_COUNT = 6 };
 
 typedef struct ds_memset_desc {
@@ -318,6 +333,7 @@ typedef struct ds_plan_op {
         ds_layernorm_desc layernorm;
         ds_geglu_desc geglu;
         ds_gn_finalize_desc gn_finalize;
+        ds_attn_desc attn;
     } u;
 } ds_plan_op;
 

@@ -27,7 +27,7 @@ def make_alphas_cumprod(linear_start=0.00085, linear_end=0.0120, n=1000):
 
 class B200LDMNet:
     def __init__(self, params, img_resolution=64, img_channels=4, num_heads=8, alphas_cumprod=None, guidance_type='classifier-free',
-                 guidance_rate=1.0, epsilon_t=1e-3, precision='fp16x3', device='cuda'):
+                 guidance_rate=1.0, epsilon_t=1e-3, precision='fp16x3', device='cuda', flash_attn=True):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.DsError('B200LDMNet needs a CUDA device (no CPU fallback)')
@@ -35,6 +35,7 @@ class B200LDMNet:
         self.img_resolution, self.img_channels, self.label_dim = img_resolution, img_channels, True
         self.guidance_type, self.guidance_rate = guidance_type, guidance_rate
         self.npass = PRECISIONS[precision]
+        self.flash_attn = bool(flash_attn)
         self.st = ldm_plan.ldm_structure(params, num_heads)
         self.wb, self.info = ldm_plan.pack_ldm_weights(self.st, params)
         blob = self.wb.bytes()
@@ -95,7 +96,8 @@ class B200LDMNet:
         key = (B, Bt, nT)
         ent = self._plans.get(key)
         if ent is None:
-            pl = ldm_plan.compile_ldm_plan(self.st, self.wb, self.info, B, Bt, nT, self.img_resolution, npass=self.npass)
+            pl = ldm_plan.compile_ldm_plan(self.st, self.wb, self.info, B, Bt, nT, self.img_resolution, npass=self.npass,
+                                               flash_attn=self.flash_attn)
             h = C.c_void_p()
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.ds_unet_create(self._wh, C.cast(pl.ops_array, C.c_void_p), pl.n_ops, C.sizeof(S.PlanOp), pl.arena_bytes,

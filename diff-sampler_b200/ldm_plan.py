@@ -177,7 +177,7 @@ def pack_ldm_weights(st, params):
     return wb, info
 
 
-def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77):
+def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_attn=True):
     """Lower the eps-net for Bt samples (Bt = B, or 2B under classifier-free guidance) at latent resolution R.
     nT in {1, Bt}: number of timestep values.  io: X = x [B,C,R,R], SIGMA = timesteps [nT], LABELS = coef [B|1][4] (c_in in slot 2),
     CTX = context [Bt, 77, ctx_dim], D = eps [Bt,C,R,R] (NCHW), BOTTLENECK = channel-mean of the middle block [Bt, 64]."""
@@ -289,8 +289,9 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77):
         A.need('ln', npl * M * inner * H2)
         A.need('qk', npl * M * 2 * hp * H2)
         A.need('vt', npl * Bt * hp * max(Lq, TP) * H2)
-        A.need('S', Bt * heads * Lq * max(Lq, 80) * F4)
-        A.need('P', npl * Bt * heads * Lq * max(Lq, TP) * H2)
+        if not (flash_attn and dp == 64 and npl == 2):
+            A.need('S', Bt * heads * Lq * max(Lq, 80) * F4)
+            A.need('P', npl * Bt * heads * Lq * max(Lq, TP) * H2)
         A.need('o', npl * M * hp * H2)
 
         def ln(k, srcbuf):
@@ -301,13 +302,19 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77):
         emit(lambda R_: G.conv_gemm(R_('ln'), Bt, H, H, inner, W(t + '.attn1.qk:w'), 2 * hp, taps=1, npass=npass, out_h16=R_('qk'))[0])
         emit(lambda R_: G.rows_gemm(W(t + '.attn1.v:w'), hp, inner, 1, R_('ln'), Lq, inner, Bt, inner, num_z=Bt, nh=1, m_valid=hp, n_valid=Lq,
                                     npass=npass, b_z_per_zb=1, out_h16=R_('vt'), o_zb=hp * Lq, ldo=Lq, o_plane=Bt * hp * Lq)[0])
-        emit(lambda R_: G.rows_gemm(R_('qk'), Lq, 2 * hp, Bt, R_('qk'), Lq, 2 * hp, Bt, dp, num_z=Bt * heads, nh=heads, m_valid=Lq, n_valid=Lq,
-                                    npass=npass, a_c_per_zh=dp, a_n_per_zb=1, b_k0=hp, b_k_per_zh=dp, b_z_per_zb=1, out_f32=R_('S'),
-                                    o_zb=heads * Lq * Lq, o_zh=Lq * Lq, ldo=Lq, scale=dh ** -0.5)[0])
-        emit(lambda R_: S.SoftmaxDesc(S=R_('S'), P=R_('P'), rows=Bt * heads * Lq, L=Lq, nplanes=npl, pitch_in=0, pitch_out=0))
-        emit(lambda R_: G.rows_gemm(R_('P'), Lq, Lq, Bt * heads, R_('vt'), hp, Lq, Bt, Lq, num_z=Bt * heads, nh=heads, m_valid=Lq, n_valid=dp,
-                                    npass=npass, a_n_per_zb=heads, a_n_per_zh=1, b_row_per_zh=dp, b_z_per_zb=1, out_h16=R_('o'),
-                                    o_zb=Lq * hp, o_zh=dp, ldo=hp, o_plane=M * hp)[0])
+        flash = flash_attn and dp == 64 and npl == 2
+        if flash:
+            # fused QK^T -> softmax -> PV (attention.cu): at 64x64 latents the 4096 x 4096 score matrix per head never reaches HBM
+            emit(lambda R_: S.AttnDesc(q=R_('qk'), k=R_('qk'), vt=R_('vt'), out=R_('o'), B=Bt, nh=heads, L=Lq, Lk=Lq, q_pitch=2 * hp, q_c0=0,
+                                       k_pitch=2 * hp, k_c0=hp, vt_pitch=Lq, o_pitch=hp, nplanes=npl, scale=dh ** -0.5))
+        else:
+            emit(lambda R_: G.rows_gemm(R_('qk'), Lq, 2 * hp, Bt, R_('qk'), Lq, 2 * hp, Bt, dp, num_z=Bt * heads, nh=heads, m_valid=Lq, n_valid=Lq,
+                                        npass=npass, a_c_per_zh=dp, a_n_per_zb=1, b_k0=hp, b_k_per_zh=dp, b_z_per_zb=1, out_f32=R_('S'),
+                                        o_zb=heads * Lq * Lq, o_zh=Lq * Lq, ldo=Lq, scale=dh ** -0.5)[0])
+            emit(lambda R_: S.SoftmaxDesc(S=R_('S'), P=R_('P'), rows=Bt * heads * Lq, L=Lq, nplanes=npl, pitch_in=0, pitch_out=0))
+            emit(lambda R_: G.rows_gemm(R_('P'), Lq, Lq, Bt * heads, R_('vt'), hp, Lq, Bt, Lq, num_z=Bt * heads, nh=heads, m_valid=Lq, n_valid=dp,
+                                        npass=npass, a_n_per_zb=heads, a_n_per_zh=1, b_row_per_zh=dp, b_z_per_zb=1, out_h16=R_('o'),
+                                        o_zb=Lq * hp, o_zh=dp, ldo=hp, o_plane=M * hp)[0])
         emit(lambda R_: G.conv_gemm(R_('o'), Bt, H, H, hp, W(t + '.attn1.out:w'), inner, taps=1, npass=npass, out_f32=R_('t1'),
                                     bias=W(t + '.attn1.out:b'), residual=R_('t0'), ldr=inner)[0])
         # ---- cross-attention (attn2): x = attn2(norm2(x), context) + x
@@ -319,13 +326,17 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77):
                                     npass=npass, out_h16=R_('k2'), ldo=hp, o_plane=Bt * T * hp)[0])
         emit(lambda R_: G.rows_gemm(W(t + '.attn2.v:w'), hp, cd, 1, R_('ctx'), T, cd, Bt, cd, num_z=Bt, nh=1, m_valid=hp, n_valid=T,
                                     npass=npass, b_z_per_zb=1, out_h16=R_('vt'), o_zb=hp * TP, ldo=TP, o_plane=Bt * hp * TP)[0])
-        emit(lambda R_: G.rows_gemm(R_('q2'), Lq, hp, Bt, R_('k2'), T, hp, Bt, dp, num_z=Bt * heads, nh=heads, m_valid=Lq, n_valid=T,
-                                    npass=npass, a_c_per_zh=dp, a_n_per_zb=1, b_k_per_zh=dp, b_z_per_zb=1, out_f32=R_('S'),
-                                    o_zb=heads * Lq * 80, o_zh=Lq * 80, ldo=80, scale=dh ** -0.5)[0])
-        emit(lambda R_: S.SoftmaxDesc(S=R_('S'), P=R_('P'), rows=Bt * heads * Lq, L=T, nplanes=npl, pitch_in=80, pitch_out=TP))
-        emit(lambda R_: G.rows_gemm(R_('P'), Lq, TP, Bt * heads, R_('vt'), hp, TP, Bt, TP, num_z=Bt * heads, nh=heads, m_valid=Lq, n_valid=dp,
-                                    npass=npass, a_n_per_zb=heads, a_n_per_zh=1, b_row_per_zh=dp, b_z_per_zb=1, out_h16=R_('o'),
-                                    o_zb=Lq * hp, o_zh=dp, ldo=hp, o_plane=M * hp, a_k_valid=T, b_k_valid=T)[0])
+        if flash:
+            emit(lambda R_: S.AttnDesc(q=R_('q2'), k=R_('k2'), vt=R_('vt'), out=R_('o'), B=Bt, nh=heads, L=Lq, Lk=T, q_pitch=hp, q_c0=0,
+                                       k_pitch=hp, k_c0=0, vt_pitch=TP, o_pitch=hp, nplanes=npl, scale=dh ** -0.5))
+        else:
+            emit(lambda R_: G.rows_gemm(R_('q2'), Lq, hp, Bt, R_('k2'), T, hp, Bt, dp, num_z=Bt * heads, nh=heads, m_valid=Lq, n_valid=T,
+                                        npass=npass, a_c_per_zh=dp, a_n_per_zb=1, b_k_per_zh=dp, b_z_per_zb=1, out_f32=R_('S'),
+                                        o_zb=heads * Lq * 80, o_zh=Lq * 80, ldo=80, scale=dh ** -0.5)[0])
+            emit(lambda R_: S.SoftmaxDesc(S=R_('S'), P=R_('P'), rows=Bt * heads * Lq, L=T, nplanes=npl, pitch_in=80, pitch_out=TP))
+            emit(lambda R_: G.rows_gemm(R_('P'), Lq, TP, Bt * heads, R_('vt'), hp, TP, Bt, TP, num_z=Bt * heads, nh=heads, m_valid=Lq, n_valid=dp,
+                                        npass=npass, a_n_per_zb=heads, a_n_per_zh=1, b_row_per_zh=dp, b_z_per_zb=1, out_h16=R_('o'),
+                                        o_zb=Lq * hp, o_zh=dp, ldo=hp, o_plane=M * hp, a_k_valid=T, b_k_valid=T)[0])
         emit(lambda R_: G.conv_gemm(R_('o'), Bt, H, H, hp, W(t + '.attn2.out:w'), inner, taps=1, npass=npass, out_f32=R_('t2'),
                                     bias=W(t + '.attn2.out:b'), residual=R_('t1'), ldr=inner)[0])
         # ---- GEGLU feed-forward: x = ff(norm3(x)) + x

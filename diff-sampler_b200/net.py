@@ -19,7 +19,7 @@ PRECISIONS = {'fp16x3': 3, 'fp16': 1}
 
 class B200Net:
     def __init__(self, params, img_resolution, img_channels, label_dim=0, sigma_min=0.002, sigma_max=80.0, sigma_data=0.5,
-                 precision='fp16x3', device='cuda', fuse_stats=True):
+                 precision='fp16x3', device='cuda', fuse_stats=True, flash_attn=True):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.DsError('B200Net needs a CUDA device (no CPU fallback)')
@@ -29,6 +29,7 @@ class B200Net:
         self.precision = precision
         self.npass = PRECISIONS[precision]
         self.fuse_stats = bool(fuse_stats)
+        self.flash_attn = bool(flash_attn)
         self.spec = edm_nets.spec_from_params(params, img_resolution, img_channels, label_dim)
         self.spec.sigma_data = sigma_data
         self.wb, self.winfo = planner.pack_weights(self.spec, params)
@@ -61,7 +62,8 @@ class B200Net:
         key = (B, nsig, nlab)
         ent = self._plans.get(key)
         if ent is None:
-            pl = planner.compile_plan(self.spec, self.wb, self.winfo, B, nsig, nlab, npass=self.npass, fuse_stats=self.fuse_stats)
+            pl = planner.compile_plan(self.spec, self.wb, self.winfo, B, nsig, nlab, npass=self.npass, fuse_stats=self.fuse_stats,
+                                           flash_attn=self.flash_attn)
             h = C.c_void_p()
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.ds_unet_create(self._wh, C.cast(pl.ops_array, C.c_void_p), pl.n_ops, C.sizeof(S.PlanOp),

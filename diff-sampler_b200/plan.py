@@ -154,7 +154,7 @@ class Plan:
         self.meta = meta
 
 
-def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True):
+def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash_attn=True):
     """Lower the forward pass for batch B.  nsig in {1, B}: number of sigma values (embedding rows);
     nlab in {0, 1, B}: rows of class labels supplied."""
     assert nsig in (1, B) and nlab in (0, 1, B)
@@ -329,21 +329,26 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True):
                                          resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))
             A.need('qk', npl * B * L * 2 * cout * H2)
             A.need('vt', npl * B * cout * L * H2)
-            A.need('S', B * nh * L * L * F4)
-            A.need('P', npl * B * nh * L * L * H2)
             A.need('o', npl * B * L * cout * H2)
             emit(lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cout, W(n + '.qk:w'), 2 * cout, taps=1, npass=npass, out_h16=R('qk'),
                                        bias=W(n + '.qk:b'))[0])
             emit(lambda R: G.rows_gemm(W(n + '.v:w'), cout, cout, 1, R('act'), L, cout, B, cout, num_z=B, nh=1, m_valid=cout,
                                        n_valid=L, npass=npass, b_z_per_zb=1, out_h16=R('vt'), o_zb=cout * L, ldo=L,
                                        o_plane=B * cout * L, bias_m=W(n + '.v:b'))[0])
-            emit(lambda R: G.rows_gemm(R('qk'), L, 2 * cout, B, R('qk'), L, 2 * cout, B, d, num_z=B * nh, nh=nh, m_valid=L, n_valid=L,
-                                       npass=npass, a_c_per_zh=d, a_n_per_zb=1, b_k0=cout, b_k_per_zh=d, b_z_per_zb=1,
-                                       out_f32=R('S'), o_zb=nh * L * L, o_zh=L * L, ldo=L, scale=1.0 / math.sqrt(d))[0])
-            emit(lambda R: S.SoftmaxDesc(S=R('S'), P=R('P'), rows=B * nh * L, L=L, nplanes=npl))
-            emit(lambda R: G.rows_gemm(R('P'), L, L, B * nh, R('vt'), cout, L, B, L, num_z=B * nh, nh=nh, m_valid=L, n_valid=d,
-                                       npass=npass, a_n_per_zb=nh, a_n_per_zh=1, b_row_per_zh=d, b_z_per_zb=1, out_h16=R('o'),
-                                       o_zb=L * cout, o_zh=d, ldo=cout, o_plane=B * L * cout)[0])
+            if flash_attn and d == 64 and npl == 2 and L % 8 == 0:
+                # one fused kernel per attention layer: the L x L score matrix never leaves the SM (attention.cu)
+                emit(lambda R: S.AttnDesc(q=R('qk'), k=R('qk'), vt=R('vt'), out=R('o'), B=B, nh=nh, L=L, Lk=L, q_pitch=2 * cout, q_c0=0,
+                                          k_pitch=2 * cout, k_c0=cout, vt_pitch=L, o_pitch=cout, nplanes=npl, scale=1.0 / math.sqrt(d)))
+            else:
+                A.need('S', B * nh * L * L * F4)
+                A.need('P', npl * B * nh * L * L * H2)
+                emit(lambda R: G.rows_gemm(R('qk'), L, 2 * cout, B, R('qk'), L, 2 * cout, B, d, num_z=B * nh, nh=nh, m_valid=L, n_valid=L,
+                                           npass=npass, a_c_per_zh=d, a_n_per_zb=1, b_k0=cout, b_k_per_zh=d, b_z_per_zb=1,
+                                           out_f32=R('S'), o_zb=nh * L * L, o_zh=L * L, ldo=L, scale=1.0 / math.sqrt(d))[0])
+                emit(lambda R: S.SoftmaxDesc(S=R('S'), P=R('P'), rows=B * nh * L, L=L, nplanes=npl))
+                emit(lambda R: G.rows_gemm(R('P'), L, L, B * nh, R('vt'), cout, L, B, L, num_z=B * nh, nh=nh, m_valid=L, n_valid=d,
+                                           npass=npass, a_n_per_zb=nh, a_n_per_zh=1, b_row_per_zh=d, b_z_per_zb=1, out_h16=R('o'),
+                                           o_zb=L * cout, o_zh=d, ldo=cout, o_plane=B * L * cout)[0])
             emit_producer(xout, cout, Mo, lambda R: G.conv_gemm(R('o'), B, Ho, Ho, cout, W(n + '.proj:w'), cout, taps=1, npass=npass, out_f32=R(xout),
                                                       bias=W(n + '.proj:b'), residual=R(mid), ldr=cout, scale=b.skip_scale)[0])
         if n == spec.bottleneck_block:

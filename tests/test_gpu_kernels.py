@@ -439,6 +439,55 @@ def test_fused_stats_rejects_partial_slabs(lib):
     sync()
 
 
+# --------------------------------------------------------------------------------------------- fused attention
+@pytest.mark.parametrize('B,nh,L,Lk,d', [(2, 3, 256, 256, 64), (1, 2, 192, 77, 40), (3, 1, 64, 64, 64), (1, 8, 1024, 1024, 40),
+                                         (2, 2, 320, 200, 64)])
+def test_fused_attention(lib, B, nh, L, Lk, d):
+    """attn_kernel (QK^T -> online softmax -> PV in one kernel, head dim padded to 64) against float64 softmax attention on the
+    same fp16 hi+lo operands: self-attention shapes, a cross-attention shape (77 keys, pitch 80), partial query / key tiles."""
+    from diff_sampler_b200 import _cstructs as S
+    torch.manual_seed(5)
+    hp = nh * 64
+    q = torch.randn(B, nh, L, d, device=dev()) * 1.5
+    k = torch.randn(B, nh, Lk, d, device=dev()) * 1.5
+    v = torch.randn(B, nh, Lk, d, device=dev())
+    k[:, :, 3] *= 4.0                                    # a dominant key: peaky rows
+    scale = d ** -0.5
+    qk = torch.zeros(B, max(L, Lk), 2 * hp, device=dev())
+    for h in range(nh):
+        qk[:, :L, h * 64:h * 64 + d] = q[:, h]
+        qk[:, :Lk, hp + h * 64:hp + h * 64 + d] = k[:, h]
+    self_attn = (L == Lk)
+    if self_attn:
+        qa = planes(qk)                                  # [2][B][L][2*hp]: q and k side by side as the nets store them
+        q_ptr = k_ptr = qa.data_ptr()
+        q_pitch = k_pitch = 2 * hp
+        q_c0, k_c0 = 0, hp
+    else:
+        qa = planes(qk[:, :L, :hp].contiguous())
+        ka = planes(qk[:, :Lk, hp:].contiguous())
+        q_ptr, k_ptr, q_pitch, k_pitch, q_c0, k_c0 = qa.data_ptr(), ka.data_ptr(), hp, hp, 0, 0
+    vt_pitch = (Lk + 7) // 8 * 8
+    vt = torch.zeros(B, hp, vt_pitch, device=dev())
+    for h in range(nh):
+        vt[:, h * 64:h * 64 + d, :Lk] = v[:, h].transpose(1, 2)
+    vta = planes(vt)
+    out = torch.full((2, B, L, hp), float('nan'), dtype=torch.float16, device=dev())
+    lib.op_launch(S.AttnDesc(q=q_ptr, k=k_ptr, vt=vta.data_ptr(), out=out.data_ptr(), B=B, nh=nh, L=L, Lk=Lk, q_pitch=q_pitch, q_c0=q_c0,
+                             k_pitch=k_pitch, k_c0=k_c0, vt_pitch=vt_pitch, o_pitch=hp, nplanes=2, scale=scale))
+    sync()
+    got = (out[0].double() + out[1].double()).reshape(B, L, nh, 64).permute(0, 2, 1, 3)
+    # reference on the operands as the kernel sees them (hi + lo), float64
+    qd = (planes(q)[0].double() + planes(q)[1].double())
+    kd = (planes(k)[0].double() + planes(k)[1].double())
+    vd = (planes(v)[0].double() + planes(v)[1].double())
+    ref = torch.softmax(scale * qd @ kd.transpose(-1, -2), dim=-1) @ vd
+    err = (got[..., :d] - ref).abs().max().item()
+    pad = got[..., d:].abs().max().item() if d < 64 else 0.0
+    print(f'fused attention B{B} nh{nh} L{L} Lk{Lk} d{d}: err {err:.3e} (max {ref.abs().max().item():.2f}), pad {pad:.1e}')
+    assert err < 2e-5 * max(1.0, ref.abs().max().item()) and pad == 0.0
+
+
 # --------------------------------------------------------------------------------------------- LDM (Stable Diffusion) building blocks
 def test_layernorm_geglu_softmax_generic(lib):
     from diff_sampler_b200 import _cstructs as S

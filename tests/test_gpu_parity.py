@@ -309,14 +309,45 @@ def test_fullsize_batch_independence_and_properties():
     assert (y2 - y).abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize('name', ['tiny_song', 'tiny_adm'])
+def test_unfused_attention_plan_matches(name):
+    """flash_attn=False keeps the QK^T GEMM -> softmax -> PV GEMM lowering (used for heads wider than 64); both lowerings hold the
+    oracle tolerance on the nets whose heads are 64 wide (where the default is the fused kernel)."""
+    from oracle import edm_oracle as O
+    from diff_sampler_b200.net import B200Net
+    on, P, S = _oracle(name)
+    x = O.stacked_randn(range(3), (3, 16, 16)) * 2.0
+    lab = _labels(S, 3)
+    ref = on(x, torch.tensor(2.0), class_labels=lab)
+    for flash in (True, False):
+        nat = B200Net(P, S['img_resolution'], S['img_channels'], S['label_dim'], device=_dev(), flash_attn=flash)
+        got = nat(x.to(_dev()), torch.tensor(2.0, device=_dev()), class_labels=None if lab is None else lab.to(_dev())).cpu()
+        err = (got - ref).abs().max().item()
+        print(f'{name} flash_attn={flash}: {err:.3e}')
+        assert err < TOL
+
+
+def test_ldm_unfused_attention_matches():
+    from oracle import edm_oracle as O
+    on, nat, cfg = _ldm_pair(flash_attn=False)
+    B, R = 2, cfg['img_resolution']
+    x0 = O.stacked_randn(range(B), (4, R, R))
+    g = torch.Generator().manual_seed(6)
+    c = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    uc = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    ref = on(x0 * 2.0, torch.tensor([2.0]), condition=c, unconditional_condition=uc)
+    got = nat((x0 * 2.0).to(_dev()), torch.tensor([2.0], device=_dev()), condition=c.to(_dev()), unconditional_condition=uc.to(_dev())).cpu()
+    assert (got - ref).abs().max().item() < TOL * max(1.0, ref.abs().max().item())
+
+
 # --------------------------------------------------------------------------------------------- latent diffusion (config 5)
-def _ldm_pair(name='tiny_ldm', guidance=7.5, precision='fp16x3'):
+def _ldm_pair(name='tiny_ldm', guidance=7.5, precision='fp16x3', flash_attn=True):
     from oracle import ldm_oracle as LO
     from diff_sampler_b200.ldm_net import B200LDMNet
     P, cfg = LO.make_params(name)
     on = LO.OracleCFGNet(P, cfg, guidance_rate=guidance)
     nat = B200LDMNet(P, img_resolution=cfg['img_resolution'], img_channels=cfg['in_channels'], num_heads=cfg['num_heads'],
-                     guidance_rate=guidance, precision=precision, device=_dev())
+                     guidance_rate=guidance, precision=precision, device=_dev(), flash_attn=flash_attn)
     return on, nat, cfg
 
 

@@ -45,9 +45,13 @@ def test_plan_lowering_invariants(name, B):
                 assert (g.a_ptr >> 60) in (S.SPACE_ARENA, S.SPACE_WEIGHTS) and (g.b_ptr >> 60) in (S.SPACE_ARENA, S.SPACE_WEIGHTS)
                 assert all(s % 16 == 0 for s in g.a_strides) and all(s % 16 == 0 for s in g.b_strides)
         assert n_gemm == pl.meta['n_gemm'] and pl.arena_bytes > 0
-    # every conv of the reference is lowered exactly once: stem + 2 per block + 4 extra per attention block (+1 head)
+    # every conv of the reference is lowered exactly once: stem + 2 per block (+1 head); an attention block adds qk, v, proj and
+    # either the fused attention op (64-wide heads) or the QK^T / PV GEMM pair around a softmax
     blocks = spec.enc + spec.dec
-    assert pl.meta['n_gemm'] == 1 + 2 * len(blocks) + 5 * sum(1 for b in blocks if b.heads) + 1
+    n_attn = sum(1 for i in range(pl.n_ops) if pl.ops_array[i].type == S.DS_OP_ATTN)
+    n_soft = sum(1 for i in range(pl.n_ops) if pl.ops_array[i].type == S.DS_OP_SOFTMAX)
+    assert n_attn + n_soft == sum(1 for b in blocks if b.heads)
+    assert pl.meta['n_gemm'] == 1 + 2 * len(blocks) + 3 * n_attn + 5 * n_soft + 1
 
 
 def test_spec_matches_oracle_structure():
