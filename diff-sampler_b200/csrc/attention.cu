@@ -195,22 +195,28 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
             mbar_wait(&ctl->s_full[sb], (j >> 1) & 1);
             tc_fence_after();
             const int kvalid = p.Lk - j * 128;          // keys of this block that exist (>= 128: all)
-            // pass 1: row maximum
-            float mx = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                DSB_TMEM_LD_32(t_row + sb * 128 + c * 32, v);
+            // pass 1: row maximum.  One warp per scheduler means no other warp hides latencies: the next TMEM chunk is
+            // requested before the current one is reduced, and the reduction runs on four independent chains.
+            float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            {
+                uint32_t v[2][32];
+                DSB_TMEM_LD_32(t_row + sb * 128, v[0]);
                 tmem_ld_wait();
-                if (kvalid >= 128) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                } else {
+                for (int c = 0; c < 4; ++c) {
+                    if (c < 3) DSB_TMEM_LD_32(t_row + sb * 128 + (c + 1) * 32, v[(c + 1) & 1]);
+                    if (kvalid >= 128) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i < kvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+                        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c & 1][i]));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (c * 32 + i < kvalid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c & 1][i]));
+                    }
+                    if (c < 3) tmem_ld_wait();
                 }
             }
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
             const float m_new = fmaxf(m, mx * p.scale_log2e);
             const float alpha = ex2_approx(m - m_new);  // first block: exp2(-inf) = 0
             if (j > 0) {
@@ -227,32 +233,44 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
                 for (int i = 0; i < 64; ++i) O[i] *= alpha;
                 l *= alpha;
             }
-            // pass 2: p = exp2(s * scale * log2e - m), split into fp16 hi / lo, swizzled K-major store
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                DSB_TMEM_LD_32(t_row + sb * 128 + c * 32, v);
+            // pass 2: p = exp2(s * scale * log2e - m), split into fp16 hi / lo (packed half2 conversions), swizzled K-major store
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                uint32_t v[2][32];
+                DSB_TMEM_LD_32(t_row + sb * 128, v[0]);
                 tmem_ld_wait();
-                const int kb = c >> 1;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    __align__(16) __half hi[8];
-                    __align__(16) __half lo[8];
+                for (int c = 0; c < 4; ++c) {
+                    if (c < 3) DSB_TMEM_LD_32(t_row + sb * 128 + (c + 1) * 32, v[(c + 1) & 1]);
+                    const int kb = c >> 1;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int col = c * 32 + g * 8 + i;
-                        float pv = ex2_approx(fmaf(__uint_as_float(v[g * 8 + i]), p.scale_log2e, -m_new));
-                        if (col >= kvalid) pv = 0.f;
-                        l += pv;
-                        hi[i] = __float2half_rn(pv);
-                        lo[i] = __float2half_rn(pv - __half2float(hi[i]));
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int col = c * 32 + g * 8 + 2 * i;
+                            float p0 = ex2_approx(fmaf(__uint_as_float(v[c & 1][g * 8 + 2 * i]), p.scale_log2e, -m_new));
+                            float p1 = ex2_approx(fmaf(__uint_as_float(v[c & 1][g * 8 + 2 * i + 1]), p.scale_log2e, -m_new));
+                            if (kvalid < 128) {
+                                if (col >= kvalid) p0 = 0.f;
+                                if (col + 1 >= kvalid) p1 = 0.f;
+                            }
+                            l4[i] += p0 + p1;
+                            const __half2 h2 = __floats2half2_rn(p0, p1);
+                            const float2 hf = __half22float2(h2);
+                            const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+                            hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                            lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                        }
+                        const int chunk = (c & 1) * 4 + g;                   // 16-byte chunk of the 128-byte row
+                        const uint32_t off = kb * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4);
+                        *reinterpret_cast<uint4*>(sP + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4*>(sP + 32768 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
-                    const int chunk = (c & 1) * 4 + g;                       // 16-byte chunk of the 128-byte row
-                    const uint32_t off = kb * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(sP + off) = *reinterpret_cast<const uint4*>(hi);
-                    *reinterpret_cast<uint4*>(sP + 32768 + off) = *reinterpret_cast<const uint4*>(lo);
+                    if (c < 3) tmem_ld_wait();
                 }
             }
+            l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
             m = m_new;
             tc_fence_before();
             fence_proxy_async();                        // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -271,16 +289,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
             __half* o = p.out + ((long long)b * p.L + grow) * p.o_pitch + h * 64;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
-                __align__(16) __half hi[8];
-                __align__(16) __half lo[8];
+                uint32_t hw[4], lw[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float val = O[g * 8 + i] * inv;
-                    hi[i] = __float2half_rn(val);
-                    lo[i] = __float2half_rn(val - __half2float(hi[i]));
+                for (int i = 0; i < 4; ++i) {
+                    const float a0 = O[g * 8 + 2 * i] * inv, a1 = O[g * 8 + 2 * i + 1] * inv;
+                    const __half2 h2 = __floats2half2_rn(a0, a1);
+                    const float2 hf = __half22float2(h2);
+                    const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+                    hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                    lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
-                *reinterpret_cast<uint4*>(o + g * 8) = *reinterpret_cast<const uint4*>(hi);
-                *reinterpret_cast<uint4*>(o + p.o_plane + g * 8) = *reinterpret_cast<const uint4*>(lo);
+                *reinterpret_cast<uint4*>(o + g * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                *reinterpret_cast<uint4*>(o + p.o_plane + g * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
             }
         }
     }

@@ -565,7 +565,9 @@ extern "C" int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream
     int by = 256 / bx; if (by < 1) by = 1;
     int pix_per_cta = 8 * by;                  // 8 loads in flight per thread
     if (pix_per_cta < 64) pix_per_cta = 64;
-    while (pix_per_cta > 64 && (long long)((d->HW + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
+    // small batches (latent diffusion: 16 samples): shorter pixel runs per CTA so that the grid still covers the SMs
+    const int min_pix = by > 8 ? by : 8;
+    while (pix_per_cta > min_pix && (long long)((d->HW + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
     const int chunks = (d->HW + pix_per_cta - 1) / pix_per_cta;
     gn_stats_kernel<<<dim3(chunks, d->B), dim3(bx, by), 0, stream>>>(*d, pix_per_cta);
     return ok();

@@ -25,20 +25,28 @@ def pick_bn(n):
     return best[1], best[2]
 
 
+def _tile_cost(bn):
+    """Relative duration of one K step of a 128 x bn tile: tensor-core time bn/2 cycles, but never less than the shared-memory
+    read of the operands (128 x 16 A + bn x 16 B fp16 at 128 B/clk) -- narrow tiles do not get proportionally cheaper."""
+    return max(bn / 2.0, 32.0 + bn / 4.0)
+
+
 def fill_bn(n, m_tiles, num_z=1):
-    """pick_bn, then — when the problem has fewer tiles than SMs (small batch / low resolution) — narrow the N tile (keeping the same
-    padded width, so packed weights are unchanged) until the persistent grid fills the 148 SMs."""
+    """N tile for a problem with few tiles (small batch / low resolution): the persistent grid runs ceil(tiles / 148) waves, so
+    160 tiles cost two full waves.  Choose the multiple of 16 that minimises waves x per-tile cost (e.g. N = 1280 over 32 M tiles:
+    144 x 9 = 288 tiles = 2 waves of 72 instead of 256 x 5 = 160 tiles = 2 waves of 128).  Large problems keep pick_bn's tiling.
+    The packed weight keeps pick_bn's padded row count; rows past it are zero-filled by TMA."""
     bn, tiles = pick_bn(n)
-    padded = bn * tiles
-    if m_tiles * tiles * num_z >= NUM_SMS or bn <= 64:
+    if m_tiles * tiles * num_z >= 4 * NUM_SMS or bn <= 64:
         return bn, tiles
-    for cand in range(bn - 16, 63, -16):
-        if padded % cand:
-            continue
-        if m_tiles * (padded // cand) * num_z >= NUM_SMS:
-            return cand, padded // cand
-    best = [c for c in range(64, bn, 16) if padded % c == 0]
-    return (best[0], padded // best[0]) if best else (bn, tiles)
+    best = None
+    for cand in range(256, 63, -16):
+        nt = -(-n // cand)
+        waves = -(-(m_tiles * nt * num_z) // NUM_SMS)
+        key = (waves * _tile_cost(cand), nt * cand - n, -cand)
+        if best is None or key < best[0]:
+            best = (key, cand, nt)
+    return best[1], best[2]
 
 
 def split_planes_rows(n_valid, bn):
@@ -68,7 +76,8 @@ def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w
     d = S.GemmDesc()
     bw, bh, bnn = conv_box(H, W)
     BN, n_tiles = (bn, -(-Cout // bn)) if bn else fill_bn(Cout, -(-(Bn * H * W) // 128))
-    cout_pad = n_tiles * BN
+    pbn, ptiles = pick_bn(Cout)
+    cout_pad = pbn * ptiles              # rows of the packed weight (pack_conv_weight); tiles past it read TMA zero fill
     ktot = taps * C + C2
     d.a_ptr = a_ptr
     cphys = 4 * C if s2d else C          # physical channel extent of the activation tensor

@@ -103,6 +103,7 @@ def pack_weights(spec, params):
             wb.add(n + '.v:b', bv)
             add_conv(n + '.proj', P(n + '.proj.weight'), bias=P(n + '.proj.bias'))
     wb.add('affine:w', torch.cat(aff_w, dim=0))
+    wb.add('affine:w16', G.split_planes(torch.cat(aff_w, dim=0)))     # [2][aff_total][emb]: N operand of the batched-embedding GEMM
     wb.add('affine:b', torch.cat(aff_b, dim=0))
     for k in ('map_layer0', 'map_layer1'):
         wb.add(k + ':w', P(k + '.weight'))
@@ -252,8 +253,18 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
                                         add=R('e2'), add_stride=ec if nsig > 1 else 0, out=R('e3'), n_rows=nE, in_f=spec.label_dim,
                                         out_f=ec, act=1, in_scale=1.0))
             emb_buf, emb_rows = 'e3', nE
-    emit(lambda R: S.LinearDesc(in_=R(emb_buf), in_stride=ec if emb_rows > 1 else 0, W=W('affine:w'), b=W('affine:b'), out=R('aff'),
-                                n_rows=emb_rows, in_f=ec, out_f=spec.aff_total, act=0, in_scale=1.0))
+    if emb_rows >= 32 and ec % 64 == 0:
+        # per-sample conditioning (class labels / per-sample sigma): [rows x emb] x [emb x aff_total] is a real GEMM (ImageNet-64 at
+        # batch 256: 20 GFLOP) -> fp16 planes of the embedding (gn_apply in pass-through mode) + the tcgen05 kernel
+        A.need('emb_planes', npl * emb_rows * ec * H2)
+        emit(lambda R: S.GnApplyDesc(src0=R(emb_buf), src1=0, C0=ec, C1=0, H=emb_rows, W=1, B=1, groups=1, sums=0, gamma=0, beta=0, eps=0.0,
+                                     silu=0, ada=0, ada_stride=0, resample=0, nplanes=npl, out_act=0, out_raw=R('emb_planes'), out_raw_f32=0))
+        emit(lambda R: G.rows_gemm(R('emb_planes'), emb_rows, ec, 1, W('affine:w16'), spec.aff_total, ec, 1, ec, num_z=1, nh=1,
+                                   m_valid=emb_rows, n_valid=spec.aff_total, npass=npass, out_f32=R('aff'), ldo=spec.aff_total,
+                                   bias_n=W('affine:b'))[0])
+    else:
+        emit(lambda R: S.LinearDesc(in_=R(emb_buf), in_stride=ec if emb_rows > 1 else 0, W=W('affine:w'), b=W('affine:b'), out=R('aff'),
+                                    n_rows=emb_rows, in_f=ec, out_f=spec.aff_total, act=0, in_scale=1.0))
     aff_stride = spec.aff_total if emb_rows > 1 else 0
 
     # ---------------- stem ---------------------------------------------------------------------------------------

@@ -327,6 +327,28 @@ def test_unfused_attention_plan_matches(name):
         assert err < TOL
 
 
+def test_batched_embedding_gemm_path():
+    """>= 32 embedding rows (per-sample labels and sigmas) lower the affine layer to the tcgen05 GEMM instead of the warp-per-feature
+    linear kernel; same tolerance against the oracle."""
+    from oracle import edm_oracle as O
+    from diff_sampler_b200.net import B200Net
+    from diff_sampler_b200 import _cstructs as CS
+    on, P, S = _oracle('tiny_adm')
+    B = 40
+    nat = B200Net(P, S['img_resolution'], S['img_channels'], S['label_dim'], device=_dev())
+    x = O.stacked_randn(range(B), (3, 16, 16))
+    sig = torch.linspace(0.05, 40.0, B)
+    lab = _labels(S, B)
+    ref = on(x * sig[:, None, None, None], sig, class_labels=lab)
+    got = nat((x * sig[:, None, None, None]).to(_dev()), sig.to(_dev()), class_labels=lab.to(_dev())).cpu()
+    _, pl = nat._plan(B, B, B)
+    n_lin = sum(1 for i in range(pl.n_ops) if pl.ops_array[i].type == CS.DS_OP_LINEAR)
+    assert n_lin == 3                                    # map_layer0, map_layer1, map_label; the affine layer is a GEMM here
+    err = (got - ref).abs().max().item()
+    print(f'tiny_adm B={B} per-sample labels/sigma (embedding GEMM): {err:.3e}')
+    assert err < TOL
+
+
 def test_ldm_unfused_attention_matches():
     from oracle import edm_oracle as O
     on, nat, cfg = _ldm_pair(flash_attn=False)

@@ -82,7 +82,9 @@ def test_weight_packing_roundtrip():
     assert (full[:70, 576:600] - sk.reshape(70, 24)).abs().max() < 1e-6 and full[70:].abs().max() == 0
     assert G.pick_bn(256) == (256, 1) and G.pick_bn(384) == (192, 2) and G.pick_bn(3) == (16, 1) and G.pick_bn(576) == (192, 3)
     assert G.pick_bn(320) == (160, 2) and G.pick_bn(1344) == (224, 6)
-    assert G.fill_bn(1280, 8) == (64, 20) and G.fill_bn(1280, 2048) == (256, 5)          # few M tiles -> narrower N tiles fill the SMs
+    # few M tiles: the N tile that minimises (waves over 148 SMs) x (per-tile cost); many tiles: pick_bn's tiling
+    assert G.fill_bn(1280, 8) == (80, 16) and G.fill_bn(1280, 32) == (144, 9) and G.fill_bn(1280, 2048) == (256, 5)
+    assert G.fill_bn(256, 256) == (256, 1) and G.fill_bn(256, 64) == (128, 2)
     assert G.conv_box(32, 32) == (32, 4, 1) and G.conv_box(8, 8) == (8, 8, 2) and G.conv_box(64, 64) == (64, 2, 1)
     # qkv de-interleave ([head][c][q|k|v] rows, networks_edm.py:174)
     C_, nh = 8, 2
