@@ -7,9 +7,10 @@
 //   warp 0      TMA producer   Q tile once; K_j [128 keys x 64] and V_j^T [64 x 128 keys] (fp16 hi/lo planes) into 2-stage rings
 //   warp 1      MMA issuer     S_j = Q K_j^T  (3 split-precision passes, 128x128x16 tcgen05.mma, two S buffers in TMEM)
 //                              O_j = P_j V_j  (3 passes, 128x64x16, fresh TMEM accumulator per block)
-//   warps 2..5  softmax        one query row per thread: running max / sum, p = exp2(s - m) split into fp16 hi/lo and written
-//                              to shared memory in the 128B-swizzled K-major layout the MMA reads; the running output lives in
-//                              registers (O = alpha * O + O_j), so the TMEM accumulator never needs rescaling.
+//   warps 2..9  softmax        one query row and one half (64 keys) of the block per thread: running max / sum, p = exp2(s - m)
+//                              split into fp16 hi/lo and written to shared memory in the 128B-swizzled K-major layout the MMA
+//                              reads; the running output lives in registers (O = alpha * O + O_j), so the TMEM accumulator
+//                              never needs rescaling.
 //
 // QK^T of block j+1 is issued before the softmax of block j finishes (two S buffers); the softmax row-max pass of block j+1
 // overlaps P_j V_j.  Same split-precision contract as the GEMM kernel: Q, K, V and P are fp16 hi + lo planes, products are
@@ -24,7 +25,7 @@ namespace dsb {
 
 int encode_map(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes, const int32_t* box);
 
-static constexpr int kAttnThreads = 192;
+static constexpr int kAttnThreads = 320;            // warp 0 TMA, warp 1 MMA, warps 2..9 softmax
 static constexpr int kQBytes = 2 * 16384;          // Q hi, lo: 128 rows x 64 fp16 each
 static constexpr int kKStage = 2 * 16384;          // K hi, lo: 128 keys x 64 fp16
 static constexpr int kVStage = 4 * 8192;           // V^T [plane][key block of 64]: 64 d-rows x 64 keys fp16
@@ -49,6 +50,7 @@ struct AttnCtl {
     uint64_t s_full[2], s_empty[2];
     uint64_t p_full, o_full, o_empty;
     uint32_t tmem_base;
+    float xch[2][128];          // row maximum / row sum exchange between the two key halves of a row
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -81,11 +83,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
             mbar_init(&ctl->v_full[s], 1);
             mbar_init(&ctl->v_empty[s], 1);
             mbar_init(&ctl->s_full[s], 1);
-            mbar_init(&ctl->s_empty[s], 4);
+            mbar_init(&ctl->s_empty[s], 8);
         }
-        mbar_init(&ctl->p_full, 4);
+        mbar_init(&ctl->p_full, 8);
         mbar_init(&ctl->o_full, 1);
-        mbar_init(&ctl->o_empty, 4);
+        mbar_init(&ctl->o_empty, 8);
         fence_barrier_init();
     } else if (warp == 1) {
         tmem_alloc(&ctl->tmem_base, 512);
@@ -172,51 +174,57 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
             }
         }
     } else {
+        // Eight softmax warps: warps w and w + 4 share a TMEM lane quadrant (w % 4); each thread owns one query row and one HALF of
+        // the block's 128 keys (half = key block of 64) plus the matching 32 output columns.  Two warps per scheduler hide each
+        // other's latencies; the halves meet once per block (row maximum, through shared memory + a named barrier).
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;               // 0: warps 2..5, 1: warps 6..9
         const int row = quad * 32 + lane;               // query row inside the tile
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-        uint8_t* sP = smem + kOffP;
+        uint8_t* sP = smem + kOffP + half * 16384;
         float m = -INFINITY, l = 0.f;
-        float O[64];
+        float O[32];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) O[i] = 0.f;
+        for (int i = 0; i < 32; ++i) O[i] = 0.f;
         auto add_block_output = [&]() {
+            uint32_t v[32];
+            DSB_TMEM_LD_32(t_row + 256 + half * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                DSB_TMEM_LD_32(t_row + 256 + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
-            }
+            for (int i = 0; i < 32; ++i) O[i] += __uint_as_float(v[i]);
         };
         for (int j = 0; j < nkv; ++j) {
             const int sb = j & 1;
             mbar_wait(&ctl->s_full[sb], (j >> 1) & 1);
             tc_fence_after();
-            const int kvalid = p.Lk - j * 128;          // keys of this block that exist (>= 128: all)
-            // pass 1: row maximum.  One warp per scheduler means no other warp hides latencies: the next TMEM chunk is
-            // requested before the current one is reduced, and the reduction runs on four independent chains.
+            const int kvalid = p.Lk - j * 128 - half * 64;   // keys of this thread's half that exist (>= 64: all)
+            const uint32_t t_s = t_row + sb * 128 + half * 64;
+            // pass 1: maximum over this thread's 64 keys (four independent chains, second chunk requested early)
             float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             {
                 uint32_t v[2][32];
-                DSB_TMEM_LD_32(t_row + sb * 128, v[0]);
+                DSB_TMEM_LD_32(t_s, v[0]);
                 tmem_ld_wait();
+                DSB_TMEM_LD_32(t_s + 32, v[1]);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < 3) DSB_TMEM_LD_32(t_row + sb * 128 + (c + 1) * 32, v[(c + 1) & 1]);
-                    if (kvalid >= 128) {
+                for (int c = 0; c < 2; ++c) {
+                    if (kvalid >= 64) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c & 1][i]));
+                        for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i < kvalid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c & 1][i]));
+                            if (c * 32 + i < kvalid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
                     }
-                    if (c < 3) tmem_ld_wait();
+                    if (c == 0) tmem_ld_wait();
                 }
             }
-            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            const float mx_own = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+            // meet the other half of the row.  Slots alternate with the block parity so that one barrier per block is enough:
+            // the slot written in block j is next overwritten (by the partner) in block j + 1, after this thread has read it.
+            ctl->xch[half ^ (j & 1)][row] = mx_own;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float mx = fmaxf(mx_own, ctl->xch[(half ^ 1) ^ (j & 1)][row]);
             const float m_new = fmaxf(m, mx * p.scale_log2e);
             const float alpha = ex2_approx(m - m_new);  // first block: exp2(-inf) = 0
             if (j > 0) {
@@ -230,28 +238,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
             }
             if (alpha != 1.f) {
 #pragma unroll
-                for (int i = 0; i < 64; ++i) O[i] *= alpha;
+                for (int i = 0; i < 32; ++i) O[i] *= alpha;
                 l *= alpha;
             }
             // pass 2: p = exp2(s * scale * log2e - m), split into fp16 hi / lo (packed half2 conversions), swizzled K-major store
             float l4[4] = {0.f, 0.f, 0.f, 0.f};
             {
                 uint32_t v[2][32];
-                DSB_TMEM_LD_32(t_row + sb * 128, v[0]);
+                DSB_TMEM_LD_32(t_s, v[0]);
                 tmem_ld_wait();
+                DSB_TMEM_LD_32(t_s + 32, v[1]);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (c < 3) DSB_TMEM_LD_32(t_row + sb * 128 + (c + 1) * 32, v[(c + 1) & 1]);
-                    const int kb = c >> 1;
+                for (int c = 0; c < 2; ++c) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint32_t hw[4], lw[4];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int col = c * 32 + g * 8 + 2 * i;
-                            float p0 = ex2_approx(fmaf(__uint_as_float(v[c & 1][g * 8 + 2 * i]), p.scale_log2e, -m_new));
-                            float p1 = ex2_approx(fmaf(__uint_as_float(v[c & 1][g * 8 + 2 * i + 1]), p.scale_log2e, -m_new));
-                            if (kvalid < 128) {
+                            float p0 = ex2_approx(fmaf(__uint_as_float(v[c][g * 8 + 2 * i]), p.scale_log2e, -m_new));
+                            float p1 = ex2_approx(fmaf(__uint_as_float(v[c][g * 8 + 2 * i + 1]), p.scale_log2e, -m_new));
+                            if (kvalid < 64) {
                                 if (col >= kvalid) p0 = 0.f;
                                 if (col + 1 >= kvalid) p1 = 0.f;
                             }
@@ -262,12 +269,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
                             hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
                             lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
                         }
-                        const int chunk = (c & 1) * 4 + g;                   // 16-byte chunk of the 128-byte row
-                        const uint32_t off = kb * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4);
+                        const int chunk = c * 4 + g;                         // 16-byte chunk of the 128-byte row
+                        const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
                         *reinterpret_cast<uint4*>(sP + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                         *reinterpret_cast<uint4*>(sP + 32768 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                     }
-                    if (c < 3) tmem_ld_wait();
+                    if (c == 0) tmem_ld_wait();
                 }
             }
             l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
@@ -283,12 +290,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
         mbar_wait(&ctl->o_full, (nkv - 1) & 1);
         tc_fence_after();
         add_block_output();
+        // row sum: both halves
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        ctl->xch[half][row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l += ctl->xch[half ^ 1][row];
         const int grow = qt * 128 + row;
         if (grow < p.L) {
             const float inv = 1.f / l;
-            __half* o = p.out + ((long long)b * p.L + grow) * p.o_pitch + h * 64;
+            __half* o = p.out + ((long long)b * p.L + grow) * p.o_pitch + h * 64 + half * 32;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
+            for (int g = 0; g < 4; ++g) {
                 uint32_t hw[4], lw[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
