@@ -37,7 +37,8 @@ def parse():
     ap.add_argument('--solver', default='heun', help='heun | euler | ipndm | dpm_pp | amed_dpm_pp (sd15)')
     ap.add_argument('--num_steps', type=int, default=10)
     ap.add_argument('--batch', type=int, default=512, help='images per GPU per step')
-    ap.add_argument('--precision', default='fp16x3', choices=['fp16x3', 'fp16'])
+    ap.add_argument('--precision', default='fp16x3', choices=['fp16x3', 'fp16', 'fp16f8'],
+                    help="fp16x3 (default): 3 fp16 MMAs per product; fp16f8: fp16 hi x hi + two e4m3 correction MMAs (block convolutions); fp16: single pass")
     ap.add_argument('--cpu_batch', type=int, default=8, help='batch of the bounded CPU-baseline sample')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--fuse_stats', type=int, default=1, help='1 (default): GroupNorm statistics from the GEMM epilogues; 0: separate gn_stats pass')
@@ -269,7 +270,8 @@ def main():
     pk = peaks()
     line = dict(metric=metric, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='fp16 operands, fp32 accumulate' + (' (split-precision: 3 tcgen05 MMAs per product)' if args.precision == 'fp16x3' else ''),
+                dtype='fp16 operands, fp32 accumulate' + {'fp16x3': ' (split-precision: 3 tcgen05 MMAs per product)',
+                                                           'fp16f8': ' (split-precision: fp16 hi x hi + two e4m3 correction MMAs per product)'}.get(args.precision, ''),
                 data='synthetic', config=config, gpu_launches=launches, clocks=clk, precision=args.precision)
     if e2e:
         line['e2e'] = e2e
@@ -413,7 +415,7 @@ def extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk):
                                 traffic=None, kernel='gemm_tc_kernel (all conv/attention contractions of one forward)',
                                 algorithmic_flops_per_forward=flops, launches_per_forward=gemm_n, gemm_ms_per_forward=gemm_ms,
                                 all_ops_ms_per_forward=fwd_ms, gemm_share_of_forward=gemm_ms / fwd_ms if fwd_ms else None,
-                                executed_mma_flops_factor=3 if args.precision == 'fp16x3' else 1, peak_source=pk['source'] + ', sustained bf16 GEMM')
+                                executed_mma_flops_factor={'fp16x3': 3, 'fp16f8': 2}.get(args.precision, 1), peak_source=pk['source'] + ', sustained bf16 GEMM')
         line['forward_breakdown_ms'] = {str(k): round(v[1], 4) for k, v in sorted(prof.items())}
         # ---- the fused solver-update kernel against the HBM roofline (HBM-resident size: 3 x 1 GiB streams) -------------
         n = 256 * 1024 * 1024
@@ -465,6 +467,21 @@ def extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk):
                                             max_abs_vs_fp16x3=(img1 - images).abs().max().item(),
                                             note='single tcgen05 pass per product; not the headline because it does not hold 1e-3 on the de-zeroed weight set')
             del net1
+        # ---- fp16f8 runs: the same sampling pass with the default fp16x3 denoiser, for the speed ratio and the output difference ----
+        if args.precision == 'fp16f8':
+            net3 = B200Net.from_config(args.net, seed=0, dezero=True, precision='fp16x3', device=dev)
+            for _ in range(2):
+                sampler(net3, latents, **kw)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(args.steps):
+                img3 = sampler(net3, latents, **kw)
+            f1.record()
+            torch.cuda.synchronize()
+            line['fp16x3_same_run'] = dict(value=B * args.steps / (f0.elapsed_time(f1) / 1e3), unit='images/s (1 GPU)',
+                                           max_abs_vs_fp16f8=(img3 - images).abs().max().item())
+            del net3
 
 
 

@@ -11,6 +11,7 @@ DS_OP_GEMM, DS_OP_GN_STATS, DS_OP_GN_APPLY, DS_OP_SOFTMAX, DS_OP_POSEMB, DS_OP_L
 DS_OP_PREP_INPUT, DS_OP_CHANMEAN, DS_OP_MEMSET, DS_OP_LAYERNORM, DS_OP_GEGLU, DS_OP_GN_FINALIZE, DS_OP_ATTN = 7, 8, 9, 10, 11, 12, 13
 DS_IO_X, DS_IO_D, DS_IO_SIGMA, DS_IO_LABELS, DS_IO_BOTTLENECK, DS_IO_CTX = 0, 1, 2, 3, 4, 5
 DS_M_X0, DS_M_EPS, DS_M_DIV, DS_M_NONE = 0, 1, 2, 3
+DS_F8_SH_A16, DS_F8_SH_LO8, DS_F8_SH_HI8 = 6, 13, 2      # csrc/ops.h: power-of-two operand scales of the f8 GEMM mode
 
 SPACE_ABS, SPACE_ARENA, SPACE_WEIGHTS, SPACE_IO = 0, 1, 2, 3
 
@@ -30,11 +31,11 @@ class GemmDesc(C.Structure):
         ('b_k0', I32), ('b_k_per_zh', I32), ('b_row_per_zh', I32), ('b_z_per_zb', I32), ('b_z_per_zh', I32),
         ('m_valid', I32), ('n_valid', I32),
         ('out_f32', P), ('out_h16', P), ('o_zb', I64), ('o_zh', I64), ('ldo', I64), ('o_plane', I64),
-        ('bias_n', P), ('bias_m', P), ('rowvec', P), ('rowvec_stride', I64), ('rows_per_sample', I32), ('pad0', I32),
+        ('bias_n', P), ('bias_m', P), ('rowvec', P), ('rowvec_stride', I64), ('rows_per_sample', I32), ('f8', I32),
         ('residual', P), ('ldr', I64), ('scale', F32),
         ('edm_out', I32), ('edm_x', P), ('edm_coef', P), ('edm_coef_stride', I32), ('edm_C', I32), ('edm_D', P),
         ('st_quads', P),
-        ('tap_dh', I32 * 9), ('tap_dw', I32 * 9), ('tap_cb', I32 * 9), ('pad1', I32),
+        ('tap_dh', I32 * 9), ('tap_dw', I32 * 9), ('tap_cb', I32 * 9), ('acc_scale', F32),
     ]
 
 
@@ -46,7 +47,7 @@ class GnStatsDesc(C.Structure):
 class GnApplyDesc(C.Structure):
     _fields_ = [('src0', P), ('src1', P), ('C0', I32), ('C1', I32), ('H', I32), ('W', I32), ('B', I32), ('groups', I32),
                 ('sums', P), ('gamma', P), ('beta', P), ('eps', F32), ('silu', I32), ('ada', P), ('ada_stride', I64),
-                ('resample', I32), ('nplanes', I32), ('out_act', P), ('out_raw', P), ('out_raw_f32', P)]
+                ('resample', I32), ('nplanes', I32), ('out_act', P), ('out_raw', P), ('out_raw_f32', P), ('fmt', I32), ('pad0', I32)]
 
 
 class SoftmaxDesc(C.Structure):

@@ -2,6 +2,7 @@
 // row softmax, timestep embedding, small dense layers, input preparation.  All NHWC, 128-bit accesses.
 #include "ops.h"
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <math.h>
 
 namespace dsb {
@@ -91,7 +92,34 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(ds_gn_finalize_desc d)
 // ------------------------------------------------------------------------------------------ GN apply
 // grid (chunks, B); block = nc8 * rows threads.  Thread (c8, prow) owns 8 fixed channels: its normalisation coefficients
 // live in registers (mean, a = rstd*gamma*(1+ada_scale), b = beta*(1+ada_scale)+ada_shift) and it streams over output pixels.
-__device__ __forceinline__ void gn_store_planes(__half* base, long long plane, long long o, const float* v, int nplanes) {
+// fmt 1 (operand of an f8 GEMM, csrc/ops.h): fp16 plane of v * 2^A16 (saturating) followed by the two e4m3 byte planes
+// (v - hi) * 2^LO8 and hi * 2^HI8, where hi is the value the fp16 plane represents.  Powers of two: the roundings are those of v.
+__device__ __forceinline__ void gn_store_f8(__half* base, long long plane, long long o, const float* v) {
+    constexpr float kA16 = (float)(1 << DS_F8_SH_A16), kLo8 = (float)(1 << DS_F8_SH_LO8), kHi8 = (float)(1 << DS_F8_SH_HI8);
+    __align__(16) __half hi[8];
+    __align__(8) unsigned short lo8[4];
+    __align__(8) unsigned short hi8[4];
+    float l[8], h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        hi[j] = __float2half_rn(fminf(fmaxf(v[j] * kA16, -65504.f), 65504.f));
+        const float hf = __half2float(hi[j]) * (1.0f / kA16);
+        l[j] = (v[j] - hf) * kLo8;
+        h[j] = hf * kHi8;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        lo8[j >> 1] = __nv_cvt_float2_to_fp8x2(make_float2(l[j], l[j + 1]), __NV_SATFINITE, __NV_E4M3);
+        hi8[j >> 1] = __nv_cvt_float2_to_fp8x2(make_float2(h[j], h[j + 1]), __NV_SATFINITE, __NV_E4M3);
+    }
+    *reinterpret_cast<uint4*>(base + o) = *reinterpret_cast<const uint4*>(hi);
+    unsigned char* b8 = reinterpret_cast<unsigned char*>(base + plane);
+    *reinterpret_cast<uint2*>(b8 + o) = *reinterpret_cast<const uint2*>(lo8);
+    *reinterpret_cast<uint2*>(b8 + plane + o) = *reinterpret_cast<const uint2*>(hi8);
+}
+
+__device__ __forceinline__ void gn_store_planes(__half* base, long long plane, long long o, const float* v, int nplanes, int fmt = 0) {
+    if (fmt == 1) { gn_store_f8(base, plane, o, v); return; }
     __align__(16) __half hi[8];
     __align__(16) __half lo[8];
 #pragma unroll
@@ -178,8 +206,8 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
             }
             const long long oa = ((long long)n * npix + po) * C + c;
             const long long ob = ((long long)n * npix + po + rows) * C + c;
-            if (oact) { gn_store_planes(oact, plane, oa, ya, d.nplanes); gn_store_planes(oact, plane, ob, yb, d.nplanes); }
-            if (oraw) { gn_store_planes(oraw, plane, oa, ea, d.nplanes); gn_store_planes(oraw, plane, ob, eb, d.nplanes); }
+            if (oact) { gn_store_planes(oact, plane, oa, ya, d.nplanes, d.fmt); gn_store_planes(oact, plane, ob, yb, d.nplanes, d.fmt); }
+            if (oraw) { gn_store_planes(oraw, plane, oa, ea, d.nplanes, d.fmt); gn_store_planes(oraw, plane, ob, eb, d.nplanes, d.fmt); }
             if (d.out_raw_f32) {
                 *reinterpret_cast<float4*>(d.out_raw_f32 + oa) = a0; *reinterpret_cast<float4*>(d.out_raw_f32 + oa + 4) = a1;
                 *reinterpret_cast<float4*>(d.out_raw_f32 + ob) = b0; *reinterpret_cast<float4*>(d.out_raw_f32 + ob + 4) = b1;
@@ -233,8 +261,8 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
             const int h2 = ho >> 1, w2 = wo >> 1, ph = ((ho & 1) << 1) | (wo & 1);
             o = (((long long)n * (d.H / 2) + h2) * (d.W / 2) + w2) * (4LL * C) + (long long)ph * C + c;
         }
-        if (oact) gn_store_planes(oact, plane, o, act, d.nplanes);
-        if (oraw) gn_store_planes(oraw, plane, o, raw, d.nplanes);
+        if (oact) gn_store_planes(oact, plane, o, act, d.nplanes, d.fmt);
+        if (oraw) gn_store_planes(oraw, plane, o, raw, d.nplanes, d.fmt);
         if (d.out_raw_f32) {
             *reinterpret_cast<float4*>(d.out_raw_f32 + o) = make_float4(raw[0], raw[1], raw[2], raw[3]);
             *reinterpret_cast<float4*>(d.out_raw_f32 + o + 4) = make_float4(raw[4], raw[5], raw[6], raw[7]);
@@ -583,6 +611,7 @@ extern "C" int ds_gn_finalize_launch(const ds_gn_finalize_desc* d, cudaStream_t 
 extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream) {
     const int C = d->C0 + d->C1;
     if (C % 8 || (d->C0 % 8)) return -2;
+    if (d->fmt != 0 && (d->fmt != 1 || d->resample == 3 || d->nplanes != 2)) return -2;   // the f8 layout reuses the two-plane footprint
     const int nc8 = C / 8;
     if (nc8 > 512) return -2;
     int rows = 256 / nc8;

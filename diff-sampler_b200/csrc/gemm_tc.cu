@@ -6,7 +6,8 @@
 // projection appended along K, and the batched Q.K^T / P.V products of self-attention.
 //
 //   warp 0      TMA producer   (cp.async.bulk.tensor 4-D boxes for A = shifted pixel tiles, 3-D for B)
-//   warp 1      MMA issuer     (tcgen05.mma kind::f16, 128 x BN x 16, fp32 accumulators in TMEM)
+//   warp 1      MMA issuer     (tcgen05.mma kind::f16, 128 x BN x 16, fp32 accumulators in TMEM; in f8 mode the two split-precision
+//                               correction products are kind::f8f6f4 e4m3 MMAs, 128 x BN x 32, into the same accumulator)
 //   warps 2..5  epilogue       (tcgen05.ld -> bias / embedding / residual / scale -> fp32 and/or fp16 hi/lo)
 //
 // Pipelines: smem ring (full/empty mbarriers) between TMA and MMA, and two TMEM accumulator
@@ -25,6 +26,9 @@ static constexpr int kThreads = 192;
 
 struct alignas(64) GemmKernelParams {
     CUtensorMap tmA, tmA2, tmB;
+    CUtensorMap tmA8, tmA2_8, tmB8;      // f8 mode: e4m3 planes of the same operands (uint8 maps, 128-channel boxes)
+    int f8, cpb8, nkb8_main, nkb8_aux, a8_plane_n;
+    float acc_scale;
     int BN, m_tiles, n_tiles, num_z, nh;
     int taps, cpb, nkb_main, nkb_aux, npass;
     int a_mode, conv_H, conv_W, a_bn_dummy;
@@ -92,7 +96,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     if (!row_ok) return;                                   // warp-uniform whenever statistics are fused (m_valid % 32 == 0)
     float r[W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) r[j] = v[j];
+    for (int j = 0; j < W; ++j) r[j] = v[j] * p.acc_scale;     // 1 unless the operands carry power-of-two scales (f8 mode): exact
     const bool full = (col0 + W <= p.n_valid);
     if (p.bias_n) {
         if (full) {
@@ -245,7 +249,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int nkb_total = p.nkb_main + p.nkb_aux;
-    const int n_iters = p.npass * nkb_total;
+    // f8 mode: 2 * nkb8 e4m3 blocks (A_lo8 x W_hi8, then A_hi8 x W_lo8; 128 channels each) followed by the nkb_total fp16 hi x hi blocks
+    const int nkb8 = p.f8 ? p.nkb8_main + p.nkb8_aux : 0;
+    const int n_iters = p.f8 ? 2 * nkb8 + nkb_total : p.npass * nkb_total;
     const int tiles_per_z = p.m_tiles * p.n_tiles;
     const int total_tiles = p.num_z * tiles_per_z;
 
@@ -253,6 +259,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         if (p.nkb_aux) tma_prefetch_desc(&p.tmA2);
+        if (p.f8) {
+            tma_prefetch_desc(&p.tmA8);
+            tma_prefetch_desc(&p.tmB8);
+            if (p.nkb8_aux) tma_prefetch_desc(&p.tmA2_8);
+        }
         for (int s = 0; s < p.num_stages; ++s) {
             mbar_init(&ctl->full[s], 1);
             mbar_init(&ctl->empty[s], 1);
@@ -298,12 +309,29 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const int b_row = nt * p.BN + zh * p.b_row_per_zh;
                 const int b_z = zb * p.b_z_per_zb + zh * p.b_z_per_zh;
                 for (int it = 0; it < n_iters; ++it) {
-                    const int pass = it / nkb_total;
-                    const int kb = it - pass * nkb_total;
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + kATileBytes;
                     mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
+                    if (it < 2 * nkb8) {
+                        // e4m3 block: 128 channels = one 128-byte swizzle row, same tile bytes as an fp16 block
+                        const int pass8 = it >= nkb8 ? 1 : 0;
+                        const int kb = it - pass8 * nkb8;
+                        const int an8 = an0 + pass8 * p.a8_plane_n;
+                        if (kb < p.nkb8_main) {
+                            const int tap = kb / p.cpb8;
+                            const int c0 = (kb - tap * p.cpb8) * 128;
+                            tma_load_4d(&p.tmA8, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an8);
+                        } else {
+                            tma_load_4d(&p.tmA2_8, &ctl->full[stage], sa, (kb - p.nkb8_main) * 128, aw0, ah0, an8);
+                        }
+                        tma_load_3d(&p.tmB8, &ctl->full[stage], sb, kb * 128, b_row, pass8);
+                        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    const int it16 = it - 2 * nkb8;
+                    const int pass = it16 / nkb_total;
+                    const int kb = it16 - pass * nkb_total;
                     const int pa = (pass == 1) ? 1 : 0;
                     const int pb = (pass == 2) ? 1 : 0;
                     if (kb < p.nkb_main) {
@@ -340,10 +368,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     const uint32_t sb = sa + kATileBytes;
                     const uint64_t da = umma_desc_sw128(sa);
                     const uint64_t db = umma_desc_sw128(sb);
+                    if (it < 2 * nkb8) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k)      // 32 e4m3 = 32 bytes per MMA: the same +2 descriptor step as 16 fp16
+                            umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&ctl->empty[stage]);
                     if (it == n_iters - 1) umma_commit(&ctl->tmem_full[acc]);
@@ -429,7 +463,8 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int encode_map(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes, const int32_t* box) {
+static int encode_map_typed(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes,
+                            const int32_t* box, bool bytes8) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return -1;
     cuuint64_t gd[5];
@@ -438,7 +473,7 @@ int encode_map(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, c
     cuuint32_t es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = (cuuint64_t)strides_bytes[i];
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = fn(m, bytes8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         fprintf(stderr, "[dsb] cuTensorMapEncodeTiled failed: %d (rank %d dims %lld %lld %lld %lld box %d %d %d %d)\n", (int)r, rank,
@@ -447,6 +482,11 @@ int encode_map(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, c
         return -2;
     }
     return 0;
+}
+
+// fp16 tensors (also used by attention.cu)
+int encode_map(CUtensorMap* m, const void* ptr, int rank, const int64_t* dims, const int64_t* strides_bytes, const int32_t* box) {
+    return encode_map_typed(m, ptr, rank, dims, strides_bytes, box, false);
 }
 
 int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
@@ -480,6 +520,38 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     kp->edm_out = d->edm_out; kp->edm_x = d->edm_x; kp->edm_coef = d->edm_coef; kp->edm_coef_stride = d->edm_coef_stride;
     kp->edm_C = d->edm_C; kp->edm_D = d->edm_D;
     kp->st_quads = d->st_quads;
+    kp->acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
+    if (d->f8) {
+        // e4m3 correction passes: byte planes behind the fp16 plane of each operand (layout: csrc/ops.h)
+        if (d->a_mode != 0 || d->num_z != 1 || d->npass != 3 || d->a_plane_n <= 0) return -16;
+        for (int t = 0; t < 9; ++t) if (d->tap_cb[t]) return -16;
+        const int64_t C = d->a_dims[0], Wd = d->a_dims[1], Hd = d->a_dims[2], Bn = d->a_plane_n;
+        const int32_t box8[4] = {128, d->a_box[1], d->a_box[2], d->a_box[3]};
+        const int64_t dims8[4] = {C, Wd, Hd, 2 * Bn};
+        const int64_t st8[3] = {C, Wd * C, Hd * Wd * C};
+        const char* a8 = static_cast<const char*>(d->a_ptr) + Bn * Hd * Wd * C * 2;
+        if (encode_map_typed(&kp->tmA8, a8, 4, dims8, st8, box8, true)) return -17;
+        kp->f8 = 1;
+        kp->a8_plane_n = (int)Bn;
+        kp->cpb8 = (d->cpb + 1) / 2;
+        kp->nkb8_main = d->taps * kp->cpb8;
+        kp->nkb8_aux = 0;
+        if (d->a2_c > 0) {
+            const int64_t C2 = d->a2_c;
+            const int64_t dims28[4] = {C2, Wd, Hd, 2 * Bn};
+            const int64_t st28[3] = {C2, Wd * C2, Hd * Wd * C2};
+            const char* a28 = static_cast<const char*>(d->a2_ptr) + Bn * Hd * Wd * C2 * 2;
+            if (encode_map_typed(&kp->tmA2_8, a28, 4, dims28, st28, box8, true)) return -18;
+            kp->nkb8_aux = (int)((C2 + 127) / 128);
+        }
+        const int64_t ktot8 = (int64_t)(kp->nkb8_main + kp->nkb8_aux) * 128;
+        const int64_t rows = d->b_dims[1];
+        const int64_t bd8[3] = {ktot8, rows, 2};
+        const int64_t bs8[2] = {ktot8, rows * ktot8};
+        const int32_t bbox8[3] = {128, d->BN, 1};
+        const char* b8 = static_cast<const char*>(d->b_ptr) + rows * d->b_dims[0] * 2;
+        if (encode_map_typed(&kp->tmB8, b8, 3, bd8, bs8, bbox8, true)) return -19;
+    }
     for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = d->tap_dh[t]; kp->tap_dw[t] = d->tap_dw[t]; kp->tap_cb[t] = d->tap_cb[t]; }
     if (d->taps != 1 && d->taps != 9) return -15;
     // fused statistics: whole 32-row slabs (row validity is then warp-uniform), whole channel quads, one z slice, fp32 output

@@ -17,6 +17,16 @@ extern "C" {
 //   a_mode 1 (rows):  plain row-major matrices, optionally batched over z = (zb, zh).
 // B is a 3-D tensor (k, row, batch).  Split precision: npass == 3 accumulates
 //   A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, with the 'lo' planes found at a_plane_n / b_plane_batch.
+//
+// f8 == 1 ("fp16f8", conv mode only): the two correction products run as e4m3 MMAs (kind::f8f6f4, twice the fp16 rate, 128
+// channels per K block).  Operand layout (all scales are powers of two, so the fp16 roundings are those of the unscaled values):
+//   A buffer  = [fp16 (v * 2^DS_F8_SH_A16)] [e4m3 ((v - hi) * 2^DS_F8_SH_LO8)] [e4m3 (hi * 2^DS_F8_SH_HI8)]   (2 + 1 + 1 bytes/elem,
+//               each plane [Bn][H][W][C]; written by ds_gn_apply with fmt == 1), same for the aux (skip) operand;
+//   B buffer  = [fp16 (w * 2^b)][cout_pad][ktot] then [2][cout_pad][ktot8] e4m3: (w_hi * 2^b1), (w_lo * 2^b2), K padded per tap to a
+//               multiple of 128, with b + A16 == b1 + LO8 == b2 + HI8 == S  (gemm_desc.pack_conv_weight_f8);
+//   the accumulator then holds 2^S * result and the epilogue multiplies by acc_scale = 2^-S before bias / residual.
+// The e4m3 blocks are issued first so that they accumulate among themselves before the large fp16 term arrives.
+enum { DS_F8_SH_A16 = 6, DS_F8_SH_LO8 = 13, DS_F8_SH_HI8 = 2 };
 typedef struct ds_gemm_desc {
     // A operand
     const void* a_ptr;
@@ -59,7 +69,7 @@ typedef struct ds_gemm_desc {
     const float* rowvec;
     int64_t rowvec_stride;  // elements between samples (0 = broadcast)
     int32_t rows_per_sample;
-    int32_t pad0;
+    int32_t f8;             // 1: fp8 correction passes (see above); requires a_mode == 0, num_z == 1, npass == 3, tap_cb == 0
     const float* residual;
     int64_t ldr;
     float scale;
@@ -82,7 +92,7 @@ typedef struct ds_gemm_desc {
     int32_t tap_dh[9];
     int32_t tap_dw[9];
     int32_t tap_cb[9];
-    int32_t pad1;
+    float acc_scale;        // accumulator pre-scale (0 is read as 1); 2^-S in f8 mode
 } ds_gemm_desc;
 
 int ds_gemm_launch(const ds_gemm_desc* d, cudaStream_t stream);
@@ -125,6 +135,8 @@ typedef struct ds_gn_apply_desc {
     void* out_act;          // fp16 [nplanes][B][Ho][Wo][C]; may be NULL
     void* out_raw;          // fp16 planes of the raw input; may be NULL
     float* out_raw_f32;     // fp32 raw input at output resolution; may be NULL
+    int32_t fmt;            // 0: fp16 hi/lo planes.  1: operand layout of an f8 GEMM (ds_gemm_desc.f8), for out_act and out_raw
+    int32_t pad0;
 } ds_gn_apply_desc;
 
 // GroupNorm statistics from the quad partials written by the producing GEMM epilogues (ds_gemm_desc.st_quads) of the one or two

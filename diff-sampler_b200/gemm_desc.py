@@ -66,12 +66,17 @@ def conv_box(H, W):
 
 def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w_planes=2, a2_ptr=0, C2=0,
               out_f32=0, out_h16=0, o_planes=2, ldo=None, bias=0, rowvec=0, rowvec_stride=0, residual=0, ldr=None, scale=1.0,
-              edm=None, bn=None, s2d=False):
+              edm=None, bn=None, s2d=False, f8=False, acc_scale=1.0):
     """3x3 (taps=9) or 1x1 (taps=1) convolution over NHWC fp16 planes [a_planes][Bn][H][W][C] with the
     packed weight matrix [w_planes][Cout_pad][taps*C + C2] (K ordered tap-major, then the aux/skip block).
-    Output rows are NHWC pixels: out[pixel][cout] (+ fused epilogue)."""
+    Output rows are NHWC pixels: out[pixel][cout] (+ fused epilogue).
+    f8=True: both operands are in the fp16 + 2 x e4m3 layout of csrc/ops.h (activations from ds_gn_apply fmt=1, weights from
+    pack_conv_weight_f8); acc_scale = 2^-S of that packed weight."""
     assert C % 64 == 0 and C2 % 64 == 0
-    if npass == 3:
+    if f8:
+        assert npass == 3 and not s2d
+        a_planes = w_planes = 1          # one fp16 plane; the e4m3 planes sit behind it (the kernel derives their tensor maps)
+    elif npass == 3:
         assert a_planes == 2 and w_planes == 2
     d = S.GemmDesc()
     bw, bh, bnn = conv_box(H, W)
@@ -125,6 +130,8 @@ def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w
     d.residual = residual
     d.ldr = ldr if ldr is not None else Cout
     d.scale = scale
+    d.f8 = 1 if f8 else 0
+    d.acc_scale = acc_scale
     if edm is not None:
         d.edm_out = 1
         d.edm_x, d.edm_coef, d.edm_coef_stride, d.edm_C, d.edm_D = edm
@@ -194,6 +201,112 @@ def pack_conv_weight(weight, skip_weight=None, cin_pad=None, bn=None):
     hi = wp.half()
     lo = (wp - hi.float()).half()
     return torch.stack([hi, lo]).contiguous()
+
+
+E4M3_MAX = 448.0
+
+
+def _e4m3_bytes(x, shift):
+    """fp32 -> e4m3 (saturating, round to nearest even) of x * 2^shift, as uint8."""
+    import torch
+    return (x * 2.0 ** shift).clamp(-E4M3_MAX, E4M3_MAX).to(torch.float8_e4m3fn).view(torch.uint8)
+
+
+def f8_weight_shift(*weights):
+    """S of an f8 GEMM (csrc/ops.h): the e4m3 copy of w_hi uses the largest power of two that keeps max|w| inside e4m3."""
+    import math
+    wmax = max(float(w.detach().abs().max()) for w in weights if w is not None)
+    b1 = int(math.floor(math.log2(E4M3_MAX / wmax))) if wmax > 0 else 0
+    return S.DS_F8_SH_LO8 + b1
+
+
+def pack_conv_weight_f8(weight, skip_weight=None, bn=None):
+    """Operand B of an f8 GEMM (csrc/ops.h): uint8 blob
+        [fp16 (w * 2^b)][Cout_pad][taps*Cin64 + C2_64]  |  [2][Cout_pad][taps*Cin128 + C2_128] e4m3: (w_hi * 2^b1), (w_lo * 2^b2)
+    with b = S - A16, b1 = S - LO8, b2 = S - HI8; K ordered (kh, kw, cin) per plane, channels padded per tap to 64 (fp16) or
+    128 (e4m3).  Returns (blob, S); the GEMM's acc_scale is 2^-S."""
+    import torch
+    cout, cin, kh, kw = weight.shape
+    Sh = f8_weight_shift(weight, skip_weight)
+    b, b1, b2 = Sh - S.DS_F8_SH_A16, Sh - S.DS_F8_SH_LO8, Sh - S.DS_F8_SH_HI8
+    BN, n_tiles = (bn, -(-cout // bn)) if bn else pick_bn(cout)
+    cout_pad = BN * n_tiles
+
+    def kmajor(t, pad):
+        """[cout, cin, kh, kw] (+ skip [cout, c2, 1, 1]) fp32 -> [cout_pad, K] with per-tap channel padding to `pad`."""
+        cp = -(-cin // pad) * pad
+        w = torch.zeros(cout, kh, kw, cp, dtype=torch.float32)
+        w[..., :cin] = t.permute(0, 2, 3, 1)
+        w = w.reshape(cout, kh * kw * cp)
+        return w
+
+    def with_skip(main, skip, pad):
+        w = kmajor(main, pad)
+        if skip is not None:
+            c2 = skip.shape[1]
+            c2p = -(-c2 // pad) * pad
+            sk = torch.zeros(cout, c2p, dtype=torch.float32)
+            sk[:, :c2] = skip.reshape(cout, c2)
+            w = torch.cat([w, sk], dim=1)
+        out = torch.zeros(cout_pad, w.shape[1], dtype=torch.float32)
+        out[:cout] = w
+        return out
+
+    wf = weight.detach().float()
+    sf = skip_weight.detach().float() if skip_weight is not None else None
+    hi16 = lambda t: (t * 2.0 ** b).clamp(-65504.0, 65504.0).half()
+    w_hi = hi16(wf)
+    s_hi = hi16(sf) if sf is not None else None
+    w_hi_f = w_hi.float() / 2.0 ** b                              # the value the fp16 plane represents
+    s_hi_f = s_hi.float() / 2.0 ** b if sf is not None else None
+    plane16 = with_skip(w_hi.float(), s_hi.float() if sf is not None else None, 64).half()      # exact: already fp16 values
+    hi8 = _e4m3_bytes(with_skip(w_hi_f, s_hi_f, 128), b1)
+    lo8 = _e4m3_bytes(with_skip(wf - w_hi_f, (sf - s_hi_f) if sf is not None else None, 128), b2)
+    blob = torch.cat([plane16.contiguous().view(torch.uint8).reshape(-1), hi8.reshape(-1), lo8.reshape(-1)]).contiguous()
+    return blob, Sh
+
+
+def act_planes_f8(x):
+    """fp32 activations [..., C] -> the uint8 image of an f8 GEMM's A operand (csrc/ops.h): fp16 plane of x * 2^A16, then the e4m3
+    planes (x - hi) * 2^LO8 and hi * 2^HI8.  This is what ds_gn_apply writes with fmt == 1; host copy for tests and documentation."""
+    import torch
+    hi = (x * 2.0 ** S.DS_F8_SH_A16).clamp(-65504.0, 65504.0).half()
+    hf = hi.float() / 2.0 ** S.DS_F8_SH_A16
+    lo8 = _e4m3_bytes(x - hf, S.DS_F8_SH_LO8)
+    hi8 = _e4m3_bytes(hf, S.DS_F8_SH_HI8)
+    return torch.cat([hi.contiguous().view(torch.uint8).reshape(-1), lo8.reshape(-1), hi8.reshape(-1)]).contiguous()
+
+
+def decode_act_planes_f8(buf, shape):
+    """Inverse view of act_planes_f8: (hi, lo8, hi8) as fp32 tensors of `shape`, unscaled."""
+    import torch
+    n = 1
+    for d in shape:
+        n *= d
+    hi = buf[:2 * n].view(torch.float16).float().reshape(shape) / 2.0 ** S.DS_F8_SH_A16
+    lo8 = buf[2 * n:3 * n].view(torch.float8_e4m3fn).float().reshape(shape) / 2.0 ** S.DS_F8_SH_LO8
+    hi8 = buf[3 * n:4 * n].view(torch.float8_e4m3fn).float().reshape(shape) / 2.0 ** S.DS_F8_SH_HI8
+    return hi, lo8, hi8
+
+
+def decode_conv_weight_f8(blob, shift, cout, cin, taps, c2=0, bn=None):
+    """Inverse view of pack_conv_weight_f8: the three weight planes as fp32 [cout, taps, cin] (+ skip [cout, c2]), unscaled."""
+    import torch
+    BN, n_tiles = (bn, -(-cout // bn)) if bn else pick_bn(cout)
+    cout_pad = BN * n_tiles
+    c64, c128 = -(-cin // 64) * 64, -(-cin // 128) * 128
+    s64, s128 = -(-c2 // 64) * 64, -(-c2 // 128) * 128
+    k16, k8 = taps * c64 + s64, taps * c128 + s128
+    n16 = cout_pad * k16 * 2
+    p16 = blob[:n16].view(torch.float16).float().reshape(cout_pad, k16) / 2.0 ** (shift - S.DS_F8_SH_A16)
+    h8 = blob[n16:n16 + cout_pad * k8].view(torch.float8_e4m3fn).float().reshape(cout_pad, k8) / 2.0 ** (shift - S.DS_F8_SH_LO8)
+    l8 = blob[n16 + cout_pad * k8:n16 + 2 * cout_pad * k8].view(torch.float8_e4m3fn).float().reshape(cout_pad, k8) / 2.0 ** (shift - S.DS_F8_SH_HI8)
+
+    def cut(p, cp, sp):
+        main = p[:cout, :taps * cp].reshape(cout, taps, cp)[:, :, :cin]
+        skip = p[:cout, taps * cp:taps * cp + sp][:, :c2]
+        return main, skip
+    return cut(p16, c64, s64), cut(h8, c128, s128), cut(l8, c128, s128)
 
 
 def split_planes(x):

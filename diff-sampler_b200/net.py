@@ -14,7 +14,9 @@ from . import _lib
 from . import edm_nets
 from . import plan as planner
 
-PRECISIONS = {'fp16x3': 3, 'fp16': 1}
+# precision -> MMA passes per product.  'fp16f8': the block convolutions (98 % of the FLOPs) run hi x hi in fp16 and the two 2^-11
+# correction products as e4m3 MMAs at twice the rate (2 MMA units per product instead of 3, csrc/ops.h); everything else is fp16x3.
+PRECISIONS = {'fp16x3': 3, 'fp16': 1, 'fp16f8': 3}
 
 
 class B200Net:
@@ -28,11 +30,12 @@ class B200Net:
         self.sigma_min, self.sigma_max, self.sigma_data = sigma_min, sigma_max, sigma_data
         self.precision = precision
         self.npass = PRECISIONS[precision]
+        self.f8 = precision == 'fp16f8'
         self.fuse_stats = bool(fuse_stats)
         self.flash_attn = bool(flash_attn)
         self.spec = edm_nets.spec_from_params(params, img_resolution, img_channels, label_dim)
         self.spec.sigma_data = sigma_data
-        self.wb, self.winfo = planner.pack_weights(self.spec, params)
+        self.wb, self.winfo = planner.pack_weights(self.spec, params, f8=self.f8)
         blob = self.wb.bytes()
         self._wh = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -63,7 +66,7 @@ class B200Net:
         ent = self._plans.get(key)
         if ent is None:
             pl = planner.compile_plan(self.spec, self.wb, self.winfo, B, nsig, nlab, npass=self.npass, fuse_stats=self.fuse_stats,
-                                           flash_attn=self.flash_attn)
+                                           flash_attn=self.flash_attn, f8=self.f8)
             h = C.c_void_p()
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.ds_unet_create(self._wh, C.cast(pl.ops_array, C.c_void_p), pl.n_ops, C.sizeof(S.PlanOp),

@@ -62,20 +62,25 @@ def _qkv_split(w, b, heads):
     return torch.cat([w2[qi], w2[ki]]), torch.cat([b[qi], b[ki]]), w2[vi], b[vi]
 
 
-def pack_weights(spec, params):
-    """Everything the kernels read that does not depend on the batch size."""
+def pack_weights(spec, params, f8=False):
+    """Everything the kernels read that does not depend on the batch size.  f8=True packs the block convolutions (conv0, conv1 +
+    skip) in the fp16 + 2 x e4m3 operand layout of the f8 GEMM mode (csrc/ops.h); everything else keeps fp16 hi/lo planes."""
     pf = spec.prefix
     P = lambda k: params[pf + k].detach().float().cpu()
     has = lambda k: (pf + k) in params
     wb = WeightBlob()
     info = {}
 
-    def add_conv(key, w, skip_w=None, bias=None):
-        packed = G.pack_conv_weight(w, skip_w)
+    def add_conv(key, w, skip_w=None, bias=None, as_f8=False):
+        if as_f8:
+            packed, shift = G.pack_conv_weight_f8(w, skip_w)
+            info[key] = dict(cout=w.shape[0], f8_shift=shift)
+        else:
+            packed = G.pack_conv_weight(w, skip_w)
+            info[key] = dict(cout=w.shape[0], cout_pad=packed.shape[1], ktot=packed.shape[2])
         wb.add(key + ':w', packed)
         if bias is not None:
             wb.add(key + ':b', bias.float())
-        info[key] = dict(cout=w.shape[0], cout_pad=packed.shape[1], ktot=packed.shape[2])
 
     add_conv(spec.stem, P(spec.stem + '.weight'), bias=P(spec.stem + '.bias'))
     aff_w, aff_b = [], []
@@ -83,7 +88,7 @@ def pack_weights(spec, params):
         n = b.name
         wb.add(n + '.norm0:g', P(n + '.norm0.weight'))
         wb.add(n + '.norm0:b', P(n + '.norm0.bias'))
-        add_conv(n + '.conv0', P(n + '.conv0.weight'), bias=P(n + '.conv0.bias'))
+        add_conv(n + '.conv0', P(n + '.conv0.weight'), bias=P(n + '.conv0.bias'), as_f8=f8)
         wb.add(n + '.norm1:g', P(n + '.norm1.weight'))
         wb.add(n + '.norm1:b', P(n + '.norm1.bias'))
         bias1 = P(n + '.conv1.bias')
@@ -91,7 +96,7 @@ def pack_weights(spec, params):
         if b.skip == 'conv':
             skip_w = P(n + '.skip.weight')
             bias1 = bias1 + P(n + '.skip.bias')
-        add_conv(n + '.conv1', P(n + '.conv1.weight'), skip_w, bias=bias1)
+        add_conv(n + '.conv1', P(n + '.conv1.weight'), skip_w, bias=bias1, as_f8=f8)
         aff_w.append(P(n + '.affine.weight'))
         aff_b.append(P(n + '.affine.bias'))
         if b.heads:
@@ -155,10 +160,16 @@ class Plan:
         self.meta = meta
 
 
-def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash_attn=True):
+def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash_attn=True, f8=False):
     """Lower the forward pass for batch B.  nsig in {1, B}: number of sigma values (embedding rows);
-    nlab in {0, 1, B}: rows of class labels supplied."""
+    nlab in {0, 1, B}: rows of class labels supplied.  f8: the block convolutions run in the f8 GEMM mode (weights must have been
+    packed with pack_weights(f8=True))."""
     assert nsig in (1, B) and nlab in (0, 1, B)
+    assert not f8 or npass == 3
+    fmt = 1 if f8 else 0
+
+    def f8_args(key):
+        return dict(f8=True, acc_scale=2.0 ** -winfo[key]['f8_shift']) if f8 else {}
     A = _Arena()
     ops = []        # list of (type, tag, builder(R) -> desc)
     F4, H2 = 4, 2
@@ -304,18 +315,18 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
         emit(lambda R: S.GnApplyDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, H=Hi, W=Hi, B=B, groups=_groups(cin), **stat_args(R, s0),
                                      gamma=W(n + '.norm0:g'), beta=W(n + '.norm0:b'), eps=b.eps, silu=1, ada=0, ada_stride=0,
                                      resample=resample, nplanes=npl, out_act=R('act'), out_raw=R('raw') if want_raw else 0,
-                                     out_raw_f32=R('rawf') if want_rawf else 0))
+                                     out_raw_f32=R('rawf') if want_rawf else 0, fmt=fmt))
         A.need('y', Mo * cout * F4)
         emit_producer('y', cout, Mo, lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cin, W(n + '.conv0:w'), cout, taps=9, npass=npass, out_f32=R('y'),
                                                  bias=W(n + '.conv0:b'), rowvec=0 if b.adaptive_scale else R('aff', b.aff_off * F4),
-                                                 rowvec_stride=aff_stride)[0])
+                                                 rowvec_stride=aff_stride, **f8_args(n + '.conv0'))[0])
         s1 = stats_slot()
         need_stats(s1, [('y', cout)], Ho * Ho)
         emit(lambda R: S.GnApplyDesc(src0=R('y'), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), **stat_args(R, s1),
                                      gamma=W(n + '.norm1:g'), beta=W(n + '.norm1:b'), eps=b.eps, silu=1,
                                      ada=R('aff', b.aff_off * F4) if b.adaptive_scale else 0,
                                      ada_stride=aff_stride if b.adaptive_scale else 0, resample=0, nplanes=npl, out_act=R('act'),
-                                     out_raw=0, out_raw_f32=0))
+                                     out_raw=0, out_raw_f32=0, fmt=fmt))
         xout = A.need('x:' + n, Mo * cout * F4)
         mid = A.need('xmid', Mo * cout * F4) if b.heads else xout
         if b.skip == 'identity':
@@ -328,7 +339,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
         emit_producer(mid, cout, Mo, lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cout, W(n + '.conv1:w'), cout, taps=9, npass=npass,
                                                  a2_ptr=R('raw') if want_raw else 0, C2=cin if want_raw else 0, out_f32=R(mid),
                                                  bias=W(n + '.conv1:b'), residual=R(res_name) if res_name else 0, ldr=cout,
-                                                 scale=b.skip_scale)[0])
+                                                 scale=b.skip_scale, **f8_args(n + '.conv1'))[0])
         if b.heads:
             nh = b.heads
             d = cout // nh
@@ -403,6 +414,6 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
         arr[i].type = S.OP_TYPE_OF[type(desc)]
         arr[i].tag = tg
         setattr(arr[i].u, S.UNION_FIELD[arr[i].type], desc)
-    meta = dict(B=B, nsig=nsig, nlab=nlab, npass=npass, n_ops=len(ops),
+    meta = dict(B=B, nsig=nsig, nlab=nlab, npass=npass, f8=bool(f8), n_ops=len(ops),
                 n_gemm=sum(1 for i in range(len(ops)) if arr[i].type == S.DS_OP_GEMM))
     return Plan(arr, len(ops), total, dict(A.offsets), meta)

@@ -7,10 +7,15 @@ Tolerance (BASELINE.json north_star): max-abs <= 1e-3 per pixel on identical lat
 checked too.  precision='fp16x3' (split-precision tcgen05, 3 MMAs per product) is the mode that must hold 1e-3;
 precision='fp16' (single pass) is reported with its own, looser bound.
 """
+import os
+
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+# The f8 GEMM mode (precision='fp16f8') is opt-in until it has a green run on a B200 recorded under profiles/.
+f8_opt_in = pytest.mark.skipif(os.environ.get('DSB_F8_TESTS') != '1', reason='f8 GEMM mode is opt-in: set DSB_F8_TESTS=1')
 
 TOL = 1e-3
 
@@ -89,6 +94,45 @@ def test_denoiser_parity(name, precision, tol):
     err = (got - ref).abs().max().item()
     print(f'{name} {precision} per-sample sigma: {err:.3e}')
     assert err < tol
+
+
+@f8_opt_in
+@pytest.mark.parametrize('name', ['tiny_song', 'tiny_adm', 'cifar10'])
+def test_denoiser_parity_f8_mode(name):
+    """precision='fp16f8': block convolutions as fp16 hi x hi + two e4m3 correction products (2 MMA units per product instead of 3).
+    Expected error ~1e-4 on the de-zeroed nets (tests/study_fp8_corrections.py), inside the 1e-3 contract."""
+    from oracle import edm_oracle as O
+    on, P, S = _oracle(name)
+    nat = _native(P, S, 'fp16f8')
+    ref_nat = _native(P, S, 'fp16x3')
+    B = 3
+    x0 = O.stacked_randn(range(B), (S['img_channels'], S['img_resolution'], S['img_resolution']))
+    lab = _labels(S, B)
+    labd = None if lab is None else lab.to(_dev())
+    for sigma in (80.0, 2.5, 0.05):
+        x = x0 * sigma
+        ref = on(x, torch.tensor(sigma), class_labels=lab)
+        got = nat(x.to(_dev()), torch.tensor(sigma, device=_dev()), class_labels=labd).cpu()
+        got3 = ref_nat(x.to(_dev()), torch.tensor(sigma, device=_dev()), class_labels=labd).cpu()
+        err, err3 = (got - ref).abs().max().item(), (got3 - ref).abs().max().item()
+        print(f'{name} fp16f8 sigma={sigma}: max-abs err {err:.3e} (fp16x3 {err3:.3e}, max|D| {ref.abs().max().item():.2f})')
+        assert err < TOL / 2
+
+
+@f8_opt_in
+def test_sampler_parity_f8_mode():
+    from oracle import edm_oracle as O
+    from oracle import solvers_oracle as SO
+    from diff_sampler_b200 import solvers
+    on, P, S = _oracle('tiny_song')
+    nat = _native(P, S, 'fp16f8')
+    lat = O.stacked_randn(range(4), (3, 16, 16))
+    for solver, kw in (('heun', dict(num_steps=6)), ('dpm_pp', dict(num_steps=7, max_order=3, predict_x0=True))):
+        ref = SO.sample(on, lat, solver, **kw)
+        got = getattr(solvers, solver + '_sampler')(nat, lat.to(_dev()), **kw).cpu()
+        err = (got - ref).abs().max().item()
+        print(f'tiny_song fp16f8 {solver}: final-image max-abs err {err:.3e}')
+        assert err < TOL
 
 
 @pytest.mark.parametrize('fuse', [True, False])

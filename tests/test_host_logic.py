@@ -96,6 +96,55 @@ def test_weight_packing_roundtrip():
     assert torch.equal(bv, idx[:, :, 2].reshape(-1).float())
 
 
+def test_f8_operand_packing_and_plan():
+    """f8 GEMM mode (csrc/ops.h): operand images are self-consistent (hi + lo reproduces the value to ~2^-15 relative, the three
+    scales of each operand pair add up to the same S) and the plan marks exactly the block convolutions."""
+    torch.manual_seed(0)
+    w = torch.randn(100, 192, 3, 3) / 40
+    sk = torch.randn(100, 64, 1, 1) / 8
+    blob, shift = G.pack_conv_weight_f8(w, sk)
+    bn, tiles = G.pick_bn(100)
+    k16, k8 = 9 * 192 + 64, 9 * 256 + 128
+    assert blob.dtype == torch.uint8 and blob.numel() == bn * tiles * (2 * k16 + 2 * k8)
+    assert shift == S.DS_F8_SH_LO8 + int(np.floor(np.log2(448.0 / max(w.abs().max().item(), sk.abs().max().item()))))
+    (m16, s16), (mh8, sh8), (ml8, sl8) = G.decode_conv_weight_f8(blob, shift, 100, 192, 9, 64)
+    wk, skk = w.permute(0, 2, 3, 1).reshape(100, 9, 192), sk.reshape(100, 64)
+    wmax = max(wk.abs().max().item(), skk.abs().max().item())
+    assert (m16 - wk).abs().max() <= 2.0 ** -11 * wmax and (s16 - skk).abs().max() <= 2.0 ** -11 * wmax
+    assert (m16 + ml8 - wk).abs().max() <= 2.0 ** -15 * wmax and (s16 + sl8 - skk).abs().max() <= 2.0 ** -15 * wmax
+    assert ((mh8 - m16).abs() <= 2.0 ** -4 * m16.abs() + 2.0 ** -10 * wmax).all()
+    x = torch.randn(2, 4, 4, 64) * 3
+    hi, lo8, hi8 = G.decode_act_planes_f8(G.act_planes_f8(x), x.shape)
+    assert (hi - x).abs().max() <= 2.0 ** -11 * 16 and (hi + lo8 - x).abs().max() <= 2.0 ** -15 * 16
+    assert ((hi8 - hi).abs() <= 2.0 ** -4 * hi.abs() + 2.0 ** -11).all()
+    # saturation instead of inf / nan for out-of-range activations
+    big = torch.tensor([[2000.0, -5000.0, 100.0, 1e-9] * 16])
+    hi, lo8, hi8 = G.decode_act_planes_f8(G.act_planes_f8(big), big.shape)
+    assert torch.isfinite(hi).all() and torch.isfinite(lo8).all() and torch.isfinite(hi8).all() and hi.abs().max() < 1024
+
+    params, cfg = edm_nets.init_params('tiny_song', seed=0)
+    spec = edm_nets.spec_from_params(params, cfg['img_resolution'], cfg['img_channels'], cfg.get('label_dim', 0))
+    wb, info = planner.pack_weights(spec, params, f8=True)
+    pl = planner.compile_plan(spec, wb, info, 3, 1, 0, npass=3, f8=True)
+    ref_wb, ref_info = planner.pack_weights(spec, params)
+    ref_pl = planner.compile_plan(spec, ref_wb, ref_info, 3, 1, 0, npass=3)
+    assert pl.n_ops == ref_pl.n_ops and pl.arena_bytes == ref_pl.arena_bytes and wb.size <= ref_wb.size * 1.35
+    n_f8 = n_fmt = 0
+    for i in range(pl.n_ops):
+        op = pl.ops_array[i]
+        if op.type == S.DS_OP_GEMM and op.u.gemm.f8:
+            g = op.u.gemm
+            n_f8 += 1
+            assert g.a_mode == 0 and g.num_z == 1 and g.npass == 3 and g.taps == 9 and g.b_dims[2] == 1 and g.a_dims[3] == g.a_plane_n
+            assert 0 < g.acc_scale < 1 and np.log2(g.acc_scale) == round(np.log2(g.acc_scale))
+        elif op.type == S.DS_OP_GEMM:
+            assert op.u.gemm.acc_scale in (0.0, 1.0)
+        if op.type == S.DS_OP_GN_APPLY and op.u.gn_apply.fmt == 1:
+            n_fmt += 1
+    blocks = spec.enc + spec.dec
+    assert n_f8 == 2 * len(blocks) and n_fmt == 2 * len(blocks)
+
+
 def test_schedules_and_deis_tables_match_reference_golden():
     d = np.load(GOLD)
     for st in ('polynomial', 'logsnr', 'time_uniform'):
