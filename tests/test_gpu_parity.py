@@ -42,12 +42,13 @@ def _labels(S, B, seed=0):
     return torch.eye(S['label_dim'])[torch.randint(S['label_dim'], (B,), generator=g)]
 
 
-@pytest.mark.parametrize('name', ['tiny_song', 'tiny_adm'])
-def test_block_outputs_localise(name):
+@pytest.mark.parametrize('name,precision', [('tiny_song', 'fp16x3'), ('tiny_adm', 'fp16x3'),
+                                            pytest.param('tiny_song', 'fp16f8', marks=f8_opt_in), pytest.param('tiny_adm', 'fp16f8', marks=f8_opt_in)])
+def test_block_outputs_localise(name, precision):
     """Per-block activations of the native plan vs the oracle's (diagnostic: names the first block that drifts)."""
     from oracle import edm_oracle as O
     on, P, S = _oracle(name)
-    nat = _native(P, S)
+    nat = _native(P, S, precision)
     B = 3
     x = O.stacked_randn(range(B), (S['img_channels'], S['img_resolution'], S['img_resolution'])) * 3.0
     lab = _labels(S, B)
@@ -66,7 +67,7 @@ def test_block_outputs_localise(name):
         print(f'{bname:28s} max|ref| {t.abs().max().item():9.4f}  err {err:.3e}')
     err = (got.cpu() - ref).abs().max().item()
     print(f'{name}: D err {err:.3e}')
-    assert worst < 1e-4 and err < TOL
+    assert worst < (1e-4 if precision == 'fp16x3' else 5e-4) and err < TOL
 
 
 @pytest.mark.parametrize('name,precision,tol', [('tiny_song', 'fp16x3', TOL), ('tiny_adm', 'fp16x3', TOL), ('tiny_song', 'fp16', 2e-2),
