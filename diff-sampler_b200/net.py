@@ -60,6 +60,20 @@ class B200Net:
         return cls(sd, net.img_resolution, net.img_channels, net.label_dim, sigma_min=float(net.sigma_min),
                    sigma_max=float(net.sigma_max), sigma_data=float(getattr(net, 'sigma_data', 0.5)), **kw)
 
+    @classmethod
+    def from_pickle(cls, f, key='ema', **kw):
+        """Load an EDM `network-snapshot-*.pkl` (what sample.py:81-82 feeds to `pickle.load(f)['ema']`) without the reference's
+        torch_utils / dnnlib on the path and without executing the source embedded in the file (checkpoint.py).  The reference then sets
+        `net.sigma_min = 0.002; net.sigma_max = 80.0` (sample.py:83-84); pass other values through `kw` if needed."""
+        from . import checkpoint
+        params, meta = checkpoint.load_edm_pickle(f, key=key)
+        kw.setdefault('sigma_min', 0.002)
+        kw.setdefault('sigma_max', 80.0)
+        kw.setdefault('sigma_data', meta['sigma_data'])
+        net = cls(params, meta['img_resolution'], meta['img_channels'], meta['label_dim'], **kw)
+        net.checkpoint_meta = meta
+        return net
+
     # ---- plan cache -------------------------------------------------------------------------------------------------
     def _plan(self, B, nsig, nlab):
         key = (B, nsig, nlab)

@@ -1,0 +1,64 @@
+"""EDM snapshot importer (diff-sampler_b200/checkpoint.py) against fixtures written by the REAL reference classes through its own
+torch_utils/persistence.py (oracle/gen_edm_pickle.py): same tensor names, order and values as the reference's state_dict()."""
+import hashlib
+import io
+import json
+import os
+import pickle
+
+import pytest
+import torch
+
+from diff_sampler_b200 import checkpoint as CK
+from diff_sampler_b200 import edm_nets, plan as planner
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+META = json.load(open(os.path.join(GOLD, 'edm_snapshot.json')))
+
+
+def digest(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(v.detach().to(torch.float32).contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize('name', ['song', 'adm_fp16'])
+def test_snapshot_matches_reference_state_dict(name):
+    m = META[name]
+    params, meta = CK.load_edm_pickle(os.path.join(GOLD, m['file']))
+    assert len(params) == m['n_tensors'] and list(params)[:4] == m['keys_head']
+    assert digest(params) == m['digest']                       # names, order and every value, bit for bit
+    assert (meta['img_resolution'], meta['img_channels'], meta['label_dim']) == (m['img_resolution'], m['img_channels'], m['label_dim'])
+    assert meta['use_fp16'] == m['use_fp16'] and meta['sigma_data'] == m['sigma_data'] and meta['class_name'] == 'EDMPrecond'
+    assert all(v.dtype == torch.float32 and v.device.type == 'cpu' for v in params.values())
+    # the imported dict drives the same spec inference / weight packing as a live reference module (B200Net.from_reference)
+    spec = edm_nets.spec_from_params(params, meta['img_resolution'], meta['img_channels'], meta['label_dim'])
+    assert spec.kind == ('song' if meta['model_type'] == 'SongUNet' else 'adm')
+    assert len(spec.enc + spec.dec) > 0
+
+
+def test_file_object_and_missing_key():
+    with open(os.path.join(GOLD, META['song']['file']), 'rb') as f:
+        params, _ = CK.load_edm_pickle(f)
+    assert digest(params) == META['song']['digest']
+    with pytest.raises(CK.CheckpointError):
+        CK.load_edm_pickle(os.path.join(GOLD, META['song']['file']), key='no_such_entry')
+
+
+def test_other_network_classes_are_refused():
+    with pytest.raises(CK.CheckpointError, match='EDMPrecond'):
+        CK.load_edm_pickle(os.path.join(GOLD, META['bare_unet']['file']))
+
+
+def test_nothing_outside_the_snapshot_vocabulary_is_unpickled():
+    """The stock loader exec()s source embedded in the file (persistence.py:222-234); this one resolves a fixed set of names only."""
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ('echo pwned',))
+    blob = pickle.dumps(dict(ema=Evil()))
+    with pytest.raises(CK.CheckpointError, match='refusing'):
+        CK.load_edm_pickle(io.BytesIO(blob))
+    with pytest.raises(CK.CheckpointError):
+        CK.load_edm_pickle(io.BytesIO(b'not a pickle at all'))
