@@ -70,3 +70,39 @@ def test_rank_batches_matches_reference_partition():
             assert all(torch.equal(a, b) for a, b in zip(mine, ref[rank::world]))
             seen += [int(v) for b in mine for v in b]
         assert sorted(seen) == list(range(50000))
+
+
+def _fid_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from diff_sampler_b200 import dist_utils, fid_stats
+    dist_utils.init(backend='gloo')
+    g = torch.Generator().manual_seed(5)
+    images = torch.randint(0, 256, (41, 6, 6, 3), generator=g, dtype=torch.uint8)         # the "finished samples" of the whole job
+    proj = torch.randn(3 * 6 * 6, 16, generator=g, dtype=torch.float64)
+    detector = lambda x: (x.reshape(x.shape[0], -1).to(torch.float64) / 255.0) @ proj       # stands in for Inception features
+    st = fid_stats.FeatureStats()
+    for b in dist_utils.rank_batches(range(41), 8, world, rank):                            # this rank's batches, ragged (41 = 5*8 + 1)
+        st.append_images(images[b], detector)
+    mu, sigma = st.reduce().finalize()
+    if rank == 0:
+        torch.save(dict(mu=mu, sigma=sigma, n=st.n, images=images, proj=proj), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fid_statistics_allreduce_matches_single_process_reference_formulas(tmp_path):
+    """fid.py:61-79 on two ranks == the same formulas over all images in one process; FID of identical statistics is ~0."""
+    import numpy as np
+    from diff_sampler_b200 import fid_stats
+    out = str(tmp_path / 'fid.pt')
+    mp.spawn(_fid_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    assert r['n'] == 41
+    f = ((r['images'].permute(0, 3, 1, 2).reshape(41, -1).to(torch.float64) / 255.0) @ r['proj']).numpy()
+    mu = f.sum(0) / 41
+    sigma = (f.T @ f - np.outer(mu, mu) * 41) / 40
+    assert np.allclose(r['mu'], mu, rtol=1e-12, atol=1e-12) and np.allclose(r['sigma'], sigma, rtol=1e-10, atol=1e-10)
+    assert np.allclose(sigma, np.cov(f, rowvar=False), rtol=1e-9, atol=1e-9)               # it is the unbiased covariance
+    assert abs(fid_stats.frechet_distance(r['mu'], r['sigma'], mu, sigma)) < 1e-6
+    shifted = fid_stats.frechet_distance(r['mu'] + 0.5, r['sigma'], mu, sigma)
+    assert abs(shifted - 0.25 * 16) < 1e-6                                                  # |dmu|^2 with equal covariances
