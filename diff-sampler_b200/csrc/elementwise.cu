@@ -4,6 +4,7 @@
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace dsb {
 
@@ -268,6 +269,100 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
             *reinterpret_cast<float4*>(d.out_raw_f32 + o + 4) = make_float4(raw[4], raw[5], raw[6], raw[7]);
         }
     }
+}
+
+// Variant of the plain (RESAMPLE == 0) path, selected with DSB_GN_APPLY_V2=1 (A/B, see profiles/): the normalisation is folded to one FMA
+// per element, y = x * a + b' with b' = b - mean * a (16 instead of 24 live coefficient registers), and four pixels are processed per
+// iteration so that eight 16-byte loads are in flight per thread (the two-pixel loop keeps ~49 KB per SM in flight, about what HBM needs).
+template <int NP>
+__device__ __forceinline__ void gn_v2_pixels(const ds_gn_apply_desc& d, const float* base, int pitch, long long n, int npix, int C, int c,
+                                             long long plane, int po, int rows, bool norm, const float* a, const float* b, __half* oact,
+                                             __half* oraw) {
+    float4 v[NP][2];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const float4* s = reinterpret_cast<const float4*>(base + (long long)(po + k * rows) * pitch);
+        v[k][0] = __ldcs(s);
+        v[k][1] = __ldcs(s + 1);
+    }
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const float e[8] = {v[k][0].x, v[k][0].y, v[k][0].z, v[k][0].w, v[k][1].x, v[k][1].y, v[k][1].z, v[k][1].w};
+        const long long o = ((long long)n * npix + po + k * rows) * C + c;
+        if (oact) {
+            float y[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float u = 0.f;
+                if (norm) {
+                    u = fmaf(e[j], a[j], b[j]);
+                    if (d.silu) u = silu_f(u);
+                }
+                y[j] = u;
+            }
+            gn_store_planes(oact, plane, o, y, d.nplanes, d.fmt);
+        }
+        if (oraw) gn_store_planes(oraw, plane, o, e, d.nplanes, d.fmt);
+        if (d.out_raw_f32) {
+            *reinterpret_cast<float4*>(d.out_raw_f32 + o) = v[k][0];
+            *reinterpret_cast<float4*>(d.out_raw_f32 + o + 4) = v[k][1];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) gn_apply_v2_kernel(ds_gn_apply_desc d, int pix_per_cta, int nc8, int rows) {
+    const int C = d.C0 + d.C1;
+    const int n = blockIdx.y;
+    const int c8 = threadIdx.x % nc8;
+    const int prow = threadIdx.x / nc8;
+    const int c = c8 * 8;
+    const bool norm = d.sums != nullptr;
+    float a[8], b[8];
+    if (norm) {
+        const int cpg = C / d.groups;
+        const double cnt = (double)cpg * d.H * d.W;
+        int g_prev = -1;
+        float mu_f = 0.f, rstd = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c + j) / cpg;
+            if (g != g_prev) {
+                const double s = d.sums[((long long)n * d.groups + g) * 2 + 0];
+                const double q = d.sums[((long long)n * d.groups + g) * 2 + 1];
+                const double mu = s / cnt;
+                double var = q / cnt - mu * mu;
+                if (var < 0.0) var = 0.0;
+                rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+                mu_f = (float)mu;
+                g_prev = g;
+            }
+            float aa = rstd * __ldg(d.gamma + c + j);
+            float bb = __ldg(d.beta + c + j);
+            if (d.ada) {
+                const float sc = d.ada[(long long)n * d.ada_stride + c + j] + 1.0f;
+                const float sh = d.ada[(long long)n * d.ada_stride + C + c + j];
+                aa *= sc;
+                bb = bb * sc + sh;
+            }
+            a[j] = aa;
+            b[j] = fmaf(-mu_f, aa, bb);
+        }
+    }
+    const int npix = d.H * d.W;
+    const long long plane = (long long)d.B * npix * C;
+    const float* base;
+    int pitch, cc;
+    if (c < d.C0) { base = d.src0; pitch = d.C0; cc = c; }
+    else { base = d.src1; pitch = d.C1; cc = c - d.C0; }
+    base += (long long)n * npix * pitch + cc;
+    __half* oact = reinterpret_cast<__half*>(d.out_act);
+    __half* oraw = reinterpret_cast<__half*>(d.out_raw);
+    const int p_begin = blockIdx.x * pix_per_cta;
+    int p_end = p_begin + pix_per_cta;
+    if (p_end > npix) p_end = npix;
+    int po = p_begin + prow;
+    for (; po + 3 * rows < p_end; po += 4 * rows) gn_v2_pixels<4>(d, base, pitch, n, npix, C, c, plane, po, rows, norm, a, b, oact, oraw);
+    for (; po < p_end; po += rows) gn_v2_pixels<1>(d, base, pitch, n, npix, C, c, plane, po, rows, norm, a, b, oact, oraw);
 }
 
 // ------------------------------------------------------------------------------------------ softmax
@@ -625,6 +720,11 @@ extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream
     while (pix_per_cta > rows && (long long)((npix + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
     const int chunks = (npix + pix_per_cta - 1) / pix_per_cta;
     dim3 grid(chunks, d->B);
+    static const int use_v2 = [] { const char* e = getenv("DSB_GN_APPLY_V2"); return e ? atoi(e) : 0; }();
+    if (use_v2 && d->resample == 0) {
+        gn_apply_v2_kernel<<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
+        return ok();
+    }
     if (d->resample == 1) gn_apply_kernel<1><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
     else if (d->resample == 3) gn_apply_kernel<3><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
     else if (d->resample == 2) gn_apply_kernel<2><<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);

@@ -16,7 +16,7 @@ from . import _lib
 from . import ldm_plan
 from .solver_utils import solver_update
 
-PRECISIONS = {'fp16x3': 3, 'fp16': 1}
+PRECISIONS = {'fp16x3': 3, 'fp16': 1, 'fp16f8': 3}       # fp16f8: ResBlock convolutions in the f8 GEMM mode (net.py, csrc/ops.h)
 
 
 def make_alphas_cumprod(linear_start=0.00085, linear_end=0.0120, n=1000):
@@ -27,17 +27,22 @@ def make_alphas_cumprod(linear_start=0.00085, linear_end=0.0120, n=1000):
 
 class B200LDMNet:
     def __init__(self, params, img_resolution=64, img_channels=4, num_heads=8, alphas_cumprod=None, guidance_type='classifier-free',
-                 guidance_rate=1.0, epsilon_t=1e-3, precision='fp16x3', device='cuda', flash_attn=True):
+                 guidance_rate=1.0, epsilon_t=1e-3, precision=None, device='cuda', flash_attn=True):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.DsError('B200LDMNet needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()
         self.img_resolution, self.img_channels, self.label_dim = img_resolution, img_channels, True
         self.guidance_type, self.guidance_rate = guidance_type, guidance_rate
+        if precision is None:
+            from .net import default_precision
+            precision = default_precision()
+        self.precision = precision
         self.npass = PRECISIONS[precision]
+        self.f8 = precision == 'fp16f8'
         self.flash_attn = bool(flash_attn)
         self.st = ldm_plan.ldm_structure(params, num_heads)
-        self.wb, self.info = ldm_plan.pack_ldm_weights(self.st, params)
+        self.wb, self.info = ldm_plan.pack_ldm_weights(self.st, params, f8=self.f8)
         blob = self.wb.bytes()
         self._wh = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -97,7 +102,7 @@ class B200LDMNet:
         ent = self._plans.get(key)
         if ent is None:
             pl = ldm_plan.compile_ldm_plan(self.st, self.wb, self.info, B, Bt, nT, self.img_resolution, npass=self.npass,
-                                               flash_attn=self.flash_attn)
+                                               flash_attn=self.flash_attn, f8=self.f8)
             h = C.c_void_p()
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.ds_unet_create(self._wh, C.cast(pl.ops_array, C.c_void_p), pl.n_ops, C.sizeof(S.PlanOp), pl.arena_bytes,

@@ -99,10 +99,11 @@ def _pad_heads_cols(w, heads, dh):
     return out
 
 
-def pack_ldm_weights(st, params):
+def pack_ldm_weights(st, params, f8=False):
+    """f8=True: the ResBlock convolutions (in_layers.2, out_layers.3 + skip_connection) are packed for the f8 GEMM mode (csrc/ops.h)."""
     P = lambda k: params[k].detach().float().cpu()
     wb = WeightBlob()
-    info = dict(res=[], ctx_dim=None)
+    info = dict(res=[], ctx_dim=None, f8_shift={})
 
     def add_lin(key, w, bias=None):
         """Linear / 1x1 conv weight [N, K] as a packed GEMM operand."""
@@ -110,8 +111,12 @@ def pack_ldm_weights(st, params):
         if bias is not None:
             wb.add(key + ':b', bias)
 
-    def add_conv(key, w, skip_w=None, bias=None):
-        wb.add(key + ':w', G.pack_conv_weight(w, skip_w))
+    def add_conv(key, w, skip_w=None, bias=None, as_f8=False):
+        if as_f8:
+            packed, info['f8_shift'][key] = G.pack_conv_weight_f8(w, skip_w)
+            wb.add(key + ':w', packed)
+        else:
+            wb.add(key + ':w', G.pack_conv_weight(w, skip_w))
         if bias is not None:
             wb.add(key + ':b', bias)
 
@@ -128,7 +133,7 @@ def pack_ldm_weights(st, params):
             elif kind == 'res':
                 wb.add(n + '.n0:g', P(n + '.in_layers.0.weight'))
                 wb.add(n + '.n0:b', P(n + '.in_layers.0.bias'))
-                add_conv(n + '.c0', P(n + '.in_layers.2.weight'), bias=P(n + '.in_layers.2.bias'))
+                add_conv(n + '.c0', P(n + '.in_layers.2.weight'), bias=P(n + '.in_layers.2.bias'), as_f8=f8)
                 wb.add(n + '.n1:g', P(n + '.out_layers.0.weight'))
                 wb.add(n + '.n1:b', P(n + '.out_layers.0.bias'))
                 b1 = P(n + '.out_layers.3.bias')
@@ -136,7 +141,7 @@ def pack_ldm_weights(st, params):
                 if (n + '.skip_connection.weight') in params:
                     skw = P(n + '.skip_connection.weight')
                     b1 = b1 + P(n + '.skip_connection.bias')
-                add_conv(n + '.c1', P(n + '.out_layers.3.weight'), skw, bias=b1)
+                add_conv(n + '.c1', P(n + '.out_layers.3.weight'), skw, bias=b1, as_f8=f8)
                 aff_w.append(P(n + '.emb_layers.1.weight'))
                 aff_b.append(P(n + '.emb_layers.1.bias'))
                 info['res'].append((n, aff_off))
@@ -177,11 +182,16 @@ def pack_ldm_weights(st, params):
     return wb, info
 
 
-def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_attn=True):
+def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_attn=True, f8=False):
     """Lower the eps-net for Bt samples (Bt = B, or 2B under classifier-free guidance) at latent resolution R.
     nT in {1, Bt}: number of timestep values.  io: X = x [B,C,R,R], SIGMA = timesteps [nT], LABELS = coef [B|1][4] (c_in in slot 2),
     CTX = context [Bt, 77, ctx_dim], D = eps [Bt,C,R,R] (NCHW), BOTTLENECK = channel-mean of the middle block [Bt, 64]."""
     assert nT in (1, Bt)
+    assert not f8 or (npass == 3 and info['f8_shift'])
+    fmt_res = 1 if f8 else 0
+
+    def f8_args(key):
+        return dict(f8=True, acc_scale=2.0 ** -info['f8_shift'][key]) if f8 else {}
     A = _Arena()
     ops = []
     npl = 2
@@ -229,11 +239,11 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
         emit(lambda R_: S.GnStatsDesc(src0=R_(n0), src1=R_(n1) if n1 else 0, C0=c0, C1=c1, HW=hw, B=Bt, groups=_groups(c0 + c1),
                                       sums=R_('stats', slot)))
 
-    def gn_apply(slot, parts, H, g, b, eps, silu, out):
+    def gn_apply(slot, parts, H, g, b, eps, silu, out, fmt=0):
         (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
         emit(lambda R_: S.GnApplyDesc(src0=R_(n0), src1=R_(n1) if n1 else 0, C0=c0, C1=c1, H=H, W=H, B=Bt, groups=_groups(c0 + c1),
                                       sums=R_('stats', slot), gamma=W(g), beta=W(b), eps=eps, silu=silu, ada=0, ada_stride=0, resample=0,
-                                      nplanes=npl, out_act=R_(out), out_raw=0, out_raw_f32=0))
+                                      nplanes=npl, out_act=R_(out), out_raw=0, out_raw_f32=0, fmt=fmt))
 
     def lower_res(L, parts, H):
         """ResBlock (openaimodel.py:255-275): GN+SiLU+conv3x3, + Linear(SiLU(emb)), GN+SiLU+conv3x3, + skip (identity | 1x1)."""
@@ -249,20 +259,21 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
         (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
         emit(lambda R_: S.GnApplyDesc(src0=R_(n0), src1=R_(n1) if n1 else 0, C0=c0, C1=c1, H=H, W=H, B=Bt, groups=_groups(cin),
                                       sums=R_('stats', s0), gamma=W(n + '.n0:g'), beta=W(n + '.n0:b'), eps=1e-5, silu=1, ada=0, ada_stride=0,
-                                      resample=0, nplanes=npl, out_act=R_('act'), out_raw=R_('raw') if has_skip else 0, out_raw_f32=0))
+                                      resample=0, nplanes=npl, out_act=R_('act'), out_raw=R_('raw') if has_skip else 0, out_raw_f32=0,
+                                      fmt=fmt_res))
         A.need('y', M * cout * F4)
         off = aff_off[n]
         emit(lambda R_: G.conv_gemm(R_('act'), Bt, H, H, cin, W(n + '.c0:w'), cout, taps=9, npass=npass, out_f32=R_('y'), bias=W(n + '.c0:b'),
-                                    rowvec=R_('aff', off * F4), rowvec_stride=aff_stride)[0])
+                                    rowvec=R_('aff', off * F4), rowvec_stride=aff_stride, **f8_args(n + '.c0'))[0])
         s1 = stats_slot()
         gn_stats(s1, [('y', cout)], H * H)
-        gn_apply(s1, [('y', cout)], H, n + '.n1:g', n + '.n1:b', 1e-5, 1, 'act')
+        gn_apply(s1, [('y', cout)], H, n + '.n1:g', n + '.n1:b', 1e-5, 1, 'act', fmt=fmt_res)
         out = A.need('h:' + n, M * cout * F4)
         res_name = None if has_skip else parts[0][0]
         assert has_skip or len(parts) == 1
         emit(lambda R_: G.conv_gemm(R_('act'), Bt, H, H, cout, W(n + '.c1:w'), cout, taps=9, npass=npass, a2_ptr=R_('raw') if has_skip else 0,
                                     C2=cin if has_skip else 0, out_f32=R_(out), bias=W(n + '.c1:b'), residual=R_(res_name) if res_name else 0,
-                                    ldr=cout, scale=1.0)[0])
+                                    ldr=cout, scale=1.0, **f8_args(n + '.c1'))[0])
         return out, cout
 
     def cast_planes(src, C, H, dst):

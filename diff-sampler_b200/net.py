@@ -19,10 +19,20 @@ from . import plan as planner
 PRECISIONS = {'fp16x3': 3, 'fp16': 1, 'fp16f8': 3}
 
 
+def default_precision():
+    """Precision of a B200Net built without an explicit `precision=`; the environment variable DSB_PRECISION overrides it."""
+    import os
+    p = os.environ.get('DSB_PRECISION', 'fp16x3')
+    if p not in PRECISIONS:
+        raise ValueError(f'DSB_PRECISION={p!r}: expected one of {sorted(PRECISIONS)}')
+    return p
+
+
 class B200Net:
     def __init__(self, params, img_resolution, img_channels, label_dim=0, sigma_min=0.002, sigma_max=80.0, sigma_data=0.5,
-                 precision='fp16x3', device='cuda', fuse_stats=True, flash_attn=True):
+                 precision=None, device='cuda', fuse_stats=True, flash_attn=True):
         self.device = torch.device(device)
+        precision = precision or default_precision()
         if self.device.type != 'cuda':
             raise _lib.DsError('B200Net needs a CUDA device (no CPU fallback)')
         self.lib = _lib.load()

@@ -64,7 +64,8 @@ def _qkv_split(w, b, heads):
 
 def pack_weights(spec, params, f8=False):
     """Everything the kernels read that does not depend on the batch size.  f8=True packs the block convolutions (conv0, conv1 +
-    skip) in the fp16 + 2 x e4m3 operand layout of the f8 GEMM mode (csrc/ops.h); everything else keeps fp16 hi/lo planes."""
+    skip) and the head conv in the fp16 + 2 x e4m3 operand layout of the f8 GEMM mode (csrc/ops.h); everything else keeps fp16 hi/lo
+    planes (the attention GEMMs share their operand planes, the stem conv reads the 3-channel input)."""
     pf = spec.prefix
     P = lambda k: params[pf + k].detach().float().cpu()
     has = lambda k: (pf + k) in params
@@ -119,7 +120,8 @@ def pack_weights(spec, params, f8=False):
             wb.add('map_label:b', P('map_label.bias'))
     wb.add(spec.head_norm + ':g', P(spec.head_norm + '.weight'))
     wb.add(spec.head_norm + ':b', P(spec.head_norm + '.bias'))
-    add_conv(spec.head_conv, P(spec.head_conv + '.weight'), bias=P(spec.head_conv + '.bias'))
+    # the head conv has 3 output channels: its cost is reading the A operand, which the f8 layout cuts from 3 to 2 tile loads per 64 channels
+    add_conv(spec.head_conv, P(spec.head_conv + '.weight'), bias=P(spec.head_conv + '.bias'), as_f8=f8)
     return wb, info
 
 
@@ -400,10 +402,11 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
     need_stats(sh, [(fin, fin_c)], HW0)
     emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=_groups(fin_c), **stat_args(R, sh),
                                  gamma=W(spec.head_norm + ':g'), beta=W(spec.head_norm + ':b'), eps=spec.head_eps, silu=1, ada=0,
-                                 ada_stride=0, resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))
+                                 ada_stride=0, resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0, fmt=fmt))
     emit(lambda R: G.conv_gemm(R('act'), B, R0, R0, fin_c, W(spec.head_conv + ':w'), spec.img_channels, taps=9, npass=npass,
                                bias=W(spec.head_conv + ':b'),
-                               edm=(io(S.DS_IO_X), R('coef'), 4 if nsig > 1 else 0, spec.img_channels, io(S.DS_IO_D)))[0])
+                               edm=(io(S.DS_IO_X), R('coef'), 4 if nsig > 1 else 0, spec.img_channels, io(S.DS_IO_D)),
+                               **f8_args(spec.head_conv))[0])
     assert stat_i[0] <= n_stats
 
     total = A.finalize()

@@ -14,8 +14,6 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-# The f8 GEMM mode (precision='fp16f8') is opt-in until it has a green run on a B200 recorded under profiles/.
-f8_opt_in = pytest.mark.skipif(os.environ.get('DSB_F8_TESTS') != '1', reason='f8 GEMM mode is opt-in: set DSB_F8_TESTS=1')
 
 TOL = 1e-3
 
@@ -30,7 +28,7 @@ def _oracle(name, dezero=True, seed=0):
     return O.OracleNet(P, S), P, S
 
 
-def _native(P, S, precision='fp16x3'):
+def _native(P, S, precision=None):
     from diff_sampler_b200.net import B200Net
     return B200Net(P, S['img_resolution'], S['img_channels'], S['label_dim'], precision=precision, device=_dev())
 
@@ -43,7 +41,7 @@ def _labels(S, B, seed=0):
 
 
 @pytest.mark.parametrize('name,precision', [('tiny_song', 'fp16x3'), ('tiny_adm', 'fp16x3'),
-                                            pytest.param('tiny_song', 'fp16f8', marks=f8_opt_in), pytest.param('tiny_adm', 'fp16f8', marks=f8_opt_in)])
+                                            ('tiny_song', 'fp16f8'), ('tiny_adm', 'fp16f8')])
 def test_block_outputs_localise(name, precision):
     """Per-block activations of the native plan vs the oracle's (diagnostic: names the first block that drifts)."""
     from oracle import edm_oracle as O
@@ -97,7 +95,6 @@ def test_denoiser_parity(name, precision, tol):
     assert err < tol
 
 
-@f8_opt_in
 @pytest.mark.parametrize('name', ['tiny_song', 'tiny_adm', 'cifar10'])
 def test_denoiser_parity_f8_mode(name):
     """precision='fp16f8': block convolutions as fp16 hi x hi + two e4m3 correction products (2 MMA units per product instead of 3).
@@ -120,7 +117,6 @@ def test_denoiser_parity_f8_mode(name):
         assert err < TOL / 2
 
 
-@f8_opt_in
 def test_sampler_parity_f8_mode():
     from oracle import edm_oracle as O
     from oracle import solvers_oracle as SO
@@ -408,7 +404,7 @@ def test_ldm_unfused_attention_matches():
 
 
 # --------------------------------------------------------------------------------------------- latent diffusion (config 5)
-def _ldm_pair(name='tiny_ldm', guidance=7.5, precision='fp16x3', flash_attn=True):
+def _ldm_pair(name='tiny_ldm', guidance=7.5, precision=None, flash_attn=True):
     from oracle import ldm_oracle as LO
     from diff_sampler_b200.ldm_net import B200LDMNet
     P, cfg = LO.make_params(name)
@@ -449,6 +445,26 @@ def test_ldm_eps_net_blocks_localise():
     e = (got.cpu() - ref).abs().max().item()
     print(f'tiny_ldm D (cfg 7.5): err {e:.3e} (max|D| {ref.abs().max().item():.2f})')
     assert worst < 1e-4 and e < TOL * max(1.0, ref.abs().max().item())
+
+
+def test_ldm_cfg_denoiser_parity_f8_mode():
+    """precision='fp16f8' on the latent-diffusion eps-net: ResBlock convolutions in the f8 GEMM mode, transformer GEMMs in fp16x3."""
+    from oracle import edm_oracle as O
+    on, nat, cfg = _ldm_pair(precision='fp16f8')
+    _, nat3, _ = _ldm_pair(precision='fp16x3')
+    B, R = 3, cfg['img_resolution']
+    x0 = O.stacked_randn(range(B), (4, R, R))
+    g = torch.Generator().manual_seed(6)
+    c = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    uc = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    for sigma in (10.0, 0.5):
+        ref = on(x0 * sigma, torch.tensor([sigma]), condition=c, unconditional_condition=uc)
+        args = ((x0 * sigma).to(_dev()), torch.tensor([sigma], device=_dev()))
+        got = nat(*args, condition=c.to(_dev()), unconditional_condition=uc.to(_dev())).cpu()
+        got3 = nat3(*args, condition=c.to(_dev()), unconditional_condition=uc.to(_dev())).cpu()
+        err, err3 = (got - ref).abs().max().item(), (got3 - ref).abs().max().item()
+        print(f'ldm fp16f8 sigma={sigma}: err {err:.3e} (fp16x3 {err3:.3e}, max|D| {ref.abs().max().item():.1f})')
+        assert err < TOL * max(1.0, ref.abs().max().item())
 
 
 @pytest.mark.parametrize('guidance', [7.5, 1.0])

@@ -142,7 +142,24 @@ def test_f8_operand_packing_and_plan():
         if op.type == S.DS_OP_GN_APPLY and op.u.gn_apply.fmt == 1:
             n_fmt += 1
     blocks = spec.enc + spec.dec
-    assert n_f8 == 2 * len(blocks) and n_fmt == 2 * len(blocks)
+    assert n_f8 == 2 * len(blocks) + 1 and n_fmt == 2 * len(blocks) + 1          # block convolutions + the head conv
+
+
+@pytest.mark.parametrize('f8', [False, True])
+def test_ldm_plan_lowering(f8):
+    """The latent-diffusion eps-net lowers on the host (no GPU) in both precisions; f8 touches exactly the ResBlock convolutions."""
+    from diff_sampler_b200 import ldm_plan
+    from oracle import ldm_oracle as LO
+    P, cfg = LO.make_params('tiny_ldm')
+    st = ldm_plan.ldm_structure(P, cfg['num_heads'])
+    wb, info = ldm_plan.pack_ldm_weights(st, P, f8=f8)
+    pl = ldm_plan.compile_ldm_plan(st, wb, info, 2, 4, 1, cfg['img_resolution'], npass=3, f8=f8)
+    n_res = sum(1 for _, ls in st['inp'] + st['mid'] + st['out'] for L in ls if L[0] == 'res')
+    n_f8 = sum(1 for i in range(pl.n_ops) if pl.ops_array[i].type == S.DS_OP_GEMM and pl.ops_array[i].u.gemm.f8)
+    n_fmt = sum(1 for i in range(pl.n_ops) if pl.ops_array[i].type == S.DS_OP_GN_APPLY and pl.ops_array[i].u.gn_apply.fmt == 1)
+    assert pl.n_ops > 50 and pl.arena_bytes > 0 and n_res > 0
+    assert (n_f8, n_fmt) == ((2 * n_res, 2 * n_res) if f8 else (0, 0))
+    assert len(info['f8_shift']) == (2 * n_res if f8 else 0)
 
 
 def test_schedules_and_deis_tables_match_reference_golden():
