@@ -37,13 +37,18 @@ def parse():
     ap.add_argument('--solver', default='heun', help='heun | euler | ipndm | dpm_pp | amed_dpm_pp (sd15)')
     ap.add_argument('--num_steps', type=int, default=10)
     ap.add_argument('--batch', type=int, default=512, help='images per GPU per step')
-    ap.add_argument('--precision', default='fp16x3', choices=['fp16x3', 'fp16', 'fp16f8'],
-                    help="fp16x3 (default): 3 fp16 MMAs per product; fp16f8: fp16 hi x hi + two e4m3 correction MMAs (block convolutions); fp16: single pass")
+    ap.add_argument('--precision', default='auto', choices=['auto', 'fp16x3', 'fp16', 'fp16f8'],
+                    help="fp16x3: 3 fp16 MMAs per product; fp16f8: fp16 hi x hi + two e4m3 correction MMAs (block / head convolutions); fp16: single "
+                         "pass; auto (default): the fastest mode whose final images stay within the 1e-3 contract for the named net (PRECISION_FOR)")
     ap.add_argument('--cpu_batch', type=int, default=8, help='batch of the bounded CPU-baseline sample')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--fuse_stats', type=int, default=1, help='1 (default): GroupNorm statistics from the GEMM epilogues; 0: separate gn_stats pass')
     ap.add_argument('--no_extras', action='store_true', help='skip the roofline / e2e / fp16 legs (timing of the main leg is unchanged)')
-    return ap.parse_args()
+    args = ap.parse_args()
+    args.precision_requested = args.precision
+    if args.precision == 'auto':
+        args.precision = PRECISION_FOR.get(args.net, 'fp16x3')
+    return args
 
 
 def peaks():
@@ -272,7 +277,8 @@ def main():
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='fp16 operands, fp32 accumulate' + {'fp16x3': ' (split-precision: 3 tcgen05 MMAs per product)',
                                                            'fp16f8': ' (split-precision: fp16 hi x hi + two e4m3 correction MMAs per product)'}.get(args.precision, ''),
-                data='synthetic', config=config, gpu_launches=launches, clocks=clk, precision=args.precision)
+                data='synthetic', config=config, gpu_launches=launches, clocks=clk, precision=args.precision,
+                precision_requested=args.precision_requested)
     if e2e:
         line['e2e'] = e2e
     if gathered:
@@ -394,6 +400,54 @@ def sd15_param_shapes():
     return sh
 
 
+# `--precision auto`: the fastest precision whose FINAL IMAGES hold max-abs <= 1e-3 against the reference on that net's BASELINE config
+# (de-zeroed random-init weights).  Measured on B200 (profiles/r01d, tests/test_gpu_parity.py::test_fullsize_sampler_parity_f8_mode):
+#   cifar10  Heun NFE=18      fp16f8 vs fp16x3 2.7e-4 (+ fp16x3 vs reference <= 1.5e-4)            -> fp16f8
+#   imagenet64 DPM++ NFE=10   3.5e-5                                                             -> fp16f8
+#   ffhq     iPNDM NFE=6      1.08e-3: over the gate (this net amplifies GEMM rounding the most)   -> fp16x3
+#   sd15     no sampler-level fp16f8 measurement yet                                              -> fp16x3
+PRECISION_FOR = {'cifar10': 'fp16f8', 'imagenet64': 'fp16f8', 'ffhq': 'fp16x3', 'sd15': 'fp16x3'}
+
+
+# DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the named GEMM, from `ncu --set full` captures of this
+# bench command committed under profiles/ (a number measured under the profiler is a byte count, not a time).
+NCU_TRAFFIC = {
+    ('conv3x3 256->256 @32x32 x512', 'fp16x3'): (0.539457e9 + 0.496578e9, 'profiles/r01b_ncu_gemm_conv_b512.txt (launch id 1)'),
+    ('conv3x3 256->256 @32x32 x512 f8', 'fp16f8'): (0.539682e9 + 0.498288e9, 'profiles/r01c/ncu_gemm_conv_b512_fp16f8.txt (launch id 0)'),
+}
+
+
+def dominant_launch(args, line, net):
+    """Per-launch view of the GEMM shape that takes the largest share of the forward: algorithmic FLOPs and bytes of one launch
+    (gemm_desc.describe) over its mean CUDA-event time in this run, plus the ncu DRAM traffic of the same launch where a capture exists."""
+    from diff_sampler_b200 import _cstructs as S
+    from diff_sampler_b200 import gemm_desc as G
+    ms, pl = net.last_profile
+    groups = {}
+    for i in range(pl.n_ops):
+        op = pl.ops_array[i]
+        if op.type != S.DS_OP_GEMM:
+            continue
+        r = G.describe(op.u.gemm)
+        g = groups.setdefault(r['label'], dict(n=0, ms=0.0, flops=r['flops'], bytes=r['bytes']))
+        g['n'] += 1
+        g['ms'] += ms[i]
+    label, g = max(groups.items(), key=lambda kv: kv[1]['ms'])
+    for (lab, prec), _ in NCU_TRAFFIC.items():            # prefer the shape the committed ncu capture shows, when this plan has it
+        if prec == args.precision and lab in groups and groups[lab]['ms'] >= 0.5 * g['ms']:
+            label, g = lab, groups[lab]
+    per = g['ms'] / g['n']
+    traffic = NCU_TRAFFIC.get((label, args.precision))
+    rl = line['roofline']
+    rl['dominant_launch'] = dict(label=label, launches_per_forward=g['n'], ms_per_launch=per, share_of_gemm_time=g['ms'] / rl['gemm_ms_per_forward'],
+                                 algorithmic_flops=g['flops'], achieved_tflops=g['flops'] / (per / 1e3) / 1e12,
+                                 frac_of_peak=g['flops'] / (per / 1e3) / 1e12 / rl['peak'], algorithmic_bytes=g['bytes'],
+                                 traffic=traffic[0] if traffic else None, traffic_source=traffic[1] if traffic else None)
+    if traffic:
+        rl['traffic'] = traffic[0]
+        rl['traffic_note'] = f'per launch of the dominant GEMM ({label}): algorithmic {g["bytes"] / 1e9:.3f} GB; ' + traffic[1]
+
+
 def extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk):
     import torch
     from diff_sampler_b200 import solver_utils
@@ -417,6 +471,10 @@ def extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk):
                                 all_ops_ms_per_forward=fwd_ms, gemm_share_of_forward=gemm_ms / fwd_ms if fwd_ms else None,
                                 executed_mma_flops_factor={'fp16x3': 3, 'fp16f8': 2}.get(args.precision, 1), peak_source=pk['source'] + ', sustained bf16 GEMM')
         line['forward_breakdown_ms'] = {str(k): round(v[1], 4) for k, v in sorted(prof.items())}
+        try:
+            dominant_launch(args, line, net)
+        except Exception as e:                   # diagnostic detail only; the aggregate roofline above stands on its own
+            line['roofline']['dominant_launch_error'] = repr(e)
         # ---- the fused solver-update kernel against the HBM roofline (HBM-resident size: 3 x 1 GiB streams) -------------
         n = 256 * 1024 * 1024
         a, b_, c = (torch.empty(n, device=dev).normal_() for _ in range(3))

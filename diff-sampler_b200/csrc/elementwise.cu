@@ -271,9 +271,10 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(ds_gn_apply_desc d, int p
     }
 }
 
-// Variant of the plain (RESAMPLE == 0) path, selected with DSB_GN_APPLY_V2=1 (A/B, see profiles/): the normalisation is folded to one FMA
-// per element, y = x * a + b' with b' = b - mean * a (16 instead of 24 live coefficient registers), and four pixels are processed per
-// iteration so that eight 16-byte loads are in flight per thread (the two-pixel loop keeps ~49 KB per SM in flight, about what HBM needs).
+// The plain (RESAMPLE == 0) path, default since round 1 (DSB_GN_APPLY_V2=0 selects the older loop inside gn_apply_kernel<0> for A/B): the
+// normalisation is folded to one FMA per element, y = x * a + b' with b' = b - mean * a (16 instead of 24 live coefficient registers), and
+// four pixels are processed per iteration so that eight 16-byte loads are in flight per thread (the two-pixel loop keeps ~49 KB per SM in
+// flight, about the minimum HBM needs).  Measured on the CIFAR-10 forward at batch 512: 10.7 -> 9.55 ms (profiles/r01d).
 template <int NP>
 __device__ __forceinline__ void gn_v2_pixels(const ds_gn_apply_desc& d, const float* base, int pitch, long long n, int npix, int C, int c,
                                              long long plane, int po, int rows, bool norm, const float* a, const float* b, __half* oact,
@@ -720,7 +721,7 @@ extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream
     while (pix_per_cta > rows && (long long)((npix + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
     const int chunks = (npix + pix_per_cta - 1) / pix_per_cta;
     dim3 grid(chunks, d->B);
-    static const int use_v2 = [] { const char* e = getenv("DSB_GN_APPLY_V2"); return e ? atoi(e) : 0; }();
+    static const int use_v2 = [] { const char* e = getenv("DSB_GN_APPLY_V2"); return e ? atoi(e) : 1; }();
     if (use_v2 && d->resample == 0) {
         gn_apply_v2_kernel<<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);
         return ok();

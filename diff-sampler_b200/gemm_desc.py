@@ -203,6 +203,30 @@ def pack_conv_weight(weight, skip_weight=None, cin_pad=None, bn=None):
     return torch.stack([hi, lo]).contiguous()
 
 
+def describe(d):
+    """Algorithmic work of one ds_gemm_desc launch (bench.py roofline): label, FLOPs (2 M N K over the valid extents, counted once per
+    product whatever the number of precision passes) and the bytes the launch has to move through HBM when every operand is read
+    once and every output written once: 4 B per A element in all layouts (fp16 hi + lo, or fp16 + 2 x e4m3), the packed weights,
+    fp32 / fp16-plane outputs, the residual."""
+    m, n, z = int(d.m_valid), int(d.n_valid), max(int(d.num_z), 1)
+    k_main = int(d.taps) * int(d.cpb) * 64
+    k_aux = int(d.a2_c)
+    k = k_main + k_aux
+    flops = 2.0 * m * n * k * z
+    a_bytes = 4 * m * (int(d.cpb) * 64 + k_aux) * z if d.a_mode == 0 else 4 * m * k * z
+    w_bytes = 4 * n * k * (z if d.a_mode == 1 else 1)
+    out_bytes = m * n * z * ((4 if d.out_f32 else 0) + (4 if d.out_h16 and d.o_plane else (2 if d.out_h16 else 0)))
+    if d.edm_out:
+        out_bytes = 2 * 4 * m * int(d.edm_C)                       # read x, write D (NCHW fp32)
+    res_bytes = 4 * m * n * z if d.residual else 0
+    if d.a_mode == 0:
+        label = f"conv{'3x3' if d.taps == 9 else '1x1'} {int(d.cpb) * 64}{'+' + str(k_aux) if k_aux else ''}->{n} @{int(d.conv_H)}x{int(d.conv_W)} x{m // max(int(d.conv_H) * int(d.conv_W), 1)}"
+    else:
+        label = f'gemm {m}x{n}x{k} z{z}'
+    return dict(label=label + (' f8' if d.f8 else ''), flops=flops, bytes=float(a_bytes + w_bytes + out_bytes + res_bytes),
+                m=m, n=n, k=k, z=z, f8=bool(d.f8))
+
+
 E4M3_MAX = 448.0
 
 

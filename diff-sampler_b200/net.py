@@ -150,6 +150,7 @@ class B200Net:
             t = self.lib.ds_unet_op_type(h, i)
             c, ms = out.get(t, (0, 0.0))
             out[t] = (c + 1, ms + buf[i])
+        self.last_profile = ([float(buf[i]) for i in range(n)], pl)          # per-op milliseconds + the plan they index
         return out
 
     def round_sigma(self, sigma):

@@ -132,6 +132,26 @@ def test_sampler_parity_f8_mode():
         assert err < TOL
 
 
+@pytest.mark.parametrize('name,solver,kw', [('cifar10', 'heun', dict(num_steps=10)),
+                                            ('imagenet64', 'dpm_pp', dict(num_steps=11, max_order=2, predict_x0=True))])
+def test_fullsize_sampler_parity_f8_mode(name, solver, kw):
+    """The configurations bench.py runs in fp16f8 by default (PRECISION_FOR): BASELINE config 2 (CIFAR-10, Heun NFE=18) and config 4's
+    net and solver (ImageNet-64, DPM-Solver++(2M) NFE=10), full-size nets, final images against the CPU oracle within the 1e-3 contract."""
+    from oracle import edm_oracle as O
+    from oracle import solvers_oracle as SO
+    from diff_sampler_b200 import solvers
+    on, P, S = _oracle(name)
+    nat = _native(P, S, 'fp16f8')
+    B = 2
+    lat = O.stacked_randn(range(B), (3, S['img_resolution'], S['img_resolution']))
+    lab = _labels(S, B)
+    ref = SO.sample(on, lat, solver, class_labels=lab, **kw)
+    got = getattr(solvers, solver + '_sampler')(nat, lat.to(_dev()), class_labels=None if lab is None else lab.to(_dev()), **kw).cpu()
+    err = (got - ref).abs().max().item()
+    print(f'{name} fp16f8 {solver} {kw}: final-image max-abs err {err:.3e} (max|x| {ref.abs().max().item():.2f})')
+    assert err < TOL
+
+
 @pytest.mark.parametrize('fuse', [True, False])
 def test_fused_groupnorm_stats_plan_matches(fuse):
     """The plan with GroupNorm statistics taken from the GEMM epilogues (default) and the one with the separate gn_stats pass give the
