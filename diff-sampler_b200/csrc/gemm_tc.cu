@@ -16,6 +16,7 @@
 #include "ptx.cuh"
 #include <cuda_fp16.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace dsb {
@@ -58,6 +59,9 @@ struct alignas(64) GemmKernelParams {
     // per 32-row slab partial {sum, sumsq} per group, plain stores (no atomics); the consumer adds the slabs of a sample.
     float* st_quads;
     int tap_dh[9], tap_dw[9], tap_cb[9];
+    // CTA-pair variant (gemm_tc_pair_kernel; appended so that the single-CTA kernel's parameter offsets stay put)
+    CUtensorMap tmBh, tmB8h;             // B boxes of BN/2 rows: each CTA of a pair loads half of the N tile
+    int pair;
 };
 
 struct SmemCtl {
@@ -446,6 +450,191 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair variant (opt-in: DSB_GEMM_2CTA=1)
+// Same roles and pipelines over a cluster of two CTAs (one TPC): the pair owns 256 output rows (M tiles 2*pm + rank) x BN columns; each
+// CTA loads its own 128-row A tile and HALF of the B tile, the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) whose
+// accumulator halves land in the two CTAs' TMEM, and each CTA's epilogue warps drain their own half.  Per 64-channel K block a pair pulls
+// 2 x 16 KB (A) + BN x 128 B (B, once) through L2 instead of 2 x (16 KB + BN x 128 B): -33 % at BN = 256, and the 32 KB stages give a
+// 7-deep ring instead of 4.  (The single-CTA kernel is L2-feed bound at ~14 TB/s, profiles/r01c.)
+// Barriers: full[s] lives in the leader (armed with both CTAs' bytes; both CTAs' TMA complete_tx on it), empty[s] and tmem_full[a] are
+// signalled in both CTAs by multicast commits, tmem_empty[a] in the leader collects the eight epilogue warps of the pair.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc_pair_kernel(const __grid_constant__ GemmKernelParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int half_bn = p.BN >> 1;
+    const int stage_bytes = kATileBytes + half_bn * 128;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.num_stages * stage_bytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int nkb_total = p.nkb_main + p.nkb_aux;
+    const int nkb8 = p.f8 ? p.nkb8_main + p.nkb8_aux : 0;
+    const int n_iters = p.f8 ? 2 * nkb8 + nkb_total : p.npass * nkb_total;
+    const int pair_m_tiles = (p.m_tiles + 1) >> 1;
+    const int total_tiles = pair_m_tiles * p.n_tiles;                     // num_z == 1 (checked on the host)
+    const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmBh);
+        if (p.nkb_aux) tma_prefetch_desc(&p.tmA2);
+        if (p.f8) {
+            tma_prefetch_desc(&p.tmA8);
+            tma_prefetch_desc(&p.tmB8h);
+            if (p.nkb8_aux) tma_prefetch_desc(&p.tmA2_8);
+        }
+        for (int s = 0; s < p.num_stages; ++s) {
+            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&ctl->tmem_full[a], 1);
+            mbar_init(&ctl->tmem_empty[a], 8);                            // 4 epilogue warps of each CTA (used in the leader only)
+        }
+        fence_barrier_init();
+    } else if (warp == 1) {
+        tmem_alloc_pair(&ctl->tmem_base, 512);
+    }
+    tc_fence_before();
+    cluster_sync_all();                                                   // both CTAs' barriers and TMEM exist before any remote use
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = first; tile < total_tiles; tile += step) {
+                const int pm = tile / p.n_tiles;
+                const int nt = tile - pm * p.n_tiles;
+                const int mt = 2 * pm + rank;                             // may be one past the last tile: TMA zero-fills, the epilogue masks
+                const int HW = p.conv_H * p.conv_W;
+                const int p0 = mt * 128;
+                const int an0 = p0 / HW;
+                const int ah0 = (p0 - an0 * HW) / p.conv_W;
+                const int aw0 = 0;
+                const int b_row = nt * p.BN + rank * half_bn;
+                for (int it = 0; it < n_iters; ++it) {
+                    mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * stage_bytes;
+                    uint8_t* sb = sa + kATileBytes;
+                    if (rank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)stage_bytes);
+                    if (it < 2 * nkb8) {
+                        const int pass8 = it >= nkb8 ? 1 : 0;
+                        const int kb = it - pass8 * nkb8;
+                        const int an8 = an0 + pass8 * p.a8_plane_n;
+                        if (kb < p.nkb8_main) {
+                            const int tap = kb / p.cpb8;
+                            const int c0 = (kb - tap * p.cpb8) * 128;
+                            tma_load_4d_pair(&p.tmA8, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an8);
+                        } else {
+                            tma_load_4d_pair(&p.tmA2_8, &ctl->full[stage], sa, (kb - p.nkb8_main) * 128, aw0, ah0, an8);
+                        }
+                        tma_load_3d_pair(&p.tmB8h, &ctl->full[stage], sb, kb * 128, b_row, pass8);
+                    } else {
+                        const int it16 = it - 2 * nkb8;
+                        const int pass = it16 / nkb_total;
+                        const int kb = it16 - pass * nkb_total;
+                        const int pa = (pass == 1) ? 1 : 0;
+                        const int pb = (pass == 2) ? 1 : 0;
+                        if (kb < p.nkb_main) {
+                            const int tap = kb / p.cpb;
+                            const int c0 = (kb - tap * p.cpb) * 64;
+                            tma_load_4d_pair(&p.tmA, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an0 + pa * p.a_plane_n);
+                        } else {
+                            tma_load_4d_pair(&p.tmA2, &ctl->full[stage], sa, (kb - p.nkb_main) * 64, aw0, ah0, an0 + pa * p.a2_plane_n);
+                        }
+                        tma_load_3d_pair(&p.tmBh, &ctl->full[stage], sb, kb * 64, b_row, pb * p.b_plane_batch);
+                    }
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = umma_idesc_pair((uint32_t)p.BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = first; tile < total_tiles; tile += step, ++iter) {
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 256;
+                for (int it = 0; it < n_iters; ++it) {
+                    mbar_wait(&ctl->full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+                    const uint32_t sb = sa + kATileBytes;
+                    const uint64_t da = umma_desc_sw128(sa);
+                    const uint64_t db = umma_desc_sw128(sb);
+                    if (it < 2 * nkb8) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_pair(&ctl->empty[stage]);                 // frees this stage in both CTAs
+                    if (it == n_iters - 1) umma_commit_pair(&ctl->tmem_full[acc]);
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5 of both CTAs, own 128 rows each)
+        const int quad = warp & 3;
+        int iter = 0;
+        for (int tile = first; tile < total_tiles; tile += step, ++iter) {
+            const int pm = tile / p.n_tiles;
+            const int nt = tile - pm * p.n_tiles;
+            const int mt = 2 * pm + rank;
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            mbar_wait(&ctl->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = quad * 32 + lane;
+            const long long grow = (long long)mt * 128 + row;
+            const bool row_ok = grow < p.m_valid;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
+            const float* res_row = p.residual ? p.residual + (row_ok ? grow : 0) * p.ldr + (long long)nt * p.BN : nullptr;
+            float4 res_next[8];
+            auto prefetch = [&](int cc) {
+                if (res_row && (long long)nt * p.BN + cc + 32 <= p.n_valid) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) res_next[q] = *reinterpret_cast<const float4*>(res_row + cc + 4 * q);
+                }
+            };
+            prefetch(0);
+            int c = 0;
+            for (; c + 32 <= p.BN; c += 32) {
+                float4 res_cur[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) res_cur[q] = res_next[q];
+                const int col0 = nt * p.BN + c;
+                const bool in_regs = res_row && (col0 + 32 <= p.n_valid);
+                if (c + 64 <= p.BN) prefetch(c + 32);
+                uint32_t v[32];
+                DSB_TMEM_LD_32(t_row + c, v);
+                tmem_ld_wait();
+                if (col0 < p.n_valid)
+                    epilogue_chunk<32>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, 0, 0, res_cur, in_regs);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&ctl->tmem_empty[acc]);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                      // the leader's MMAs read the peer's shared memory; neither CTA may exit before both are done
+    if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------ host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -482,6 +671,11 @@ static int encode_map_typed(CUtensorMap* m, const void* ptr, int rank, const int
         return -2;
     }
     return 0;
+}
+
+static bool all_tap_cb_zero(const ds_gemm_desc* d) {
+    for (int t = 0; t < 9; ++t) if (d->tap_cb[t]) return false;
+    return true;
 }
 
 // fp16 tensors (also used by attention.cu)
@@ -556,7 +750,25 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     if (d->taps != 1 && d->taps != 9) return -15;
     // fused statistics: whole 32-row slabs (row validity is then warp-uniform), whole channel quads, one z slice, fp32 output
     if (d->st_quads && (d->num_z != 1 || d->m_valid % 32 != 0 || d->n_valid % 4 != 0 || d->edm_out != 0)) return -14;
-    const int stage_bytes = kATileBytes + d->BN * 128;
+    int stage_bytes = kATileBytes + d->BN * 128;
+    // CTA-pair variant (opt-in): convolution GEMMs with at least two full waves of row pairs and an N tile that splits into two
+    // whole 32-row halves; everything else keeps the single-CTA kernel
+    static const int pair_env = [] { const char* e = getenv("DSB_GEMM_2CTA"); return e ? atoi(e) : 0; }();
+    if (pair_env && d->a_mode == 0 && d->num_z == 1 && d->BN % 32 == 0 && d->BN >= 64 && d->m_tiles >= 4 * 148 && all_tap_cb_zero(d)) {
+        int32_t hbox[3] = {64, d->BN / 2, 1};
+        if (encode_map(&kp->tmBh, d->b_ptr, 3, d->b_dims, d->b_strides, hbox)) return -30;
+        if (d->f8) {
+            const int64_t ktot8 = (int64_t)(kp->nkb8_main + kp->nkb8_aux) * 128;
+            const int64_t rows = d->b_dims[1];
+            const int64_t bd8[3] = {ktot8, rows, 2};
+            const int64_t bs8[2] = {ktot8, rows * ktot8};
+            const int32_t hbox8[3] = {128, d->BN / 2, 1};
+            const char* b8 = static_cast<const char*>(d->b_ptr) + rows * d->b_dims[0] * 2;
+            if (encode_map_typed(&kp->tmB8h, b8, 3, bd8, bs8, hbox8, true)) return -31;
+        }
+        kp->pair = 1;
+        stage_bytes = kATileBytes + (d->BN / 2) * 128;
+    }
     int ns = (227 * 1024 - 2048) / stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;
     kp->num_stages = ns;
@@ -569,6 +781,23 @@ void gemm_patch_edm(GemmKernelParams* kp, const float* x, float* D) { kp->edm_x 
 static int g_num_sms = 0;
 static bool g_attr_set = false;
 
+static bool g_pair_attr_set = false;
+
+static int gemm_run_pair(const GemmKernelParams* kp, cudaStream_t stream) {
+    if (!g_pair_attr_set) {
+        if (cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -22;
+        g_pair_attr_set = true;
+    }
+    const int stage_bytes = kATileBytes + (kp->BN / 2) * 128;
+    const size_t smem = (size_t)kp->num_stages * stage_bytes + sizeof(SmemCtl) + 1024;
+    const int tiles = ((kp->m_tiles + 1) / 2) * kp->n_tiles;
+    int clusters = g_num_sms / 2;
+    if (tiles < clusters) clusters = tiles;
+    if (clusters <= 0) return 0;
+    gemm_tc_pair_kernel<<<2 * clusters, kThreads, smem, stream>>>(*kp);       // cluster shape (2,1,1) is part of the kernel (__cluster_dims__)
+    return cudaGetLastError() == cudaSuccess ? 0 : -23;
+}
+
 int gemm_run(const GemmKernelParams* kp, cudaStream_t stream) {
     if (!g_attr_set) {
         int dev = 0;
@@ -577,6 +806,7 @@ int gemm_run(const GemmKernelParams* kp, cudaStream_t stream) {
         if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -20;
         g_attr_set = true;
     }
+    if (kp->pair) return gemm_run_pair(kp, stream);
     const int stage_bytes = kATileBytes + kp->BN * 128;
     const size_t smem = (size_t)kp->num_stages * stage_bytes + sizeof(SmemCtl) + 1024;
     const int tiles = kp->num_z * kp->m_tiles * kp->n_tiles;
