@@ -715,7 +715,7 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     kp->edm_C = d->edm_C; kp->edm_D = d->edm_D;
     kp->st_quads = d->st_quads;
     kp->acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
-    if (d->f8) {
+    if (d->f8 & 1) {
         // e4m3 correction passes: byte planes behind the fp16 plane of each operand (layout: csrc/ops.h)
         if (d->a_mode != 0 || d->num_z != 1 || d->npass != 3 || d->a_plane_n <= 0) return -16;
         for (int t = 0; t < 9; ++t) if (d->tap_cb[t]) return -16;
@@ -754,10 +754,12 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     // CTA-pair variant (opt-in): convolution GEMMs with at least two full waves of row pairs and an N tile that splits into two
     // whole 32-row halves; everything else keeps the single-CTA kernel
     static const int pair_env = [] { const char* e = getenv("DSB_GEMM_2CTA"); return e ? atoi(e) : 0; }();
-    if (pair_env && d->a_mode == 0 && d->num_z == 1 && d->BN % 32 == 0 && d->BN >= 64 && d->m_tiles >= 4 * 148 && all_tap_cb_zero(d)) {
+    const bool pair_forced = (d->f8 & 2) != 0;          // bit 1 of ds_gemm_desc.f8: request the pair kernel for this launch (tests, A/B)
+    if ((pair_forced || (pair_env && d->m_tiles >= 4 * 148)) && d->a_mode == 0 && d->num_z == 1 && d->BN % 32 == 0 && d->BN >= 64 &&
+        all_tap_cb_zero(d)) {
         int32_t hbox[3] = {64, d->BN / 2, 1};
         if (encode_map(&kp->tmBh, d->b_ptr, 3, d->b_dims, d->b_strides, hbox)) return -30;
-        if (d->f8) {
+        if (d->f8 & 1) {
             const int64_t ktot8 = (int64_t)(kp->nkb8_main + kp->nkb8_aux) * 128;
             const int64_t rows = d->b_dims[1];
             const int64_t bd8[3] = {ktot8, rows, 2};

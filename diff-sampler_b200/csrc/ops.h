@@ -69,7 +69,8 @@ typedef struct ds_gemm_desc {
     const float* rowvec;
     int64_t rowvec_stride;  // elements between samples (0 = broadcast)
     int32_t rows_per_sample;
-    int32_t f8;             // 1: fp8 correction passes (see above); requires a_mode == 0, num_z == 1, npass == 3, tap_cb == 0
+    int32_t f8;             // bit 0: fp8 correction passes (see above); requires a_mode == 0, num_z == 1, npass == 3, tap_cb == 0
+                            // bit 1: run this launch on the CTA-pair kernel (gemm_tc_pair_kernel; conv mode, BN % 32 == 0)
     const float* residual;
     int64_t ldr;
     float scale;

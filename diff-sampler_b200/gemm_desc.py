@@ -66,7 +66,7 @@ def conv_box(H, W):
 
 def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w_planes=2, a2_ptr=0, C2=0,
               out_f32=0, out_h16=0, o_planes=2, ldo=None, bias=0, rowvec=0, rowvec_stride=0, residual=0, ldr=None, scale=1.0,
-              edm=None, bn=None, s2d=False, f8=False, acc_scale=1.0):
+              edm=None, bn=None, s2d=False, f8=False, acc_scale=1.0, pair=False):
     """3x3 (taps=9) or 1x1 (taps=1) convolution over NHWC fp16 planes [a_planes][Bn][H][W][C] with the
     packed weight matrix [w_planes][Cout_pad][taps*C + C2] (K ordered tap-major, then the aux/skip block).
     Output rows are NHWC pixels: out[pixel][cout] (+ fused epilogue).
@@ -130,7 +130,7 @@ def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w
     d.residual = residual
     d.ldr = ldr if ldr is not None else Cout
     d.scale = scale
-    d.f8 = 1 if f8 else 0
+    d.f8 = (1 if f8 else 0) | (2 if pair else 0)        # bit 1: CTA-pair kernel for this launch (opt-in, csrc/ops.h)
     d.acc_scale = acc_scale
     if edm is not None:
         d.edm_out = 1
@@ -223,8 +223,8 @@ def describe(d):
         label = f"conv{'3x3' if d.taps == 9 else '1x1'} {int(d.cpb) * 64}{'+' + str(k_aux) if k_aux else ''}->{n} @{int(d.conv_H)}x{int(d.conv_W)} x{m // max(int(d.conv_H) * int(d.conv_W), 1)}"
     else:
         label = f'gemm {m}x{n}x{k} z{z}'
-    return dict(label=label + (' f8' if d.f8 else ''), flops=flops, bytes=float(a_bytes + w_bytes + out_bytes + res_bytes),
-                m=m, n=n, k=k, z=z, f8=bool(d.f8))
+    return dict(label=label + (' f8' if d.f8 & 1 else ''), flops=flops, bytes=float(a_bytes + w_bytes + out_bytes + res_bytes),
+                m=m, n=n, k=k, z=z, f8=bool(d.f8 & 1))
 
 
 E4M3_MAX = 448.0
