@@ -737,9 +737,15 @@ def test_conv_pair_kernel(lib, f8, Bn, H, W, Cin, Cout, C2):
     x2 = torch.randn(Bn, C2, H, W, device=dev()) if C2 else None
     w2 = torch.randn(Cout, C2, 1, 1, device=dev()) / C2 ** 0.5 if C2 else None
     bn = 256 if Cout % 256 == 0 else (192 if Cout % 192 == 0 else 128)
-    outs = {}
+    small = Bn * H * W <= 4096                   # the float64 CPU reference only for the small problem; the large ones are held to the
+    ref = None                                   # single-CTA kernel (itself held to the references by the tests above)
     if f8:
-        ref, blob, shift, abuf, a2buf = _f8_reference(x, w, x2, w2)
+        if small:
+            ref, blob, shift, abuf, a2buf = _f8_reference(x, w, x2, w2)
+        else:
+            blob, shift = G.pack_conv_weight_f8(w.cpu(), None if w2 is None else w2.cpu())
+            abuf = G.act_planes_f8(x.permute(0, 2, 3, 1).contiguous())
+            a2buf = G.act_planes_f8(x2.permute(0, 2, 3, 1).contiguous()) if C2 else None
         wp, xa = blob.to(dev()), abuf.to(dev())
         x2a = a2buf.to(dev()) if C2 else None
         tol = 5e-6
@@ -747,23 +753,27 @@ def test_conv_pair_kernel(lib, f8, Bn, H, W, Cin, Cout, C2):
         xa = planes(x.permute(0, 2, 3, 1).contiguous())
         x2a = planes(x2.permute(0, 2, 3, 1).contiguous()) if C2 else None
         wp = G.pack_conv_weight(w.cpu(), None if w2 is None else w2.cpu()).to(dev())
-        ref = F.conv2d(x.double().cpu(), w.double().cpu(), padding=1)
-        if C2:
-            ref = ref + F.conv2d(x2.double().cpu(), w2.double().cpu())
+        if small:
+            ref = F.conv2d(x.double().cpu(), w.double().cpu(), padding=1)
+            if C2:
+                ref = ref + F.conv2d(x2.double().cpu(), w2.double().cpu())
         tol = 2e-5
-    ms = {}
+    ms, outs = {}, {}
     for pair in (False, True):
         out = torch.full((Bn * H * W, Cout), float('nan'), device=dev())
         kw = dict(f8=True, acc_scale=2.0 ** -shift) if f8 else {}
         d, info = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=9, npass=3, a2_ptr=x2a.data_ptr() if C2 else 0, C2=C2,
                               out_f32=out.data_ptr(), bn=bn, pair=pair, **kw)
         ms[pair] = _time_launch(lib, d)
-        outs[pair] = out.double().cpu()
-    ref = ref.permute(0, 2, 3, 1).reshape(Bn * H * W, Cout)
-    scale = ref.abs().max().item()
-    err = (outs[True] - ref).abs().max().item()
+        outs[pair] = out
+    scale = outs[False].abs().max().item()
     dif = (outs[True] - outs[False]).abs().max().item()
-    print(f'pair conv f8={f8} {Bn}x{H}x{W} {Cin}(+{C2})->{Cout} BN={bn}: single {ms[False] * 1e3:.1f} us, pair {ms[True] * 1e3:.1f} us; '
-          f'pair vs ref {err:.3e}, pair vs single {dif:.3e} (scale {scale:.2f})')
+    msg = f'pair conv f8={f8} {Bn}x{H}x{W} {Cin}(+{C2})->{Cout} BN={bn}: single {ms[False] * 1e3:.1f} us, pair {ms[True] * 1e3:.1f} us; pair vs single {dif:.3e}'
+    if ref is not None:
+        ref = ref.permute(0, 2, 3, 1).reshape(Bn * H * W, Cout)
+        err = (outs[True].double().cpu() - ref).abs().max().item()
+        msg += f', pair vs reference {err:.3e}'
+        assert err <= tol * scale
+    print(msg + f' (scale {scale:.2f})')
     assert not torch.isnan(outs[True]).any()
-    assert err <= tol * scale and dif <= tol * scale
+    assert dif <= tol * scale
