@@ -74,11 +74,11 @@ class ChanmeanDesc(C.Structure):
 
 
 class LayernormDesc(C.Structure):
-    _fields_ = [('src', P), ('gamma', P), ('beta', P), ('out', P), ('rows', I64), ('C', I32), ('nplanes', I32), ('eps', F32), ('pad0', I32)]
+    _fields_ = [('src', P), ('gamma', P), ('beta', P), ('out', P), ('rows', I64), ('C', I32), ('nplanes', I32), ('eps', F32), ('fmt', I32)]
 
 
 class GegluDesc(C.Structure):
-    _fields_ = [('src', P), ('out', P), ('rows', I64), ('I', I32), ('nplanes', I32)]
+    _fields_ = [('src', P), ('out', P), ('rows', I64), ('I', I32), ('nplanes', I32), ('fmt', I32), ('pad0', I32)]
 
 
 class GnFinalizeDesc(C.Structure):

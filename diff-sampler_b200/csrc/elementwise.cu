@@ -663,6 +663,97 @@ __global__ void geglu_kernel(ds_geglu_desc d) {
     if (d.nplanes > 1) *reinterpret_cast<uint2*>(out + d.rows * d.I + row * d.I + j) = *reinterpret_cast<const uint2*>(lo);
 }
 
+// ---- f8 operand image (csrc/ops.h) of four consecutive values: fp16 (v * 2^A16) | e4m3 ((v - hi) * 2^LO8) | e4m3 (hi * 2^HI8) --------------
+// `plane` = elements per plane; o = element offset.  Same arithmetic as gn_store_f8 (which handles eight values).
+__device__ __forceinline__ void store4_f8(__half* base, long long plane, long long o, const float* v) {
+    constexpr float kA16 = (float)(1 << DS_F8_SH_A16), kLo8 = (float)(1 << DS_F8_SH_LO8), kHi8 = (float)(1 << DS_F8_SH_HI8);
+    __align__(8) __half hi[4];
+    __align__(4) unsigned short lo8[2];
+    __align__(4) unsigned short hi8[2];
+    float l[4], h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hi[j] = __float2half_rn(fminf(fmaxf(v[j] * kA16, -65504.f), 65504.f));
+        const float hf = __half2float(hi[j]) * (1.0f / kA16);
+        l[j] = (v[j] - hf) * kLo8;
+        h[j] = hf * kHi8;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+        lo8[j >> 1] = __nv_cvt_float2_to_fp8x2(make_float2(l[j], l[j + 1]), __NV_SATFINITE, __NV_E4M3);
+        hi8[j >> 1] = __nv_cvt_float2_to_fp8x2(make_float2(h[j], h[j + 1]), __NV_SATFINITE, __NV_E4M3);
+    }
+    *reinterpret_cast<uint2*>(base + o) = *reinterpret_cast<const uint2*>(hi);
+    unsigned char* b8 = reinterpret_cast<unsigned char*>(base + plane);
+    *reinterpret_cast<unsigned int*>(b8 + o) = *reinterpret_cast<const unsigned int*>(lo8);
+    *reinterpret_cast<unsigned int*>(b8 + plane + o) = *reinterpret_cast<const unsigned int*>(hi8);
+}
+
+// LayerNorm / GEGLU writing the f8 operand image (fmt == 1; opt-in, feeds an f8 GEMM).  Separate kernels so that the default ones above
+// stay byte-identical; the arithmetic before the store is the same.
+__global__ void layernorm_f8_kernel(ds_layernorm_desc d) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= d.rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* x = d.src + row * d.C;
+    constexpr int MAXV = 16;
+    float4 v[MAXV];
+    const int nv = d.C / 4;
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nv) {
+            v[k] = *reinterpret_cast<const float4*>(x + 4 * j);
+            sum += v[k].x + v[k].y + v[k].z + v[k].w;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)d.C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nv) {
+            const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, e = v[k].w - mean;
+            sq += a * a + b * b + c * c + e * e;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)d.C + d.eps);
+    __half* out = reinterpret_cast<__half*>(d.out);
+    const long long plane = d.rows * d.C;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+        const int j = lane + 32 * k;
+        if (j < nv) {
+            const float4 g = *reinterpret_cast<const float4*>(d.gamma + 4 * j);
+            const float4 b = *reinterpret_cast<const float4*>(d.beta + 4 * j);
+            const float y[4] = {(v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y,
+                                (v[k].z - mean) * rstd * g.z + b.z, (v[k].w - mean) * rstd * g.w + b.w};
+            store4_f8(out, plane, row * d.C + 4 * j, y);
+        }
+    }
+}
+
+__global__ void geglu_f8_kernel(ds_geglu_desc d) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i4 = d.I / 4;
+    const long long total = d.rows * i4;
+    if (idx >= total) return;
+    const long long row = idx / i4;
+    const int j = (int)(idx - row * i4) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(d.src + row * 2 * d.I + j);
+    const float4 g = *reinterpret_cast<const float4*>(d.src + row * 2 * d.I + d.I + j);
+    const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+    float y[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) y[q] = av[q] * (0.5f * gv[q] * (1.0f + erff(gv[q] * 0.70710678118654752f)));
+    store4_f8(reinterpret_cast<__half*>(d.out), d.rows * d.I, row * d.I + j, y);
+}
+
 __global__ void chanmean_kernel(ds_chanmean_desc d) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= d.rows) return;
@@ -736,6 +827,11 @@ extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream
 extern "C" int ds_layernorm_launch(const ds_layernorm_desc* d, cudaStream_t stream) {
     if (d->C % 4 || d->C > 2048) return -2;
     const int wpb = 8;
+    if (d->fmt == 1) {
+        if (d->nplanes != 2) return -2;
+        layernorm_f8_kernel<<<(unsigned)((d->rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(*d);
+        return ok();
+    }
     layernorm_kernel<<<(unsigned)((d->rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(*d);
     return ok();
 }
@@ -743,6 +839,11 @@ extern "C" int ds_layernorm_launch(const ds_layernorm_desc* d, cudaStream_t stre
 extern "C" int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream) {
     if (d->I % 4) return -2;
     const long long total = d->rows * (d->I / 4);
+    if (d->fmt == 1) {
+        if (d->nplanes != 2) return -2;
+        geglu_f8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(*d);
+        return ok();
+    }
     geglu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(*d);
     return ok();
 }

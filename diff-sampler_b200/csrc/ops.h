@@ -231,7 +231,7 @@ typedef struct ds_layernorm_desc {
     int32_t C;
     int32_t nplanes;
     float eps;
-    int32_t pad0;
+    int32_t fmt;            // 0: fp16 hi/lo planes.  1: operand image of an f8 GEMM (ds_gemm_desc.f8)
 } ds_layernorm_desc;
 
 // GEGLU gate: out = x[:, :I] * gelu(x[:, I:]) on fp32 [rows][2I] -> fp16 hi/lo planes [rows][I]  (attention.py:42-44, exact erf GELU).
@@ -241,6 +241,8 @@ typedef struct ds_geglu_desc {
     int64_t rows;
     int32_t I;
     int32_t nplanes;
+    int32_t fmt;            // as ds_layernorm_desc.fmt
+    int32_t pad0;
 } ds_geglu_desc;
 
 // Channel mean of an NHWC fp32 tensor (AMED bottleneck read-out, solvers_amed.py:24,27).

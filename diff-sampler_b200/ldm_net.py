@@ -27,7 +27,7 @@ def make_alphas_cumprod(linear_start=0.00085, linear_end=0.0120, n=1000):
 
 class B200LDMNet:
     def __init__(self, params, img_resolution=64, img_channels=4, num_heads=8, alphas_cumprod=None, guidance_type='classifier-free',
-                 guidance_rate=1.0, epsilon_t=1e-3, precision=None, device='cuda', flash_attn=True):
+                 guidance_rate=1.0, epsilon_t=1e-3, precision=None, device='cuda', flash_attn=True, f8_linear=None):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.DsError('B200LDMNet needs a CUDA device (no CPU fallback)')
@@ -40,9 +40,14 @@ class B200LDMNet:
         self.precision = precision
         self.npass = PRECISIONS[precision]
         self.f8 = precision == 'fp16f8'
+        # opt-in (not yet run on hardware): with fp16f8, also run proj_in / attn2.to_q / GEGLU ff / proj_out in the f8 GEMM mode
+        if f8_linear is None:
+            import os
+            f8_linear = os.environ.get('DSB_LDM_F8_LINEAR') == '1'
+        self.f8_linear = bool(f8_linear) and self.f8
         self.flash_attn = bool(flash_attn)
         self.st = ldm_plan.ldm_structure(params, num_heads)
-        self.wb, self.info = ldm_plan.pack_ldm_weights(self.st, params, f8=self.f8)
+        self.wb, self.info = ldm_plan.pack_ldm_weights(self.st, params, f8=self.f8, f8_linear=self.f8_linear)
         blob = self.wb.bytes()
         self._wh = C.c_void_p()
         with torch.cuda.device(self.device):
@@ -102,7 +107,7 @@ class B200LDMNet:
         ent = self._plans.get(key)
         if ent is None:
             pl = ldm_plan.compile_ldm_plan(self.st, self.wb, self.info, B, Bt, nT, self.img_resolution, npass=self.npass,
-                                               flash_attn=self.flash_attn, f8=self.f8)
+                                               flash_attn=self.flash_attn, f8=self.f8, f8_linear=self.f8_linear)
             h = C.c_void_p()
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.ds_unet_create(self._wh, C.cast(pl.ops_array, C.c_void_p), pl.n_ops, C.sizeof(S.PlanOp), pl.arena_bytes,

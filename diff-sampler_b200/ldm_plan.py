@@ -99,15 +99,22 @@ def _pad_heads_cols(w, heads, dh):
     return out
 
 
-def pack_ldm_weights(st, params, f8=False):
-    """f8=True: the ResBlock convolutions (in_layers.2, out_layers.3 + skip_connection) are packed for the f8 GEMM mode (csrc/ops.h)."""
+def pack_ldm_weights(st, params, f8=False, f8_linear=False):
+    """f8=True: the ResBlock convolutions (in_layers.2, out_layers.3 + skip_connection) are packed for the f8 GEMM mode (csrc/ops.h).
+    f8_linear=True (opt-in, needs f8): also the transformer linears whose A operand has a single consumer -- proj_in, attn2.to_q, the
+    GEGLU feed-forward pair and proj_out (75 % of the transformer's linear FLOPs)."""
+    assert f8 or not f8_linear
     P = lambda k: params[k].detach().float().cpu()
     wb = WeightBlob()
     info = dict(res=[], ctx_dim=None, f8_shift={})
 
-    def add_lin(key, w, bias=None):
+    def add_lin(key, w, bias=None, as_f8=False):
         """Linear / 1x1 conv weight [N, K] as a packed GEMM operand."""
-        wb.add(key + ':w', G.pack_conv_weight(w.reshape(w.shape[0], w.shape[1], 1, 1)))
+        if as_f8:
+            packed, info['f8_shift'][key] = G.pack_conv_weight_f8(w.reshape(w.shape[0], w.shape[1], 1, 1))
+            wb.add(key + ':w', packed)
+        else:
+            wb.add(key + ':w', G.pack_conv_weight(w.reshape(w.shape[0], w.shape[1], 1, 1)))
         if bias is not None:
             wb.add(key + ':b', bias)
 
@@ -151,7 +158,7 @@ def pack_ldm_weights(st, params, f8=False):
                 t = n + '.transformer_blocks.0'
                 wb.add(n + '.norm:g', P(n + '.norm.weight'))
                 wb.add(n + '.norm:b', P(n + '.norm.bias'))
-                add_lin(n + '.proj_in', P(n + '.proj_in.weight').reshape(heads * dh, ch), P(n + '.proj_in.bias'))
+                add_lin(n + '.proj_in', P(n + '.proj_in.weight').reshape(heads * dh, ch), P(n + '.proj_in.bias'), as_f8=f8_linear)
                 for k in (1, 2, 3):
                     wb.add(f'{t}.norm{k}:g', P(f'{t}.norm{k}.weight'))
                     wb.add(f'{t}.norm{k}:b', P(f'{t}.norm{k}.bias'))
@@ -161,14 +168,14 @@ def pack_ldm_weights(st, params, f8=False):
                 wb.add(t + '.attn1.v:w', G.split_planes(wv))
                 add_lin(t + '.attn1.out', _pad_heads_cols(P(t + '.attn1.to_out.0.weight'), heads, dh), P(t + '.attn1.to_out.0.bias'))
                 # cross-attention
-                add_lin(t + '.attn2.q', _pad_heads_rows(P(t + '.attn2.to_q.weight'), heads, dh))
+                add_lin(t + '.attn2.q', _pad_heads_rows(P(t + '.attn2.to_q.weight'), heads, dh), as_f8=f8_linear)
                 add_lin(t + '.attn2.k', _pad_heads_rows(P(t + '.attn2.to_k.weight'), heads, dh))
                 wb.add(t + '.attn2.v:w', G.split_planes(_pad_heads_rows(P(t + '.attn2.to_v.weight'), heads, dh)))
                 add_lin(t + '.attn2.out', _pad_heads_cols(P(t + '.attn2.to_out.0.weight'), heads, dh), P(t + '.attn2.to_out.0.bias'))
                 info['ctx_dim'] = P(t + '.attn2.to_k.weight').shape[1]
-                add_lin(t + '.ff1', P(t + '.ff.net.0.proj.weight'), P(t + '.ff.net.0.proj.bias'))
-                add_lin(t + '.ff2', P(t + '.ff.net.2.weight'), P(t + '.ff.net.2.bias'))
-                add_lin(n + '.proj_out', P(n + '.proj_out.weight').reshape(ch, heads * dh), P(n + '.proj_out.bias'))
+                add_lin(t + '.ff1', P(t + '.ff.net.0.proj.weight'), P(t + '.ff.net.0.proj.bias'), as_f8=f8_linear)
+                add_lin(t + '.ff2', P(t + '.ff.net.2.weight'), P(t + '.ff.net.2.bias'), as_f8=f8_linear)
+                add_lin(n + '.proj_out', P(n + '.proj_out.weight').reshape(ch, heads * dh), P(n + '.proj_out.bias'), as_f8=f8_linear)
             elif kind == 'down':
                 add_conv(n, P(n + '.op.weight'), bias=P(n + '.op.bias'))
             elif kind == 'up':
@@ -182,16 +189,18 @@ def pack_ldm_weights(st, params, f8=False):
     return wb, info
 
 
-def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_attn=True, f8=False):
+def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_attn=True, f8=False, f8_linear=False):
     """Lower the eps-net for Bt samples (Bt = B, or 2B under classifier-free guidance) at latent resolution R.
     nT in {1, Bt}: number of timestep values.  io: X = x [B,C,R,R], SIGMA = timesteps [nT], LABELS = coef [B|1][4] (c_in in slot 2),
     CTX = context [Bt, 77, ctx_dim], D = eps [Bt,C,R,R] (NCHW), BOTTLENECK = channel-mean of the middle block [Bt, 64]."""
     assert nT in (1, Bt)
     assert not f8 or (npass == 3 and info['f8_shift'])
+    assert f8 or not f8_linear
     fmt_res = 1 if f8 else 0
+    fmt_lin = 1 if f8_linear else 0
 
     def f8_args(key):
-        return dict(f8=True, acc_scale=2.0 ** -info['f8_shift'][key]) if f8 else {}
+        return dict(f8=True, acc_scale=2.0 ** -info['f8_shift'][key]) if key in info['f8_shift'] else {}
     A = _Arena()
     ops = []
     npl = 2
@@ -276,10 +285,10 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
                                     ldr=cout, scale=1.0, **f8_args(n + '.c1'))[0])
         return out, cout
 
-    def cast_planes(src, C, H, dst):
-        """fp32 NHWC -> fp16 hi/lo planes (no normalisation)."""
+    def cast_planes(src, C, H, dst, fmt=0):
+        """fp32 NHWC -> fp16 hi/lo planes, or the f8 operand image (fmt=1); no normalisation."""
         emit(lambda R_: S.GnApplyDesc(src0=R_(src), src1=0, C0=C, C1=0, H=H, W=H, B=Bt, groups=32, sums=0, gamma=0, beta=0, eps=0.0, silu=0,
-                                      ada=0, ada_stride=0, resample=0, nplanes=npl, out_act=0, out_raw=R_(dst), out_raw_f32=0))
+                                      ada=0, ada_stride=0, resample=0, nplanes=npl, out_act=0, out_raw=R_(dst), out_raw_f32=0, fmt=fmt))
 
     def lower_attn(L, src, H):
         """SpatialTransformer with one BasicTransformerBlock (attention.py:250-261, :211-215)."""
@@ -292,11 +301,11 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
         s0 = stats_slot()
         gn_stats(s0, [(src, ch)], Lq)
         A.need('act', npl * M * max(ch, inner) * H2)
-        gn_apply(s0, [(src, ch)], H, n + '.norm:g', n + '.norm:b', 1e-6, 0, 'act')
+        gn_apply(s0, [(src, ch)], H, n + '.norm:g', n + '.norm:b', 1e-6, 0, 'act', fmt=fmt_lin)
         for nm in ('t0', 't1', 't2', 't3'):
             A.need(nm, M * inner * F4)
         emit(lambda R_: G.conv_gemm(R_('act'), Bt, H, H, ch, W(n + '.proj_in:w'), inner, taps=1, npass=npass, out_f32=R_('t0'),
-                                    bias=W(n + '.proj_in:b'))[0])
+                                    bias=W(n + '.proj_in:b'), **(f8_args(n + '.proj_in') if f8_linear else {}))[0])
         A.need('ln', npl * M * inner * H2)
         A.need('qk', npl * M * 2 * hp * H2)
         A.need('vt', npl * Bt * hp * max(Lq, TP) * H2)
@@ -305,9 +314,9 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
             A.need('P', npl * Bt * heads * Lq * max(Lq, TP) * H2)
         A.need('o', npl * M * hp * H2)
 
-        def ln(k, srcbuf):
+        def ln(k, srcbuf, fmt=0):
             emit(lambda R_: S.LayernormDesc(src=R_(srcbuf), gamma=W(f'{t}.norm{k}:g'), beta=W(f'{t}.norm{k}:b'), out=R_('ln'), rows=M, C=inner,
-                                            nplanes=npl, eps=1e-5))
+                                            nplanes=npl, eps=1e-5, fmt=fmt))
         # ---- self-attention (attn1): x = attn1(norm1(x)) + x
         ln(1, 't0')
         emit(lambda R_: G.conv_gemm(R_('ln'), Bt, H, H, inner, W(t + '.attn1.qk:w'), 2 * hp, taps=1, npass=npass, out_h16=R_('qk'))[0])
@@ -329,10 +338,11 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
         emit(lambda R_: G.conv_gemm(R_('o'), Bt, H, H, hp, W(t + '.attn1.out:w'), inner, taps=1, npass=npass, out_f32=R_('t1'),
                                     bias=W(t + '.attn1.out:b'), residual=R_('t0'), ldr=inner)[0])
         # ---- cross-attention (attn2): x = attn2(norm2(x), context) + x
-        ln(2, 't1')
+        ln(2, 't1', fmt=fmt_lin)           # single consumer: the to_q GEMM below
         A.need('q2', npl * M * hp * H2)
         A.need('k2', npl * Bt * T * hp * H2)
-        emit(lambda R_: G.conv_gemm(R_('ln'), Bt, H, H, inner, W(t + '.attn2.q:w'), hp, taps=1, npass=npass, out_h16=R_('q2'))[0])
+        emit(lambda R_: G.conv_gemm(R_('ln'), Bt, H, H, inner, W(t + '.attn2.q:w'), hp, taps=1, npass=npass, out_h16=R_('q2'),
+                                    **(f8_args(t + '.attn2.q') if f8_linear else {}))[0])
         emit(lambda R_: G.rows_gemm(R_('ctx'), Bt * T, cd, 1, W(t + '.attn2.k:w'), prows(hp), cd, 1, cd, num_z=1, nh=1, m_valid=Bt * T, n_valid=hp,
                                     npass=npass, out_h16=R_('k2'), ldo=hp, o_plane=Bt * T * hp)[0])
         emit(lambda R_: G.rows_gemm(W(t + '.attn2.v:w'), hp, cd, 1, R_('ctx'), T, cd, Bt, cd, num_z=Bt, nh=1, m_valid=hp, n_valid=T,
@@ -351,19 +361,19 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
         emit(lambda R_: G.conv_gemm(R_('o'), Bt, H, H, hp, W(t + '.attn2.out:w'), inner, taps=1, npass=npass, out_f32=R_('t2'),
                                     bias=W(t + '.attn2.out:b'), residual=R_('t1'), ldr=inner)[0])
         # ---- GEGLU feed-forward: x = ff(norm3(x)) + x
-        ln(3, 't2')
+        ln(3, 't2', fmt=fmt_lin)
         A.need('ff', M * 8 * inner * F4)
         A.need('gg', npl * M * 4 * inner * H2)
         emit(lambda R_: G.conv_gemm(R_('ln'), Bt, H, H, inner, W(t + '.ff1:w'), 8 * inner, taps=1, npass=npass, out_f32=R_('ff'),
-                                    bias=W(t + '.ff1:b'))[0])
-        emit(lambda R_: S.GegluDesc(src=R_('ff'), out=R_('gg'), rows=M, I=4 * inner, nplanes=npl))
+                                    bias=W(t + '.ff1:b'), **(f8_args(t + '.ff1') if f8_linear else {}))[0])
+        emit(lambda R_: S.GegluDesc(src=R_('ff'), out=R_('gg'), rows=M, I=4 * inner, nplanes=npl, fmt=fmt_lin))
         emit(lambda R_: G.conv_gemm(R_('gg'), Bt, H, H, 4 * inner, W(t + '.ff2:w'), inner, taps=1, npass=npass, out_f32=R_('t3'),
-                                    bias=W(t + '.ff2:b'), residual=R_('t2'), ldr=inner)[0])
+                                    bias=W(t + '.ff2:b'), residual=R_('t2'), ldr=inner, **(f8_args(t + '.ff2') if f8_linear else {}))[0])
         # ---- proj_out + outer residual
-        cast_planes('t3', inner, H, 'ln')
+        cast_planes('t3', inner, H, 'ln', fmt=fmt_lin)
         out = A.need('h:' + n, M * ch * F4)
         emit(lambda R_: G.conv_gemm(R_('ln'), Bt, H, H, inner, W(n + '.proj_out:w'), ch, taps=1, npass=npass, out_f32=R_(out),
-                                    bias=W(n + '.proj_out:b'), residual=R_(src), ldr=ch)[0])
+                                    bias=W(n + '.proj_out:b'), residual=R_(src), ldr=ch, **(f8_args(n + '.proj_out') if f8_linear else {}))[0])
         return out, ch
 
     def lower_down(L, src, H):

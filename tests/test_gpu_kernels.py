@@ -777,3 +777,35 @@ def test_conv_pair_kernel(lib, f8, Bn, H, W, Cin, Cout, C2):
     print(msg + f' (scale {scale:.2f})')
     assert not torch.isnan(outs[True]).any()
     assert dif <= tol * scale
+
+
+# --------------------------------------------------------------------------------------------- LayerNorm / GEGLU writing the f8 operand image (opt-in)
+ldm_f8_linear_opt_in = pytest.mark.skipif(os.environ.get('DSB_LDM_F8_LINEAR_TESTS') != '1',
+                                          reason='f8 operand image from LayerNorm / GEGLU is opt-in until it has a green run on hardware')
+
+
+@ldm_f8_linear_opt_in
+def test_layernorm_geglu_f8_image(lib):
+    from diff_sampler_b200 import _cstructs as S
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(31)
+    rows, C = 300, 320
+    x = torch.randn(rows, C, device=dev()) * 2.0 + 0.5
+    g, b = torch.randn(C, device=dev()), torch.randn(C, device=dev())
+    out = torch.zeros(4 * rows * C, dtype=torch.uint8, device=dev())
+    lib.op_launch(S.LayernormDesc(src=x.data_ptr(), gamma=g.data_ptr(), beta=b.data_ptr(), out=out.data_ptr(), rows=rows, C=C, nplanes=2,
+                                  eps=1e-5, fmt=1))
+    I = 640
+    src = torch.randn(rows, 2 * I, device=dev()) * 1.5
+    out2 = torch.zeros(4 * rows * I, dtype=torch.uint8, device=dev())
+    lib.op_launch(S.GegluDesc(src=src.data_ptr(), out=out2.data_ptr(), rows=rows, I=I, nplanes=2, fmt=1))
+    sync()
+    want_ln = F.layer_norm(x.double(), (C,), g.double(), b.double(), 1e-5).cpu()
+    want_gg = (src[:, :I].double() * F.gelu(src[:, I:].double())).cpu()
+    for name, buf, want in (('layernorm', out, want_ln), ('geglu', out2, want_gg)):
+        hi, lo8, hi8 = [t.double() for t in G.decode_act_planes_f8(buf.cpu(), want.shape)]
+        m = max(1.0, want.abs().max().item())
+        e_hi, e_sum = (hi - want).abs().max().item(), (hi + lo8 - want).abs().max().item()
+        e_h8 = ((hi8 - hi).abs() / hi.abs().clamp_min(2.0 ** -8)).max().item()
+        print(f'{name} f8 image: |hi - y| {e_hi:.2e}  |hi + lo8 - y| {e_sum:.2e}  rel |hi8 - hi| {e_h8:.3f}')
+        assert e_hi < 6e-4 * m and e_sum < 4e-5 * m and e_h8 < 0.07

@@ -487,6 +487,30 @@ def test_ldm_cfg_denoiser_parity_f8_mode():
         assert err < TOL * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.skipif(os.environ.get('DSB_LDM_F8_LINEAR_TESTS') != '1', reason='opt-in until it has a green run on hardware')
+def test_ldm_cfg_denoiser_parity_f8_linear():
+    """fp16f8 with f8_linear=True: ResBlock convolutions and the single-consumer transformer linears in the f8 GEMM mode."""
+    from oracle import edm_oracle as O
+    from oracle import ldm_oracle as LO
+    from diff_sampler_b200.ldm_net import B200LDMNet
+    P, cfg = LO.make_params('tiny_ldm')
+    on = LO.OracleCFGNet(P, cfg, guidance_rate=7.5)
+    nat = B200LDMNet(P, img_resolution=cfg['img_resolution'], img_channels=cfg['in_channels'], num_heads=cfg['num_heads'], guidance_rate=7.5,
+                     precision='fp16f8', device=_dev(), f8_linear=True)
+    assert nat.f8_linear
+    B, R = 3, cfg['img_resolution']
+    x0 = O.stacked_randn(range(B), (4, R, R))
+    g = torch.Generator().manual_seed(6)
+    c = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    uc = torch.randn(B, 77, cfg['context_dim'], generator=g)
+    for sigma in (10.0, 0.5):
+        ref = on(x0 * sigma, torch.tensor([sigma]), condition=c, unconditional_condition=uc)
+        got = nat((x0 * sigma).to(_dev()), torch.tensor([sigma], device=_dev()), condition=c.to(_dev()), unconditional_condition=uc.to(_dev())).cpu()
+        err = (got - ref).abs().max().item()
+        print(f'ldm fp16f8 + f8_linear sigma={sigma}: err {err:.3e} (max|D| {ref.abs().max().item():.1f})')
+        assert err < TOL * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize('guidance', [7.5, 1.0])
 def test_ldm_cfg_denoiser_parity(guidance):
     from oracle import edm_oracle as O

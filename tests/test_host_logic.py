@@ -143,23 +143,73 @@ def test_f8_operand_packing_and_plan():
             n_fmt += 1
     blocks = spec.enc + spec.dec
     assert n_f8 == 2 * len(blocks) + 1 and n_fmt == 2 * len(blocks) + 1          # block convolutions + the head conv
+    last_fmt = {}
+    for i in range(pl.n_ops):                       # every GEMM reads its operands in the format their last producer wrote
+        o = pl.ops_array[i]
+        if o.type == S.DS_OP_GN_APPLY:
+            for ptr in (o.u.gn_apply.out_act, o.u.gn_apply.out_raw):
+                if ptr:
+                    last_fmt[ptr] = o.u.gn_apply.fmt
+        elif o.type == S.DS_OP_GEMM:
+            g = o.u.gemm
+            for ptr, used in ((g.a_ptr, True), (g.a2_ptr, bool(g.a2_c)), (g.b_ptr, g.a_mode == 1)):
+                if used and ptr in last_fmt:
+                    assert last_fmt[ptr] == ((1 if g.f8 & 1 else 0) if ptr != g.b_ptr else 0), (i, o.tag)
 
 
-@pytest.mark.parametrize('f8', [False, True])
-def test_ldm_plan_lowering(f8):
-    """The latent-diffusion eps-net lowers on the host (no GPU) in both precisions; f8 touches exactly the ResBlock convolutions."""
+@pytest.mark.parametrize('f8,f8_linear', [(False, False), (True, False), (True, True)])
+def test_ldm_plan_lowering(f8, f8_linear):
+    """The latent-diffusion eps-net lowers on the host (no GPU) in every precision; f8 touches exactly the ResBlock convolutions, and the
+    opt-in f8_linear additionally the five single-consumer linears of every transformer block (with their producers' output format)."""
     from diff_sampler_b200 import ldm_plan
     from oracle import ldm_oracle as LO
     P, cfg = LO.make_params('tiny_ldm')
     st = ldm_plan.ldm_structure(P, cfg['num_heads'])
-    wb, info = ldm_plan.pack_ldm_weights(st, P, f8=f8)
-    pl = ldm_plan.compile_ldm_plan(st, wb, info, 2, 4, 1, cfg['img_resolution'], npass=3, f8=f8)
-    n_res = sum(1 for _, ls in st['inp'] + st['mid'] + st['out'] for L in ls if L[0] == 'res')
-    n_f8 = sum(1 for i in range(pl.n_ops) if pl.ops_array[i].type == S.DS_OP_GEMM and pl.ops_array[i].u.gemm.f8)
-    n_fmt = sum(1 for i in range(pl.n_ops) if pl.ops_array[i].type == S.DS_OP_GN_APPLY and pl.ops_array[i].u.gn_apply.fmt == 1)
-    assert pl.n_ops > 50 and pl.arena_bytes > 0 and n_res > 0
-    assert (n_f8, n_fmt) == ((2 * n_res, 2 * n_res) if f8 else (0, 0))
-    assert len(info['f8_shift']) == (2 * n_res if f8 else 0)
+    wb, info = ldm_plan.pack_ldm_weights(st, P, f8=f8, f8_linear=f8_linear)
+    pl = ldm_plan.compile_ldm_plan(st, wb, info, 2, 4, 1, cfg['img_resolution'], npass=3, f8=f8, f8_linear=f8_linear)
+    layers = [L for _, ls in st['inp'] + st['mid'] + st['out'] for L in ls]
+    n_res = sum(1 for L in layers if L[0] == 'res')
+    n_att = sum(1 for L in layers if L[0] == 'attn')
+    ops = [pl.ops_array[i] for i in range(pl.n_ops)]
+    n_f8 = sum(1 for o in ops if o.type == S.DS_OP_GEMM and o.u.gemm.f8)
+    n_fmt = sum(1 for o in ops if o.type == S.DS_OP_GN_APPLY and o.u.gn_apply.fmt == 1)
+    n_ln = sum(1 for o in ops if o.type == S.DS_OP_LAYERNORM and o.u.layernorm.fmt == 1)
+    n_gg = sum(1 for o in ops if o.type == S.DS_OP_GEGLU and o.u.geglu.fmt == 1)
+    assert pl.n_ops > 50 and pl.arena_bytes > 0 and n_res > 0 and n_att > 0
+    lin = 1 if f8_linear else 0
+    assert n_f8 == (2 * n_res if f8 else 0) + 5 * n_att * lin
+    assert n_fmt == (2 * n_res if f8 else 0) + 2 * n_att * lin           # + norm -> proj_in and the cast before proj_out
+    assert (n_ln, n_gg) == (2 * n_att * lin, n_att * lin)                # norm2, norm3; norm1 feeds both an A and a B operand and stays fp16
+    assert len(info['f8_shift']) == (2 * n_res if f8 else 0) + 5 * n_att * lin
+    # every f8 GEMM reads an operand some producer wrote in the f8 image: same buffer reference
+    f8_inputs = {o.u.gemm.a_ptr for o in ops if o.type == S.DS_OP_GEMM and o.u.gemm.f8} | \
+                {o.u.gemm.a2_ptr for o in ops if o.type == S.DS_OP_GEMM and o.u.gemm.f8 and o.u.gemm.a2_c}
+    f8_outputs = {o.u.gn_apply.out_act for o in ops if o.type == S.DS_OP_GN_APPLY and o.u.gn_apply.fmt == 1} | \
+                 {o.u.gn_apply.out_raw for o in ops if o.type == S.DS_OP_GN_APPLY and o.u.gn_apply.fmt == 1} | \
+                 {o.u.layernorm.out for o in ops if o.type == S.DS_OP_LAYERNORM and o.u.layernorm.fmt == 1} | \
+                 {o.u.geglu.out for o in ops if o.type == S.DS_OP_GEGLU and o.u.geglu.fmt == 1}
+    assert f8_inputs <= f8_outputs
+    # order-aware: scratch buffers ('act', 'ln', ...) are reused with different formats, so each GEMM must find its A operand (and the
+    # K-appended skip operand) in the format of the LAST producer that wrote that buffer before it
+    last_fmt = {}
+    for o in ops:
+        if o.type == S.DS_OP_GN_APPLY:
+            for ptr in (o.u.gn_apply.out_act, o.u.gn_apply.out_raw):
+                if ptr:
+                    last_fmt[ptr] = o.u.gn_apply.fmt
+        elif o.type == S.DS_OP_LAYERNORM:
+            last_fmt[o.u.layernorm.out] = o.u.layernorm.fmt
+        elif o.type == S.DS_OP_GEGLU:
+            last_fmt[o.u.geglu.out] = o.u.geglu.fmt
+        elif o.type == S.DS_OP_GEMM:
+            g = o.u.gemm
+            want = 1 if g.f8 & 1 else 0
+            if g.a_ptr in last_fmt:
+                assert last_fmt[g.a_ptr] == want, (o.tag, 'A operand format')
+            if g.a2_c and g.a2_ptr in last_fmt:
+                assert last_fmt[g.a2_ptr] == want, (o.tag, 'skip operand format')
+            if g.a_mode == 1 and g.b_ptr in last_fmt:
+                assert last_fmt[g.b_ptr] == 0, (o.tag, 'B-side activations are always fp16 hi/lo planes')
 
 
 def test_schedules_and_deis_tables_match_reference_golden():
