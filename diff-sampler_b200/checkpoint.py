@@ -30,6 +30,7 @@ class CheckpointError(RuntimeError):
 class _Record:
     """Stand-in for an unpickled object: keeps the class path and whatever state pickle hands over."""
     _path = '?'
+    state = {}              # pickle creates instances with cls.__new__ (no __init__): objects without a BUILD state read this default
 
     def __init__(self, *args, **kwargs):
         self.args, self.kwargs, self.state = args, kwargs, {}
