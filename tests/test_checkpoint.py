@@ -62,3 +62,28 @@ def test_nothing_outside_the_snapshot_vocabulary_is_unpickled():
         CK.load_edm_pickle(io.BytesIO(blob))
     with pytest.raises(CK.CheckpointError):
         CK.load_edm_pickle(io.BytesIO(b'not a pickle at all'))
+
+
+def test_torch1_era_tensor_records_are_readable():
+    """The published EDM snapshots were written by torch 1.12: tensors appear as `_rebuild_tensor_v2(storage, ...)` whose storage is
+    `torch.storage._load_from_bytes(<legacy non-zip torch.save bytes>)`.  The restricted unpickler resolves exactly that chain (with the
+    tensor-only loader inside)."""
+    import collections
+    import warnings
+    t = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        b = io.BytesIO()
+        torch.save(t.storage(), b, _use_new_zipfile_serialization=False)
+    raw = b.getvalue()
+
+    class Storage:
+        def __reduce__(self):
+            return (torch.storage._load_from_bytes, (raw,))
+
+    class Tensor:
+        def __reduce__(self):
+            return (torch._utils._rebuild_tensor_v2, (Storage(), 0, (3, 4), (4, 1), False, collections.OrderedDict()))
+
+    obj = CK._Unpickler(io.BytesIO(pickle.dumps({'w': Tensor()}))).load()
+    assert torch.equal(obj['w'], t)
