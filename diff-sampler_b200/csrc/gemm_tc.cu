@@ -510,11 +510,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 const int pm = tile / p.n_tiles;
                 const int nt = tile - pm * p.n_tiles;
                 const int mt = 2 * pm + rank;                             // may be one past the last tile: TMA zero-fills, the epilogue masks
+                // 128 consecutive NHWC pixels: whole image rows (W <= 128, box (64, W, 128/W.., ..)) or a 128-pixel segment of one row
+                // (W a multiple of 128 > 128, box (64, 128, 1, 1): the first-stage decoder's 256- and 512-wide layers)
                 const int HW = p.conv_H * p.conv_W;
                 const int p0 = mt * 128;
                 const int an0 = p0 / HW;
-                const int ah0 = (p0 - an0 * HW) / p.conv_W;
-                const int aw0 = 0;
+                const int rem = p0 - an0 * HW;
+                const int ah0 = rem / p.conv_W;
+                const int aw0 = rem - ah0 * p.conv_W;
                 const int b_row = nt * p.BN + rank * half_bn;
                 for (int it = 0; it < n_iters; ++it) {
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
@@ -748,6 +751,8 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     }
     for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = d->tap_dh[t]; kp->tap_dw[t] = d->tap_dw[t]; kp->tap_cb[t] = d->tap_cb[t]; }
     if (d->taps != 1 && d->taps != 9) return -15;
+    // image rows wider than one M tile are only handled by the pair kernel's tile -> (w, h, n) mapping
+    if (d->a_mode == 0 && d->conv_W > 128 && !((d->f8 & 2) && d->BN % 32 == 0 && d->num_z == 1 && d->conv_W % 128 == 0)) return -13;
     // fused statistics: whole 32-row slabs (row validity is then warp-uniform), whole channel quads, one z slice, fp32 output
     if (d->st_quads && (d->num_z != 1 || d->m_valid % 32 != 0 || d->n_valid % 4 != 0 || d->edm_out != 0)) return -14;
     int stage_bytes = kATileBytes + d->BN * 128;
@@ -755,7 +760,7 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     // whole 32-row halves; everything else keeps the single-CTA kernel
     static const int pair_env = [] { const char* e = getenv("DSB_GEMM_2CTA"); return e ? atoi(e) : 0; }();
     const bool pair_forced = (d->f8 & 2) != 0;          // bit 1 of ds_gemm_desc.f8: request the pair kernel for this launch (tests, A/B)
-    if ((pair_forced || (pair_env && d->m_tiles >= 4 * 148)) && d->a_mode == 0 && d->num_z == 1 && d->BN % 32 == 0 && d->BN >= 64 &&
+    if ((pair_forced || (pair_env && d->m_tiles >= 4 * 148 && d->BN >= 64)) && d->a_mode == 0 && d->num_z == 1 && d->BN % 32 == 0 &&
         all_tap_cb_zero(d)) {
         int32_t hbox[3] = {64, d->BN / 2, 1};
         if (encode_map(&kp->tmBh, d->b_ptr, 3, d->b_dims, d->b_strides, hbox)) return -30;

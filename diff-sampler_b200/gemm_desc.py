@@ -55,8 +55,12 @@ def split_planes_rows(n_valid, bn):
 
 
 def conv_box(H, W):
-    """TMA box (64, bw, bh, bn) covering 128 consecutive NHWC pixels."""
-    assert W <= 128 and 128 % W == 0, f'unsupported width {W}'
+    """TMA box (64, bw, bh, bn) covering 128 consecutive NHWC pixels: whole rows for W <= 128, a 128-pixel row segment for wider
+    images (W a multiple of 128; only the CTA-pair kernel maps tiles to such segments -- conv_gemm requests it)."""
+    if W > 128:
+        assert W % 128 == 0, f'unsupported width {W}'
+        return 128, 1, 1
+    assert 128 % W == 0, f'unsupported width {W}'
     bw = W
     bh = min(H, 128 // W)
     bn = 128 // (bw * bh)
@@ -81,6 +85,11 @@ def conv_gemm(a_ptr, Bn, H, W, C, w_ptr, Cout, *, taps=9, npass=3, a_planes=2, w
     d = S.GemmDesc()
     bw, bh, bnn = conv_box(H, W)
     BN, n_tiles = (bn, -(-Cout // bn)) if bn else fill_bn(Cout, -(-(Bn * H * W) // 128))
+    if W > 128:                          # wide rows: pair kernel, whose N tile must split into two 16-row halves
+        pair = True
+        if BN % 32:
+            BN = -(-BN // 32) * 32
+            n_tiles = -(-Cout // BN)
     pbn, ptiles = pick_bn(Cout)
     cout_pad = pbn * ptiles              # rows of the packed weight (pack_conv_weight); tiles past it read TMA zero fill
     ktot = taps * C + C2

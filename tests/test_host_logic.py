@@ -212,6 +212,38 @@ def test_ldm_plan_lowering(f8, f8_linear):
                 assert last_fmt[g.b_ptr] == 0, (o.tag, 'B-side activations are always fp16 hi/lo planes')
 
 
+@pytest.mark.parametrize('name,R,B', [('tiny_vae', 8, 2), ('wide_vae', 64, 2), ('sd_vae', 64, 1)])
+def test_vae_decoder_plan_lowering(name, R, B):
+    """First-stage decoder (vae_plan.py): the structure read back from state_dict names equals the oracle's module list (which is pinned
+    to the reference Decoder), every module is lowered once, rows wider than one M tile go to the pair kernel with a splittable N tile."""
+    from diff_sampler_b200 import vae_plan
+    from oracle import vae_oracle as VO
+    P, cfg = VO.make_params(name, seed=0)
+    mods, meta = vae_plan.vae_structure(P)
+    omods, c_end = VO.structure(cfg)
+    assert [tuple(m) for m in mods] == [tuple(m) for m in omods] and meta['c_end'] == c_end
+    assert meta['upscale'] == 2 ** (len(cfg['ch_mult']) - 1) and meta['out_ch'] == cfg['out_ch']
+    wb = vae_plan.pack_vae_weights(mods, meta, P)
+    pl = vae_plan.compile_vae_plan(mods, meta, wb, B, R)
+    ops = [pl.ops_array[i] for i in range(pl.n_ops)]
+    gemms = [o.u.gemm for o in ops if o.type == S.DS_OP_GEMM]
+    n_res = sum(1 for m in mods if m[0] == 'res')
+    n_att = sum(1 for m in mods if m[0] == 'attn')
+    n_up = sum(1 for m in mods if m[0] == 'up')
+    assert len(gemms) == 2 + 2 * n_res + 5 * n_att + n_up + 1            # post_quant + conv_in, 2 per block, qk/v/S/PV/proj, up convs, conv_out
+    assert sum(1 for o in ops if o.type == S.DS_OP_GN_STATS) == 2 * n_res + n_att + 1
+    assert pl.meta['out_res'] == R * meta['upscale']
+    for g in gemms:
+        wide = g.a_mode == 0 and g.conv_W > 128
+        assert bool(g.f8 & 2) == wide                                    # pair kernel exactly for the wide rows
+        if wide:
+            assert g.conv_W % 128 == 0 and tuple(g.a_box) == (64, 128, 1, 1) and g.BN % 32 == 0 and g.num_z == 1
+        assert g.m_tiles * 128 >= g.m_valid and g.n_tiles * g.BN >= g.n_valid
+    last = gemms[-1]
+    assert last.edm_out == 2 and last.edm_C == cfg['out_ch'] and last.n_valid == cfg['out_ch']
+    assert gemms[0].taps == 1 and gemms[0].ldo == 64 and gemms[0].n_valid == cfg['z_channels'] and gemms[1].a_ptr == gemms[0].out_h16
+
+
 def test_schedules_and_deis_tables_match_reference_golden():
     d = np.load(GOLD)
     for st in ('polynomial', 'logsnr', 'time_uniform'):

@@ -188,3 +188,17 @@ def test_ldm_oracle_matches_reference():
         out = SO.sample(net, x, 'dpm_pp', condition=c, unconditional_condition=uc, num_steps=5, sigma_min=net.sigma_min,
                         sigma_max=net.sigma_max, schedule_type='discrete', schedule_rho=1, max_order=2, predict_x0=False).numpy()
         assert np.abs(out - d['ldm/tiny_ldm/sample_dpmpp']).max() <= 1e-5 * np.abs(d['ldm/tiny_ldm/sample_dpmpp']).max()
+
+
+def test_vae_oracle_matches_reference():
+    """First-stage decoder restatement (oracle/vae_oracle.py) vs the real reference Decoder run in this container (oracle/gen_vae_golden.py)."""
+    from oracle import vae_oracle as VO
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_vae.npz'))
+    for name in ('tiny_vae', 'wide_vae'):
+        P, cfg = VO.make_params(name, seed=0)
+        z = torch.from_numpy(d[f'vae/{name}/z'])
+        with torch.no_grad():
+            x = VO.decode(P, cfg, z).numpy()
+        ref = d[f'vae/{name}/x']
+        assert x.shape == ref.shape
+        assert np.abs(x - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), np.abs(x - ref).max()

@@ -1,0 +1,82 @@
+"""Plans as data, checked without a GPU: the CPU plan interpreter (oracle/plan_interp.py) executes what the plan compilers emit --
+arena offsets, operand planes and formats, packed weights and their scales, tap tables, epilogue options -- and the result must agree
+with the network oracles (which are pinned to the real reference).  The EDM cases double as the interpreter's own validation: those
+plans are the ones the B200 runs green in tests/test_gpu_parity.py."""
+import pytest
+import torch
+
+from diff_sampler_b200 import _cstructs as S
+from diff_sampler_b200 import edm_nets, ldm_plan, plan as planner, vae_plan
+from oracle import edm_oracle as O
+from oracle import ldm_oracle as LO
+from oracle import plan_interp as PI
+from oracle import vae_oracle as VO
+
+TOL = {False: 3e-5, True: 3e-4}          # fp16 hi/lo planes carry ~2^-22; the f8 mode adds ~3 % of the single-pass fp16 error
+
+
+@pytest.mark.parametrize('name,f8', [('tiny_song', False), ('tiny_adm', False), ('tiny_song4', False), ('tiny_song', True), ('tiny_adm', True)])
+def test_edm_plan_on_the_cpu_interpreter(name, f8):
+    P, St = O.make_net(name, seed=0, dezero=True)
+    spec = edm_nets.spec_from_params(P, St['img_resolution'], St['img_channels'], St['label_dim'])
+    spec.sigma_data = 0.5
+    wb, info = planner.pack_weights(spec, P, f8=f8)
+    B = 2
+    pl = planner.compile_plan(spec, wb, info, B, 1, B if spec.label_dim else 0, npass=3, f8=f8)
+    x = (O.stacked_randn(range(B), (3, St['img_resolution'], St['img_resolution'])) * 2.0).contiguous()
+    sig = torch.tensor([2.0])
+    lab = torch.eye(spec.label_dim)[torch.arange(B) % spec.label_dim].contiguous() if spec.label_dim else None
+    D = torch.zeros_like(x)
+    bott = torch.zeros(B, 64)
+    PI.run_plan(pl, wb.bytes(), {S.DS_IO_X: x, S.DS_IO_D: D, S.DS_IO_SIGMA: sig, S.DS_IO_LABELS: lab, S.DS_IO_BOTTLENECK: bott})
+    ref = O.OracleNet(P, St)(x, sig[0], class_labels=lab)
+    err = (D - ref).abs().max().item()
+    print(f'{name} f8={f8}: interpreter vs oracle {err:.3e}')
+    assert err < TOL[f8] * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('mode', ['fp16x3', 'f8', 'f8_linear'])
+def test_ldm_plan_on_the_cpu_interpreter(mode):
+    f8, f8l = mode != 'fp16x3', mode == 'f8_linear'
+    P, cfg = LO.make_params('tiny_ldm')
+    st = ldm_plan.ldm_structure(P, cfg['num_heads'])
+    wb, info = ldm_plan.pack_ldm_weights(st, P, f8=f8, f8_linear=f8l)
+    B = Bt = 2
+    R = cfg['img_resolution']
+    pl = ldm_plan.compile_ldm_plan(st, wb, info, B, Bt, 1, R, npass=3, f8=f8, f8_linear=f8l)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, cfg['in_channels'], R, R, generator=g).contiguous()
+    ctx = torch.randn(Bt, 77, cfg['context_dim'], generator=g).contiguous()
+    t = torch.tensor([417.0])
+    c_in = 0.37
+    eps = torch.zeros(Bt, cfg['in_channels'], R, R)
+    io = {S.DS_IO_X: x, S.DS_IO_D: eps, S.DS_IO_SIGMA: t, S.DS_IO_LABELS: torch.tensor([[0.0, 0.0, c_in, 0.0]]), S.DS_IO_BOTTLENECK: torch.zeros(Bt, 64),
+          S.DS_IO_CTX: ctx}
+    PI.run_plan(pl, wb.bytes(), io)
+    with torch.no_grad():
+        ref = LO.unet_forward(P, cfg, x * c_in, t.expand(Bt), ctx)
+    err = (eps - ref).abs().max().item()
+    print(f'tiny_ldm {mode}: interpreter vs oracle {err:.3e}')
+    assert err < TOL[f8] * max(1.0, ref.abs().max().item())
+
+
+def test_vae_decoder_plan_on_the_cpu_interpreter():
+    """The first-stage decoder lowering (vae_plan.py) has not run on hardware yet; as data it reproduces the oracle module by module."""
+    P, cfg = VO.make_params('tiny_vae', seed=0)
+    mods, meta = vae_plan.vae_structure(P)
+    wb = vae_plan.pack_vae_weights(mods, meta, P)
+    B, R = 2, 8
+    pl = vae_plan.compile_vae_plan(mods, meta, wb, B, R)
+    g = torch.Generator().manual_seed(3)
+    z = (torch.randn(B, cfg['z_channels'], R, R, generator=g) * cfg['scale_factor'] * 1.3).contiguous()
+    out = torch.zeros(B, meta['out_ch'], R * meta['upscale'], R * meta['upscale'])
+    io = {S.DS_IO_X: z, S.DS_IO_D: out, S.DS_IO_LABELS: torch.tensor([[0.0, 0.0, 1.0 / cfg['scale_factor'], 0.0]])}
+    mem = PI.run_plan(pl, wb.bytes(), io)
+    taps = {}
+    with torch.no_grad():
+        ref = VO.decode(P, cfg, z, taps=taps)
+    for mname, t in taps.items():
+        n, c, h, w = t.shape
+        mine = PI.read_buffer(mem, pl, 'h:' + mname, (n, h, w, c)).permute(0, 3, 1, 2)
+        assert (mine - t).abs().max().item() < 3e-5 * max(1.0, t.abs().max().item()), mname
+    assert (out - ref).abs().max().item() < 3e-5
