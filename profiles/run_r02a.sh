@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of the next round: hardware contact for everything that is opt-in at the end of round 1, then the A/Bs that decide defaults.
+#   1. opt-in tests: CTA-pair kernel (incl. row-segment tiles), LayerNorm/GEGLU f8 images + LDM f8_linear parity, first-stage decoder parity
+#   2. default bench, and the same with the pair kernel on all large convolutions (sustained power-capped A/B)
+#   3. SD-v1.5 config: fp16x3 vs fp16f8 vs fp16f8 + f8_linear
+# usage (repo root on the GPU box):  bash profiles/run_r02a.sh
+O=gpurun_out/r02a
+mkdir -p $O
+DSB_PAIR_TESTS=1 DSB_LDM_F8_LINEAR_TESTS=1 DSB_VAE_TESTS=1 timeout 600 python -m pytest tests -m gpu -q -s \
+    -k "pair_kernel or f8_image or f8_linear or vae_decoder" > $O/tests_optin.log 2>&1; echo "tests_optin rc=$?" >> $O/status.txt
+timeout 360 python bench.py --no_cpu_baseline > $O/bench_default.json 2> $O/bench_default.err; echo "bench_default rc=$?" >> $O/status.txt
+DSB_GEMM_2CTA=1 timeout 360 python bench.py --no_cpu_baseline > $O/bench_default_pair.json 2> $O/bench_default_pair.err; echo "bench_pair rc=$?" >> $O/status.txt
+for mode in "fp16x3 0" "fp16f8 0" "fp16f8 1"; do
+    set -- $mode
+    DSB_LDM_F8_LINEAR=$2 timeout 600 python bench.py --net sd15 --solver amed_dpm_pp --num_steps 4 --batch 8 --precision $1 --no_cpu_baseline \
+        > $O/bench_sd15_$1_lin$2.json 2> $O/bench_sd15_$1_lin$2.err; echo "bench_sd15 $1 f8_linear=$2 rc=$?" >> $O/status.txt
+done
+cat $O/status.txt
+grep -E "passed|failed|pair conv|f8 image|f8_linear|image err" $O/tests_optin.log | head -40
+for f in $O/bench_*.json; do echo "$f: $(python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['value'], d.get('precision'), d.get('forward_breakdown_ms'))" 2>&1 | cut -c1-300)"; done
