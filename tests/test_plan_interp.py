@@ -35,6 +35,29 @@ def test_edm_plan_on_the_cpu_interpreter(name, f8):
     assert err < TOL[f8] * max(1.0, ref.abs().max().item())
 
 
+def test_edm_plan_variants_per_sample_sigma_and_broadcast_label():
+    """The (batch, #sigma, #labels) plan variants: per-sample sigma (AMED evaluates the net at scale_time * t_mid per sample) and one
+    class label broadcast to the batch (networks_edm.py:485)."""
+    P, St = O.make_net('tiny_adm', seed=0, dezero=True)
+    spec = edm_nets.spec_from_params(P, St['img_resolution'], St['img_channels'], St['label_dim'])
+    spec.sigma_data = 0.5
+    wb, info = planner.pack_weights(spec, P)
+    B = 3
+    x0 = O.stacked_randn(range(B), (3, St['img_resolution'], St['img_resolution']))
+    on = O.OracleNet(P, St)
+    for nsig, nlab in ((B, B), (1, 1), (B, 1)):
+        pl = planner.compile_plan(spec, wb, info, B, nsig, nlab, npass=3)
+        sig = torch.tensor([3.0, 0.4, 11.0])[:nsig].contiguous()
+        x = (x0 * (sig[:, None, None, None] if nsig > 1 else sig[0])).contiguous()
+        lab = torch.eye(spec.label_dim)[torch.tensor([1, 4, 7])[:nlab]].contiguous()
+        D = torch.zeros_like(x)
+        PI.run_plan(pl, wb.bytes(), {S.DS_IO_X: x, S.DS_IO_D: D, S.DS_IO_SIGMA: sig, S.DS_IO_LABELS: lab, S.DS_IO_BOTTLENECK: torch.zeros(B, 64)})
+        ref = on(x, sig if nsig > 1 else sig[0], class_labels=lab if nlab > 1 else lab.expand(B, -1))
+        err = (D - ref).abs().max().item()
+        print(f'tiny_adm nsig={nsig} nlab={nlab}: {err:.3e}')
+        assert err < TOL[False] * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize('mode', ['fp16x3', 'f8', 'f8_linear'])
 def test_ldm_plan_on_the_cpu_interpreter(mode):
     f8, f8l = mode != 'fp16x3', mode == 'f8_linear'
