@@ -40,6 +40,7 @@ def parse():
     ap.add_argument('--precision', default='auto', choices=['auto', 'fp16x3', 'fp16', 'fp16f8'],
                     help="fp16x3: 3 fp16 MMAs per product; fp16f8: fp16 hi x hi + two e4m3 correction MMAs (block / head convolutions); fp16: single "
                          "pass; auto (default): the fastest mode whose final images stay within the 1e-3 contract for the named net (PRECISION_FOR)")
+    ap.add_argument('--f8_min_channels', type=int, default=0, help='fp16f8 only: blocks with fewer input or output channels stay fp16x3 (0 = all blocks in f8)')
     ap.add_argument('--cpu_batch', type=int, default=8, help='batch of the bounded CPU-baseline sample')
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--fuse_stats', type=int, default=1, help='1 (default): GroupNorm statistics from the GEMM epilogues; 0: separate gn_stats pass')
@@ -197,7 +198,8 @@ def main():
     if args.net == 'sd15':
         net, sampler, kw = build_sd15(args, dev, B, gen)
     else:
-        net = B200Net.from_config(args.net, seed=0, dezero=True, precision=args.precision, device=dev, fuse_stats=bool(args.fuse_stats))
+        net = B200Net.from_config(args.net, seed=0, dezero=True, precision=args.precision, device=dev, fuse_stats=bool(args.fuse_stats),
+                                  f8_min_channels=args.f8_min_channels)
         sampler = getattr(solvers, args.solver + '_sampler')
     shape = (B, net.img_channels, net.img_resolution, net.img_resolution)
     latents = torch.randn(shape, generator=gen, device=dev)
@@ -278,7 +280,7 @@ def main():
                 dtype='fp16 operands, fp32 accumulate' + {'fp16x3': ' (split-precision: 3 tcgen05 MMAs per product)',
                                                            'fp16f8': ' (split-precision: fp16 hi x hi + two e4m3 correction MMAs per product)'}.get(args.precision, ''),
                 data='synthetic', config=config, gpu_launches=launches, clocks=clk, precision=args.precision,
-                precision_requested=args.precision_requested)
+                precision_requested=args.precision_requested, f8_min_channels=args.f8_min_channels)
     if e2e:
         line['e2e'] = e2e
     if gathered:

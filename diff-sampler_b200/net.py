@@ -30,7 +30,7 @@ def default_precision():
 
 class B200Net:
     def __init__(self, params, img_resolution, img_channels, label_dim=0, sigma_min=0.002, sigma_max=80.0, sigma_data=0.5,
-                 precision=None, device='cuda', fuse_stats=True, flash_attn=True):
+                 precision=None, device='cuda', fuse_stats=True, flash_attn=True, f8_min_channels=None):
         self.device = torch.device(device)
         precision = precision or default_precision()
         if self.device.type != 'cuda':
@@ -41,11 +41,15 @@ class B200Net:
         self.precision = precision
         self.npass = PRECISIONS[precision]
         self.f8 = precision == 'fp16f8'
+        if f8_min_channels is None:
+            import os
+            f8_min_channels = int(os.environ.get('DSB_F8_MIN_CHANNELS', '0'))
+        self.f8_min_channels = int(f8_min_channels)          # fp16f8 only: blocks narrower than this stay fp16x3 (plan.pack_weights)
         self.fuse_stats = bool(fuse_stats)
         self.flash_attn = bool(flash_attn)
         self.spec = edm_nets.spec_from_params(params, img_resolution, img_channels, label_dim)
         self.spec.sigma_data = sigma_data
-        self.wb, self.winfo = planner.pack_weights(self.spec, params, f8=self.f8)
+        self.wb, self.winfo = planner.pack_weights(self.spec, params, f8=self.f8, f8_min_channels=self.f8_min_channels)
         blob = self.wb.bytes()
         self._wh = C.c_void_p()
         with torch.cuda.device(self.device):

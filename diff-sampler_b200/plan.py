@@ -62,10 +62,12 @@ def _qkv_split(w, b, heads):
     return torch.cat([w2[qi], w2[ki]]), torch.cat([b[qi], b[ki]]), w2[vi], b[vi]
 
 
-def pack_weights(spec, params, f8=False):
+def pack_weights(spec, params, f8=False, f8_min_channels=0):
     """Everything the kernels read that does not depend on the batch size.  f8=True packs the block convolutions (conv0, conv1 +
     skip) and the head conv in the fp16 + 2 x e4m3 operand layout of the f8 GEMM mode (csrc/ops.h); everything else keeps fp16 hi/lo
-    planes (the attention GEMMs share their operand planes, the stem conv reads the 3-channel input)."""
+    planes (the attention GEMMs share their operand planes, the stem conv reads the 3-channel input).
+    f8_min_channels > 0 keeps blocks with fewer input or output channels in fp16x3: the narrow, high-resolution levels average the e4m3
+    rounding over the fewest terms and dominate the f8 error (FFHQ-64: the 128-channel 64x64 levels, tests/study_fp8_corrections.py)."""
     pf = spec.prefix
     P = lambda k: params[pf + k].detach().float().cpu()
     has = lambda k: (pf + k) in params
@@ -89,7 +91,8 @@ def pack_weights(spec, params, f8=False):
         n = b.name
         wb.add(n + '.norm0:g', P(n + '.norm0.weight'))
         wb.add(n + '.norm0:b', P(n + '.norm0.bias'))
-        add_conv(n + '.conv0', P(n + '.conv0.weight'), bias=P(n + '.conv0.bias'), as_f8=f8)
+        blk_f8 = f8 and min(b.cin, b.cout) >= f8_min_channels
+        add_conv(n + '.conv0', P(n + '.conv0.weight'), bias=P(n + '.conv0.bias'), as_f8=blk_f8)
         wb.add(n + '.norm1:g', P(n + '.norm1.weight'))
         wb.add(n + '.norm1:b', P(n + '.norm1.bias'))
         bias1 = P(n + '.conv1.bias')
@@ -97,7 +100,7 @@ def pack_weights(spec, params, f8=False):
         if b.skip == 'conv':
             skip_w = P(n + '.skip.weight')
             bias1 = bias1 + P(n + '.skip.bias')
-        add_conv(n + '.conv1', P(n + '.conv1.weight'), skip_w, bias=bias1, as_f8=f8)
+        add_conv(n + '.conv1', P(n + '.conv1.weight'), skip_w, bias=bias1, as_f8=blk_f8)
         aff_w.append(P(n + '.affine.weight'))
         aff_b.append(P(n + '.affine.bias'))
         if b.heads:
@@ -121,7 +124,8 @@ def pack_weights(spec, params, f8=False):
     wb.add(spec.head_norm + ':g', P(spec.head_norm + '.weight'))
     wb.add(spec.head_norm + ':b', P(spec.head_norm + '.bias'))
     # the head conv has 3 output channels: its cost is reading the A operand, which the f8 layout cuts from 3 to 2 tile loads per 64 channels
-    add_conv(spec.head_conv, P(spec.head_conv + '.weight'), bias=P(spec.head_conv + '.bias'), as_f8=f8)
+    add_conv(spec.head_conv, P(spec.head_conv + '.weight'), bias=P(spec.head_conv + '.bias'),
+             as_f8=f8 and P(spec.head_conv + '.weight').shape[1] >= f8_min_channels)
     return wb, info
 
 
@@ -168,10 +172,13 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
     packed with pack_weights(f8=True))."""
     assert nsig in (1, B) and nlab in (0, 1, B)
     assert not f8 or npass == 3
-    fmt = 1 if f8 else 0
+
+    def is_f8(key):
+        """This GEMM was packed for the f8 mode (pack_weights decides per block: f8_min_channels)."""
+        return f8 and 'f8_shift' in winfo[key]
 
     def f8_args(key):
-        return dict(f8=True, acc_scale=2.0 ** -winfo[key]['f8_shift']) if f8 else {}
+        return dict(f8=True, acc_scale=2.0 ** -winfo[key]['f8_shift']) if is_f8(key) else {}
     A = _Arena()
     ops = []        # list of (type, tag, builder(R) -> desc)
     F4, H2 = 4, 2
@@ -317,7 +324,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
         emit(lambda R: S.GnApplyDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, H=Hi, W=Hi, B=B, groups=_groups(cin), **stat_args(R, s0),
                                      gamma=W(n + '.norm0:g'), beta=W(n + '.norm0:b'), eps=b.eps, silu=1, ada=0, ada_stride=0,
                                      resample=resample, nplanes=npl, out_act=R('act'), out_raw=R('raw') if want_raw else 0,
-                                     out_raw_f32=R('rawf') if want_rawf else 0, fmt=fmt))
+                                     out_raw_f32=R('rawf') if want_rawf else 0, fmt=1 if is_f8(n + '.conv0') else 0))
         A.need('y', Mo * cout * F4)
         emit_producer('y', cout, Mo, lambda R: G.conv_gemm(R('act'), B, Ho, Ho, cin, W(n + '.conv0:w'), cout, taps=9, npass=npass, out_f32=R('y'),
                                                  bias=W(n + '.conv0:b'), rowvec=0 if b.adaptive_scale else R('aff', b.aff_off * F4),
@@ -328,7 +335,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
                                      gamma=W(n + '.norm1:g'), beta=W(n + '.norm1:b'), eps=b.eps, silu=1,
                                      ada=R('aff', b.aff_off * F4) if b.adaptive_scale else 0,
                                      ada_stride=aff_stride if b.adaptive_scale else 0, resample=0, nplanes=npl, out_act=R('act'),
-                                     out_raw=0, out_raw_f32=0, fmt=fmt))
+                                     out_raw=0, out_raw_f32=0, fmt=1 if is_f8(n + '.conv1') else 0))
         xout = A.need('x:' + n, Mo * cout * F4)
         mid = A.need('xmid', Mo * cout * F4) if b.heads else xout
         if b.skip == 'identity':
@@ -402,7 +409,8 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
     need_stats(sh, [(fin, fin_c)], HW0)
     emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=_groups(fin_c), **stat_args(R, sh),
                                  gamma=W(spec.head_norm + ':g'), beta=W(spec.head_norm + ':b'), eps=spec.head_eps, silu=1, ada=0,
-                                 ada_stride=0, resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0, fmt=fmt))
+                                 ada_stride=0, resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0,
+                                 fmt=1 if is_f8(spec.head_conv) else 0))
     emit(lambda R: G.conv_gemm(R('act'), B, R0, R0, fin_c, W(spec.head_conv + ':w'), spec.img_channels, taps=9, npass=npass,
                                bias=W(spec.head_conv + ':b'),
                                edm=(io(S.DS_IO_X), R('coef'), 4 if nsig > 1 else 0, spec.img_channels, io(S.DS_IO_D)),

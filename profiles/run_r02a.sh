@@ -15,6 +15,9 @@ for mode in "fp16x3 0" "fp16f8 0" "fp16f8 1"; do
     DSB_LDM_F8_LINEAR=$2 timeout 600 python bench.py --net sd15 --solver amed_dpm_pp --num_steps 4 --batch 8 --precision $1 --no_cpu_baseline \
         > $O/bench_sd15_$1_lin$2.json 2> $O/bench_sd15_$1_lin$2.err; echo "bench_sd15 $1 f8_linear=$2 rc=$?" >> $O/status.txt
 done
+# FFHQ: f8 only in the blocks with >= 256 channels (the 128-channel 64x64 levels dominate the f8 error; CPU study: -38 % on D)
+timeout 400 python bench.py --net ffhq --solver ipndm --num_steps 7 --batch 256 --precision fp16f8 --f8_min_channels 256 --no_cpu_baseline \
+    > $O/bench_ffhq_f8_min256.json 2> $O/bench_ffhq_f8_min256.err; echo "bench_ffhq f8>=256 rc=$?" >> $O/status.txt
 cat $O/status.txt
 grep -E "passed|failed|pair conv|f8 image|f8_linear|image err" $O/tests_optin.log | head -40
-for f in $O/bench_*.json; do echo "$f: $(python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['value'], d.get('precision'), d.get('forward_breakdown_ms'))" 2>&1 | cut -c1-300)"; done
+for f in $O/bench_*.json; do echo "$f: $(python -c "import json,sys; d=json.loads(open('$f').read().strip().splitlines()[-1]); print(d['value'], d.get('precision'), d.get('fp16x3_same_run'), d.get('forward_breakdown_ms'))" 2>&1 | cut -c1-300)"; done

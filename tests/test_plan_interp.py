@@ -35,6 +35,26 @@ def test_edm_plan_on_the_cpu_interpreter(name, f8):
     assert err < TOL[f8] * max(1.0, ref.abs().max().item())
 
 
+def test_edm_plan_mixed_precision_by_channel_count():
+    """fp16f8 with f8_min_channels: narrow blocks stay fp16x3, wide ones run in the f8 mode; each GEMM finds its operands in its own format."""
+    P, St = O.make_net('tiny_song', seed=0, dezero=True)
+    spec = edm_nets.spec_from_params(P, 16, 3, 0)
+    spec.sigma_data = 0.5
+    x = (O.stacked_randn(range(2), (3, 16, 16)) * 2.0).contiguous()
+    sig = torch.tensor([2.0])
+    ref = O.OracleNet(P, St)(x, sig[0])
+    counts, errs = [], []
+    for thr in (0, 128, 1000):
+        wb, info = planner.pack_weights(spec, P, f8=True, f8_min_channels=thr)
+        pl = planner.compile_plan(spec, wb, info, 2, 1, 0, npass=3, f8=True)
+        counts.append(sum(1 for i in range(pl.n_ops) if pl.ops_array[i].type == S.DS_OP_GEMM and pl.ops_array[i].u.gemm.f8))
+        D = torch.zeros_like(x)
+        PI.run_plan(pl, wb.bytes(), {S.DS_IO_X: x, S.DS_IO_D: D, S.DS_IO_SIGMA: sig, S.DS_IO_BOTTLENECK: torch.zeros(2, 64)})
+        errs.append((D - ref).abs().max().item())
+    assert counts[0] > counts[1] > counts[2] == 0
+    assert errs[0] < TOL[True] and errs[1] < errs[0] and errs[2] < TOL[False]
+
+
 def test_edm_plan_variants_per_sample_sigma_and_broadcast_label():
     """The (batch, #sigma, #labels) plan variants: per-sample sigma (AMED evaluates the net at scale_time * t_mid per sample) and one
     class label broadcast to the batch (networks_edm.py:485)."""
