@@ -9,6 +9,13 @@ num_steps=10 => NFE=18, batch 512 per GPU, synthetic Gaussian latents.  One "ste
 `value` = images/sec with latents resident in HBM; `e2e` = the same through the public API with pinned-host latents copied in
 and finished images copied back every step.  Scaling is weak: every rank samples its own 512-image batch, no collective on
 the sampling path; one NCCL all_gather of the uint8 images after the timed region (what FID consumes).
+
+At N=1 the same line also carries (rank 0, after the headline measurement; `--no_extras` skips them):
+  `configs`    BASELINE configs 3, 4 and 5 (FFHQ-64 iPNDM NFE=6, ImageNet-64 DPM-Solver++(2M) NFE=10, SD-v1.5 AMED-DPM++ NFE=5) measured the
+               same way (value, e2e, roofline, precision) at their per-GPU batch, >= 10 timed steps each;
+  `gpu_eager`  the reference's own GPU path -- eager PyTorch (cuDNN / cuBLAS: F.conv2d, F.group_norm, einsum attention), stated through the
+               functional nets of oracle/ (bit-identical to the reference modules on CPU, tests/golden) -- on the same B200, same batch / NFE:
+               the "beat PyTorch-eager on the same GPU" bar of SURVEY.md section 2.2.  A comparator, never the thing measured as `value`.
 """
 import argparse
 import json
@@ -45,10 +52,16 @@ def parse():
     ap.add_argument('--no_cpu_baseline', action='store_true')
     ap.add_argument('--fuse_stats', type=int, default=1, help='1 (default): GroupNorm statistics from the GEMM epilogues; 0: separate gn_stats pass')
     ap.add_argument('--no_extras', action='store_true', help='skip the roofline / e2e / fp16 legs (timing of the main leg is unchanged)')
+    ap.add_argument('--all_configs', type=int, default=1, help='1 (default, N=1 only): also measure BASELINE configs 3-5 into `configs`')
+    ap.add_argument('--config_steps', type=int, default=10, help='timed steps of each `configs` entry')
+    ap.add_argument('--gpu_eager', type=int, default=1, help='1 (default, N=1 only): time the eager-PyTorch GPU path of the same configs')
     args = ap.parse_args()
     args.precision_requested = args.precision
+    args.f8_min_channels_requested = args.f8_min_channels
     if args.precision == 'auto':
         args.precision = PRECISION_FOR.get(args.net, 'fp16x3')
+        if args.f8_min_channels == 0:
+            args.f8_min_channels = F8_MIN_CHANNELS_FOR.get(args.net, 0)
     return args
 
 
@@ -140,22 +153,89 @@ def cpu_reference_leg(args, steps, warmup):
                        f'{len(times)} timed + {warmup} warm-up passes, torch CPU fp32 {torch.__version__}, {cores} threads')
 
 
+def make_config(args, world):
+    nfe = SOLVER_NFE[args.solver](args.num_steps)
+    return dict(workload=f'EDM {args.net} U-Net, {args.solver} num_steps={args.num_steps} (NFE={nfe}), batch {args.batch}/GPU',
+                net=args.net, solver=args.solver, nfe=nfe, batch_per_gpu=args.batch, global_batch=args.batch * max(world, 1),
+                weights='random init (reference constructors, seed 0), init_zero layers de-zeroed', parallelism=f'dp{world}',
+                l2='per-forward activation working set (GBs) >> 126 MB L2')
+
+
+def build_workload(args, dev, rank):
+    """(net, sampler, kwargs, latents, labels) of one configuration."""
+    import torch
+    from diff_sampler_b200 import solvers
+    from diff_sampler_b200.net import B200Net
+    B = args.batch
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    labels = None
+    if args.net == 'sd15':
+        net, sampler, kw = build_sd15(args, dev, B, gen)
+    else:
+        net = B200Net.from_config(args.net, seed=0, dezero=True, precision=args.precision, device=dev, fuse_stats=bool(args.fuse_stats),
+                                  f8_min_channels=args.f8_min_channels)
+        sampler = getattr(solvers, args.solver + '_sampler')
+    shape = (B, net.img_channels, net.img_resolution, net.img_resolution)
+    latents = torch.randn(shape, generator=gen, device=dev)
+    if args.net != 'sd15':
+        if net.label_dim:
+            labels = torch.eye(net.label_dim, device=dev)[torch.randint(net.label_dim, (B,), generator=gen, device=dev)]
+        kw = dict(class_labels=labels, num_steps=args.num_steps, sigma_min=0.002, sigma_max=80, schedule_type='polynomial', schedule_rho=7)
+    return net, sampler, kw, latents, labels
+
+
+def timed_steps(fn, steps, barrier, dev, world):
+    """EXACTLY `steps` calls of fn between CUDA events on the current stream, barrier + synchronize on both sides, max over ranks (ms)."""
+    import torch
+    import torch.distributed as dist
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item(), out
+
+
+def measure_e2e(sampler, net, kw, shape, steps, barrier, dev, world):
+    """The same metric through the public sampler API with HOST buffers: pinned latents copied in and finished images copied back
+    inside the timed region, every step."""
+    import torch
+    host_in = torch.randn(shape).pin_memory()
+    host_out = torch.empty(shape).pin_memory()
+    dev_in = torch.empty(shape, device=dev)
+
+    def e2e_step():
+        dev_in.copy_(host_in, non_blocking=True)
+        out = sampler(net, dev_in, **kw)
+        host_out.copy_(out, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    ms, _ = timed_steps(e2e_step, steps, barrier, dev, world)
+    nbytes = host_in.numel() * 4
+    return dict(value=world * shape[0] * steps / (ms / 1e3), unit='images/s', h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    nfe = SOLVER_NFE[args.solver](args.num_steps)
-    config = dict(workload=f'EDM {args.net} U-Net, {args.solver} num_steps={args.num_steps} (NFE={nfe}), batch {args.batch}/GPU',
-                  net=args.net, solver=args.solver, nfe=nfe, batch_per_gpu=args.batch, global_batch=args.batch * max(world, 1),
-                  weights='random init (reference constructors, seed 0), init_zero layers de-zeroed', parallelism=f'dp{world}',
-                  l2='per-forward activation working set (GBs) >> 126 MB L2')
+    config = make_config(args, world)
     metric = 'images/sec at fixed NFE'
 
     if args.impl == 'reference':
         if rank != 0:
             return
         cb = cpu_reference_leg(args, max(1, args.steps), min(args.warmup, 1))
+        # same net / solver / NFE as the native arm's config; each step is a BOUNDED SAMPLE of it (batch `cpu_batch`, not batch_per_gpu)
+        config['workload'] += f' -- CPU arm: each step is a bounded sample of this workload, batch {args.cpu_batch} on {cb["cores"]} host threads'
+        config['sample_batch'] = args.cpu_batch
         line = dict(metric=metric, value=cb['value'], unit='images/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=cb['seconds_per_step'] * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
                     data='synthetic', impl='reference', config=config,
@@ -166,8 +246,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from diff_sampler_b200 import solver_utils, solvers
-    from diff_sampler_b200.net import B200Net
+    from diff_sampler_b200 import solver_utils
     assert torch.cuda.is_available(), 'the native arm needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -193,20 +272,8 @@ def main():
         torch.cuda.synchronize()
 
     B = args.batch
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    labels = None
-    if args.net == 'sd15':
-        net, sampler, kw = build_sd15(args, dev, B, gen)
-    else:
-        net = B200Net.from_config(args.net, seed=0, dezero=True, precision=args.precision, device=dev, fuse_stats=bool(args.fuse_stats),
-                                  f8_min_channels=args.f8_min_channels)
-        sampler = getattr(solvers, args.solver + '_sampler')
-    shape = (B, net.img_channels, net.img_resolution, net.img_resolution)
-    latents = torch.randn(shape, generator=gen, device=dev)
-    if args.net != 'sd15':
-        if net.label_dim:
-            labels = torch.eye(net.label_dim, device=dev)[torch.randint(net.label_dim, (B,), generator=gen, device=dev)]
-        kw = dict(class_labels=labels, num_steps=args.num_steps, sigma_min=0.002, sigma_max=80, schedule_type='polynomial', schedule_rho=7)
+    net, sampler, kw, latents, labels = build_workload(args, dev, rank)
+    shape = tuple(latents.shape)
 
     def run_step():
         return sampler(net, latents, **kw)
@@ -218,55 +285,35 @@ def main():
     if rank == 0:
         clocks.start()
     l0 = net.total_launches + solver_utils.LAUNCHES[0]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        images = run_step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, images = timed_steps(run_step, args.steps, barrier, dev, world)
     launches = net.total_launches + solver_utils.LAUNCHES[0] - l0
     clk = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item()
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end-to-end through the public API with host buffers -------------------------------------------------------
     e2e = None
     if not args.no_extras:
-        host_in = torch.randn(shape).pin_memory()
-        host_out = torch.empty(shape).pin_memory()
-        dev_in = torch.empty(shape, device=dev)
+        e2e = measure_e2e(sampler, net, kw, shape, args.steps, barrier, dev, world)
 
-        def e2e_step():
-            dev_in.copy_(host_in, non_blocking=True)
-            out = sampler(net, dev_in, **kw)
-            host_out.copy_(out, non_blocking=True)
-        for _ in range(2):
-            e2e_step()
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(args.steps):
-            e2e_step()
-        a1.record()
-        barrier()
-        t2 = torch.tensor([a0.elapsed_time(a1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-        nbytes = host_in.numel() * 4
-        e2e = dict(value=world * B * args.steps / (t2.item() / 1e3), unit='images/s', h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes)
-
-    # ---- finished samples: one NCCL all_gather of the uint8 images (outside the timed region) -------------------------
+    # ---- finished samples: FID statistics path over NCCL (outside the timed region) ------------------------------------
     gathered = None
+    fid_allreduce = None
     if world > 1:
-        from diff_sampler_b200 import dist_utils
+        from diff_sampler_b200 import dist_utils, fid_stats
         u8 = dist_utils.to_uint8_nhwc(images)
         allimg = [torch.empty_like(u8) for _ in range(world)]
         dist.all_gather(allimg, u8)
         gathered = sum(x.numel() for x in allimg)
+        try:
+            # fid.py:61-75: per-rank feature moments, all_reduce of mu / sigma over NCCL.  Features here are the image pixels pooled to 8x8
+            # (the detector is caller-supplied in the reference; what is exercised is the accumulation + collective).
+            det = lambda u8: torch.nn.functional.adaptive_avg_pool2d(u8.float(), 8).flatten(1)
+            st = fid_stats.FeatureStats().append_images(u8, det).reduce()
+            mu, sigma = st.finalize()
+            fid_allreduce = dict(features=int(mu.shape[0]), n=int(st.n), mu_norm=float((mu ** 2).sum() ** 0.5), sigma_trace=float(sigma.trace()),
+                                 backend='nccl', note='fid.py:61-79 moments + all_reduce over NCCL; pooled-pixel features stand in for the caller-supplied detector')
+        except Exception as e:                   # diagnostic only
+            fid_allreduce = dict(error=repr(e))
 
     if rank != 0:
         if world > 1:
@@ -277,20 +324,31 @@ def main():
     pk = peaks()
     line = dict(metric=metric, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-                dtype='fp16 operands, fp32 accumulate' + {'fp16x3': ' (split-precision: 3 tcgen05 MMAs per product)',
-                                                           'fp16f8': ' (split-precision: fp16 hi x hi + two e4m3 correction MMAs per product)'}.get(args.precision, ''),
-                data='synthetic', config=config, gpu_launches=launches, clocks=clk, precision=args.precision,
+                dtype=DTYPE_TEXT(args.precision), data='synthetic', config=config, gpu_launches=launches, clocks=clk, precision=args.precision,
                 precision_requested=args.precision_requested, f8_min_channels=args.f8_min_channels)
     if e2e:
         line['e2e'] = e2e
     if gathered:
         line['allgather_bytes'] = gathered
+    if fid_allreduce:
+        line['fid_allreduce'] = fid_allreduce
 
     try:
         if not args.no_extras:
             extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk)
     except Exception as e:                       # the main measurement above is already complete; report instead of dying
         line['extras_error'] = repr(e)
+
+    solo = world == 1 and not args.no_extras
+    if solo and args.gpu_eager and args.net != 'sd15':
+        try:
+            line['gpu_eager'] = gpu_eager_leg(args, dev, native_value=value)
+        except Exception as e:
+            line['gpu_eager'] = dict(error=repr(e))
+    if solo and args.all_configs and (args.net, args.solver) == ('cifar10', 'heun'):
+        del net, images
+        torch.cuda.empty_cache()
+        line['configs'] = other_configs(args, dev, pk)
 
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_reference_leg(args, 1, 1)
@@ -299,6 +357,134 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def DTYPE_TEXT(precision):
+    return 'fp16 operands, fp32 accumulate' + {'fp16x3': ' (split-precision: 3 tcgen05 MMAs per product)',
+                                               'fp16f8': ' (split-precision: fp16 hi x hi + two e4m3 correction MMAs per product)'}.get(precision, '')
+
+
+# BASELINE.json configs[2..4] at their per-GPU batch (1024 / 4, 2048 / 8, 64 / 8 images per GPU)
+OTHER_CONFIGS = [
+    dict(id=3, net='ffhq', solver='ipndm', num_steps=7, batch=256, baseline='EDM FFHQ-64, iPNDM NFE=6 (4-term multistep history), batch 1024 on 4xB200'),
+    dict(id=4, net='imagenet64', solver='dpm_pp', num_steps=11, batch=256,
+         baseline='EDM ImageNet-64 class-cond, DPM-Solver++(2M) NFE=10 with GITS schedule, batch 2048 on 8xB200'),
+    dict(id=5, net='sd15', solver='amed_dpm_pp', num_steps=4, batch=8, baseline='Stable Diffusion v1.5 latent 512x512, AMED-plugin on DPM++ NFE=5, batch 64 on 8xB200'),
+]
+
+
+def other_configs(args, dev, pk):
+    """BASELINE configs 3-5 on one GPU at their per-GPU batch: value (latents resident), e2e (host buffers), roofline of the GEMM
+    kernel (CUDA events per op), the eager-PyTorch comparator where the oracle has a GPU-capable net (configs 3, 4)."""
+    import copy
+    import torch
+    out = []
+    for c in OTHER_CONFIGS:
+        a = copy.copy(args)
+        a.net, a.solver, a.num_steps, a.batch = c['net'], c['solver'], c['num_steps'], c['batch']
+        a.precision = PRECISION_FOR.get(a.net, 'fp16x3') if args.precision_requested == 'auto' else args.precision
+        a.f8_min_channels = F8_MIN_CHANNELS_FOR.get(a.net, 0) if a.precision == 'fp16f8' else 0
+        ent = dict(id=c['id'], baseline_config=c['baseline'], workload=make_config(a, 1)['workload'], precision=a.precision,
+                   f8_min_channels=a.f8_min_channels, steps=args.config_steps)
+        try:
+            t0 = time.time()
+            net, sampler, kw, latents, labels = build_workload(a, dev, 0)
+            if a.solver == 'dpm_pp' and a.net == 'imagenet64':
+                # config 4 samples on a GITS schedule: 11 of the 61 teacher grid points, picked by the DP over native teacher trajectories
+                from diff_sampler_b200 import gits_utils, solver_utils
+                gk = dict(dataset_name='imagenet64', num_warmup=16, max_batch_size=16, sigma_min=0.002, sigma_max=80, num_steps=11, num_steps_tea=61,
+                          schedule_type='polynomial', schedule_rho=7, afs=False, metric='dev', coeff=1.15, model_source='edm', solver='dpmpp',
+                          solver_tea='dpmpp', max_order=2, deis_mode='tab', prompt=None, guidance_rate=1.0, predict_x0=True, lower_order_final=True)
+                torch.manual_seed(0)
+                g0 = time.time()
+                dp_list = gits_utils.get_dp_list(net, dev, **gk)
+                kw.update(t_steps=solver_utils.get_schedule(61, 0.002, 80, device=dev, dp_list=dp_list), max_order=2, predict_x0=True,
+                          lower_order_final=True)
+                ent['gits'] = dict(dp_list=[int(v) for v in dp_list], seconds=time.time() - g0, teacher='dpm_pp(2M) on the 61-point polynomial grid, 16 warm-up latents')
+            elif a.solver == 'ipndm':
+                kw.update(max_order=4)
+            elif a.solver == 'dpm_pp':
+                kw.update(max_order=2, predict_x0=True)
+            ent['build_s'] = time.time() - t0
+            sync = torch.cuda.synchronize
+            step = lambda: sampler(net, latents, **kw)
+            for _ in range(3):
+                step()
+            clocks = ClockSampler(dev.index or 0)
+            clocks.start()
+            ms, images = timed_steps(step, args.config_steps, sync, dev, 1)
+            ent['clocks'] = clocks.stop()
+            ent['value'] = a.batch * args.config_steps / (ms / 1e3)
+            ent['unit'] = 'images/s (1 GPU)'
+            ent['ms_per_step'] = ms / args.config_steps
+            ent['e2e'] = measure_e2e(sampler, net, kw, tuple(latents.shape), args.config_steps, sync, dev, 1)
+            sub = {}
+            roofline_leg(a, sub, net, latents, labels, a.batch, dev, pk, kw)
+            ent['roofline'] = sub.get('roofline')
+            ent['forward_breakdown_ms'] = sub.get('forward_breakdown_ms')
+            del net, images
+            torch.cuda.empty_cache()
+            if args.gpu_eager and a.net != 'sd15':
+                try:
+                    ent['gpu_eager'] = gpu_eager_leg(a, dev, native_value=ent['value'], t_steps=kw.get('t_steps'), solver_kw={k: kw[k] for k in ('max_order', 'predict_x0', 'lower_order_final') if k in kw})
+                except Exception as e:
+                    ent['gpu_eager'] = dict(error=repr(e))
+        except Exception as e:
+            ent['error'] = repr(e)
+        out.append(ent)
+        torch.cuda.empty_cache()
+    return out
+
+
+def gpu_eager_leg(args, dev, native_value, t_steps=None, solver_kw=None):
+    """The reference's GPU path on this B200: eager PyTorch (cuDNN convolutions, cuBLAS einsum attention, ATen elementwise solver steps)
+    through oracle/'s functional restatement of the reference modules (networks_edm.py:60-82 conv2d path, :96-98 group_norm, :105-118
+    attention; solvers.py loops), same net / batch / NFE / latents shape.  Three settings:
+      default  torch defaults, which is what sample.py runs with: cuDNN TF32 convolutions on, fp32 matmuls (sample.py sets no flags)
+      fp32     TF32 off everywhere (the numerics our 1e-3 contract is stated against)
+      fp16     the model body in fp16 as EDMPrecond(use_fp16=True) does (networks_edm.py:486) -- the fastest the reference can run
+    ratio_* = native images/s / eager images/s on the same GPU in the same process."""
+    import torch
+    from oracle import edm_oracle as O
+    from oracle import solvers_oracle as SO
+    P, S = O.make_net(args.net, seed=0, dezero=True)
+    P = {k: v.to(dev) for k, v in P.items()}
+    B = args.batch
+    g = torch.Generator(device=dev).manual_seed(99)
+    lat = torch.randn(B, S['img_channels'], S['img_resolution'], S['img_resolution'], generator=g, device=dev)
+    lab = None
+    if S['label_dim']:
+        lab = torch.eye(S['label_dim'], device=dev)[torch.randint(S['label_dim'], (B,), generator=g, device=dev)]
+    kw = dict(class_labels=lab, num_steps=args.num_steps, **(solver_kw or {}))
+    if t_steps is not None:
+        kw['t_steps'] = t_steps
+    res = dict(note='eager PyTorch on the same GPU (oracle functional nets = the reference modules, bit-identical on CPU); comparator only',
+               batch=B, torch=torch.__version__)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True                     # sample.py:150 (`torch.backends.cudnn.benchmark = True` in the reference's generators)
+    try:
+        for name, tf32c, tf32m, dt, timed in (('default', True, False, torch.float32, 2), ('fp16', True, False, torch.float16, 2),
+                                              ('fp32', False, False, torch.float32, 1)):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32c, tf32m
+            net = O.OracleNet(P, S, dtype=dt)
+            with torch.no_grad():
+                out = SO.sample(net, lat, args.solver, **kw)         # warm-up (cuDNN autotune)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(timed):
+                    out = SO.sample(net, lat, args.solver, **kw)
+                e1.record()
+                torch.cuda.synchronize()
+            v = B * timed / (e0.elapsed_time(e1) / 1e3)
+            res[name] = dict(value=v, unit='images/s (1 GPU)', timed_steps=timed, cudnn_tf32=tf32c, matmul_tf32=tf32m,
+                             dtype=str(dt).replace('torch.', ''), finite=bool(torch.isfinite(out.float()).all()))
+            res['ratio_vs_' + name] = native_value / v
+            del net, out
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    return res
 
 
 def build_sd15(args, dev, B, gen):
@@ -409,6 +595,8 @@ def sd15_param_shapes():
 #   ffhq     iPNDM NFE=6      1.08e-3: over the gate (this net amplifies GEMM rounding the most)   -> fp16x3
 #   sd15     no sampler-level fp16f8 measurement yet                                              -> fp16x3
 PRECISION_FOR = {'cifar10': 'fp16f8', 'imagenet64': 'fp16f8', 'ffhq': 'fp16x3', 'sd15': 'fp16x3'}
+# with fp16f8: blocks narrower than this stay fp16x3 (plan.pack_weights).  Only nets whose all-f8 run misses the gate need it.
+F8_MIN_CHANNELS_FOR = {}
 
 
 # DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of ONE launch of the named GEMM, from `ncu --set full` captures of this
@@ -450,29 +638,63 @@ def dominant_launch(args, line, net):
         rl['traffic_note'] = f'per launch of the dominant GEMM ({label}): algorithmic {g["bytes"] / 1e9:.3f} GB; ' + traffic[1]
 
 
+def roofline_leg(args, line, net, latents, labels, B, dev, pk, kw):
+    """Roofline of the dominant kernel (the tcgen05 GEMM / conv kernel), measured live: every op of one denoiser evaluation is bracketed by
+    CUDA events on the launch stream (ds_unet_set_profiling); achieved = algorithmic FLOPs of one evaluation / summed GEMM time."""
+    import torch
+    from diff_sampler_b200 import _cstructs as S
+    x = latents * 2.0
+    if hasattr(net, 'profile_call'):                 # latent-diffusion net (CFG: 2B samples per evaluation)
+        prof, _ = net.profile_call(x, torch.tensor([2.0], device=dev), kw['condition'], kw['unconditional_condition'])
+    else:
+        prof = net.profile_forward(x, torch.tensor(2.0, device=dev), labels)
+    gemm_n, gemm_ms = prof.get(S.DS_OP_GEMM, (0, 0.0))
+    attn_n, attn_ms = prof.get(S.DS_OP_ATTN, (0, 0.0))
+    fwd_ms = sum(v[1] for v in prof.values())
+    flops = GFLOP_PER_IMG_NFE.get(args.net, 0.0) * 1e9 * B
+    tc_ms = gemm_ms + attn_ms                        # all tensor-core kernels: the fused attention kernel carries part of the algorithmic FLOPs
+    achieved = flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else None
+    peak = pk['tflops_sustained']
+    # forward time without the per-op events: N evaluations back to back between two events (what a sampler step actually pays per NFE)
+    n_rep = 5
+    if hasattr(net, 'profile_call'):
+        call = lambda: net(x, torch.tensor([2.0], device=dev), condition=kw['condition'], unconditional_condition=kw['unconditional_condition'])
+    else:
+        call = lambda: net(x, torch.tensor(2.0, device=dev), class_labels=labels)
+    call()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n_rep):
+        call()
+    f1.record()
+    torch.cuda.synchronize()
+    line['roofline'] = dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
+                            traffic=None, kernel='gemm_tc_kernel (+ attn_kernel): all conv / linear / attention contractions of one denoiser evaluation',
+                            algorithmic_flops_per_forward=flops, launches_per_forward=gemm_n + attn_n, gemm_ms_per_forward=gemm_ms,
+                            attn_ms_per_forward=attn_ms, all_ops_ms_per_forward=fwd_ms, forward_ms_back_to_back=f0.elapsed_time(f1) / n_rep,
+                            gemm_share_of_forward=tc_ms / fwd_ms if fwd_ms else None,
+                            executed_mma_flops_factor={'fp16x3': 3, 'fp16f8': 2}.get(args.precision, 1),
+                            executed_frac_of_peak=(achieved / peak * {'fp16x3': 3, 'fp16f8': 2}.get(args.precision, 1)) if achieved else None,
+                            peak_source=pk['source'] + ', sustained bf16 GEMM',
+                            note='frac = algorithmic FLOPs / time / peak; every product costs executed_mma_flops_factor MMA units under the 1e-3 contract '
+                                 '(DESIGN.md section 2), so frac <= 1 / factor; executed_frac_of_peak is the tensor-pipe view')
+    line['forward_breakdown_ms'] = {OP_NAMES.get(k, str(k)): round(v[1], 4) for k, v in sorted(prof.items())}
+
+
+OP_NAMES = {1: 'gemm', 2: 'gn_stats', 3: 'gn_apply', 4: 'softmax', 5: 'posemb', 6: 'linear', 7: 'prep_input', 8: 'chanmean', 9: 'memset',
+            10: 'layernorm', 11: 'geglu', 12: 'gn_finalize', 13: 'attn'}
+
+
 def extras(args, line, net, sampler, kw, latents, labels, images, B, dev, pk):
     import torch
     from diff_sampler_b200 import solver_utils
     from diff_sampler_b200.net import B200Net
+    from diff_sampler_b200 import _cstructs as S
     if True:
-        # ---- roofline of the dominant kernel (tcgen05 GEMM/conv), measured live with CUDA events on the launch stream ---
+        roofline_leg(args, line, net, latents, labels, B, dev, pk, kw)
         if not hasattr(net, 'profile_forward'):
             return
-        x = latents * 2.0
-        sig = torch.tensor(2.0, device=dev)
-        prof = net.profile_forward(x, sig, labels)
-        from diff_sampler_b200 import _cstructs as S
-        gemm_n, gemm_ms = prof.get(S.DS_OP_GEMM, (0, 0.0))
-        fwd_ms = sum(v[1] for v in prof.values())
-        flops = GFLOP_PER_IMG_NFE.get(args.net, 0.0) * 1e9 * B
-        achieved = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-        peak = pk['tflops_sustained']
-        line['roofline'] = dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
-                                traffic=None, kernel='gemm_tc_kernel (all conv/attention contractions of one forward)',
-                                algorithmic_flops_per_forward=flops, launches_per_forward=gemm_n, gemm_ms_per_forward=gemm_ms,
-                                all_ops_ms_per_forward=fwd_ms, gemm_share_of_forward=gemm_ms / fwd_ms if fwd_ms else None,
-                                executed_mma_flops_factor={'fp16x3': 3, 'fp16f8': 2}.get(args.precision, 1), peak_source=pk['source'] + ', sustained bf16 GEMM')
-        line['forward_breakdown_ms'] = {str(k): round(v[1], 4) for k, v in sorted(prof.items())}
         try:
             dominant_launch(args, line, net)
         except Exception as e:                   # diagnostic detail only; the aggregate roofline above stands on its own

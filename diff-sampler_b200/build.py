@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
             print(' '.join(cmd))
         subprocess.check_call(cmd)
         objs.append(obj)
-    cmd = [nvcc, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    cmd = [nvcc, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd)

@@ -6,6 +6,7 @@
 #include "ops.h"
 #include "ptx.cuh"
 #include <cuda_fp16.h>
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX3: ranges cost nothing unless a profiler (nsys / ncu --nvtx) is attached
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -25,6 +26,13 @@ size_t attn_params_size();
 }  // namespace dsb
 
 static thread_local std::string g_err;
+
+// NVTX range per denoiser evaluation (= one NFE) and per solver update: `ncu --nvtx --nvtx-include "ds_unet_forward/"` or an nsys
+// timeline then groups the launch list by NFE.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -226,6 +234,7 @@ int ds_unet_forward(ds_unet* u, const float* x, const float* sigma, const float*
 
 int ds_unet_forward_io(ds_unet* u, const void* const* io_in, int n_io, void* stream) {
     if (!u) return fail(-1, "ds_unet_forward: null handle");
+    NvtxRange nvtx_range("ds_unet_forward");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const void* io[DS_IO_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     for (int k = 0; k < n_io && k < DS_IO_COUNT; ++k) io[k] = io_in[k];
@@ -300,10 +309,11 @@ int ds_unet_get_profile(ds_unet* u, float* ms_per_op, int n) {
 
 int ds_unet_op_type(const ds_unet* u, int i) { return (u && i >= 0 && i < (int)u->ops.size()) ? u->ops[i].type : -1; }
 
-int ds_solver_update(float* out_x, float* out_m, const float* xb, const float* xs, const float* D, const float* const* hist, int nhist,
-                     const float* thr, int mode, float t, const float* t_dev, const float* coef6, const float* coef_dev,
-                     int64_t n_per_sample, int B, void* stream) {
+static int solver_update_impl(float* out_x, float* out_m, unsigned char* out_u8, int u8_C, int u8_HW, const float* xb, const float* xs,
+                              const float* D, const float* const* hist, int nhist, const float* thr, int mode, float t, const float* t_dev,
+                              const float* coef6, const float* coef_dev, int64_t n_per_sample, int B, void* stream) {
     if (!xb || nhist < 0 || nhist > 4) return fail(-1, "ds_solver_update: bad argument");
+    NvtxRange nvtx_range("ds_solver_update");
     ds_update_desc d;
     memset(&d, 0, sizeof d);
     d.out_x = out_x; d.out_m = out_m; d.xb = xb; d.xs = xs; d.D = D;
@@ -311,10 +321,24 @@ int ds_solver_update(float* out_x, float* out_m, const float* xb, const float* x
     d.thr = thr; d.coef_dev = coef_dev; d.t_dev = t_dev;
     if (coef6) for (int k = 0; k < 6; ++k) d.coef[k] = coef6[k];
     d.t = t; d.mode = mode; d.nhist = nhist; d.B = B; d.n_per_sample = n_per_sample;
+    d.out_u8 = out_u8; d.u8_C = u8_C; d.u8_HW = u8_HW;
     if ((mode == DS_M_X0 || mode == DS_M_EPS) && !D) return fail(-1, "ds_solver_update: mode needs D");
     int rc = ds_update_launch(&d, static_cast<cudaStream_t>(stream));
     if (rc) return fail(rc, std::string("ds_solver_update: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     return 0;
+}
+
+int ds_solver_update(float* out_x, float* out_m, const float* xb, const float* xs, const float* D, const float* const* hist, int nhist,
+                     const float* thr, int mode, float t, const float* t_dev, const float* coef6, const float* coef_dev,
+                     int64_t n_per_sample, int B, void* stream) {
+    return solver_update_impl(out_x, out_m, nullptr, 0, 0, xb, xs, D, hist, nhist, thr, mode, t, t_dev, coef6, coef_dev, n_per_sample, B, stream);
+}
+
+int ds_solver_update_u8(float* out_x, float* out_m, unsigned char* out_u8, int C, int HW, const float* xb, const float* xs, const float* D,
+                        const float* const* hist, int nhist, const float* thr, int mode, float t, const float* t_dev, const float* coef6,
+                        const float* coef_dev, int64_t n_per_sample, int B, void* stream) {
+    if (!out_u8 || C <= 0 || HW <= 0) return fail(-1, "ds_solver_update_u8: bad image geometry");
+    return solver_update_impl(out_x, out_m, out_u8, C, HW, xb, xs, D, hist, nhist, thr, mode, t, t_dev, coef6, coef_dev, n_per_sample, B, stream);
 }
 
 int ds_dyn_threshold(const float* x0, float* thr, int B, int row_len, float q, float floor_val, void* stream) {

@@ -276,6 +276,10 @@ typedef struct ds_update_desc {
     int32_t nhist;          // number of history buffers used (0..4)
     int32_t B;
     int64_t n_per_sample;
+    // optional fused image epilogue of the LAST step (sample.py:311): out_u8[n][hw][c] = uint8(clip(out * 127.5 + 128, 0, 255)),
+    // NCHW fp32 -> NHWC uint8 in the same pass (n_per_sample == u8_C * u8_HW, u8_HW % 4 == 0)
+    unsigned char* out_u8;
+    int32_t u8_C, u8_HW;
 } ds_update_desc;
 
 // Per-sample dynamic threshold s = max(quantile(|x0|, 0.995), 1)  (solver_utils.py:77-86), exact radix select.

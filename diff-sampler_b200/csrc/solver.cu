@@ -8,6 +8,8 @@ namespace dsb {
 __device__ __forceinline__ float4 ld4(const float* p, long long i4) { return __ldcs(reinterpret_cast<const float4*>(p) + i4); }
 __device__ __forceinline__ void st4(float* p, long long i4, float4 v) { __stcs(reinterpret_cast<float4*>(p) + i4, v); }
 
+__device__ __forceinline__ int b_of(long long i4, long long n4_per_sample) { return (int)(i4 / n4_per_sample); }
+
 template <int NH, int MODE>
 __global__ void __launch_bounds__(256) update_kernel(ds_update_desc d, long long n4_total, long long n4_per_sample) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -46,6 +48,15 @@ __global__ void __launch_bounds__(256) update_kernel(ds_update_desc d, long long
         if (NH >= 4) { const float4 h = ld4(d.h[3], i); o.x += c4 * h.x; o.y += c4 * h.y; o.z += c4 * h.z; o.w += c4 * h.w; }
         if (d.out_x) st4(d.out_x, i, o);
         if (d.out_m) st4(d.out_m, i, m);
+        if (d.out_u8) {
+            // the four values are consecutive pixels of one channel plane (HW % 4 == 0): scatter them into the NHWC byte image
+            const long long e = (i - (long long)b_of(i, n4_per_sample) * n4_per_sample) * 4;     // element offset inside the sample
+            const int c = (int)(e / d.u8_HW), p = (int)(e - (long long)c * d.u8_HW);
+            unsigned char* dst = d.out_u8 + ((long long)b_of(i, n4_per_sample) * d.u8_HW + p) * d.u8_C + c;
+            const float v[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dst[(long long)k * d.u8_C] = (unsigned char)fminf(fmaxf(v[k] * 127.5f + 128.0f, 0.0f), 255.0f);
+        }
     }
 }
 
@@ -64,15 +75,20 @@ static int launch_update_nh(const ds_update_desc& d, long long n4, long long n4p
 // ------------------------------------------------------------------------------------------ quantile
 // One CTA per sample.  |x| bit patterns are monotone as uint32, so an MSB-first 8-bit radix select
 // finds the exact k-th order statistic; the (k+1)-th is either equal or the minimum of the larger keys.
+// KEYS_IN_SMEM = false: rows too long for shared memory (> 50 K elements, e.g. 3x256x256 pixel models) re-read |x| from global memory
+// (L2-resident after the first pass) in each of the five passes instead of staging the keys.
+template <bool KEYS_IN_SMEM>
 __global__ void __launch_bounds__(256) threshold_kernel(ds_threshold_desc d) {
-    extern __shared__ uint32_t keys[];
+    extern __shared__ uint32_t keys_smem[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_k, s_less;
     __shared__ uint32_t s_min_above;
     const int b = blockIdx.x;
     const int n = d.row_len;
     const float* x = d.x0 + (long long)b * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = __float_as_uint(fabsf(x[i]));
+    auto key_at = [&](int i) -> uint32_t { return KEYS_IN_SMEM ? keys_smem[i] : __float_as_uint(fabsf(__ldg(x + i))); };
+    if (KEYS_IN_SMEM)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) keys_smem[i] = __float_as_uint(fabsf(x[i]));
     // rank arithmetic in fp32, as torch.quantile does for an fp32 input
     const float rank = d.q * (float)(n - 1);
     const float below = floorf(rank);
@@ -86,7 +102,7 @@ __global__ void __launch_bounds__(256) threshold_kernel(ds_threshold_desc d) {
         __syncthreads();
         const uint32_t prefix = s_prefix;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t key = keys[i];
+            const uint32_t key = key_at(i);
             if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1u);
         }
         __syncthreads();
@@ -108,7 +124,7 @@ __global__ void __launch_bounds__(256) threshold_kernel(ds_threshold_desc d) {
     // count of keys == vk and min of keys > vk
     uint32_t my_eq = 0, my_min = 0xFFFFFFFFu;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint32_t key = keys[i];
+        const uint32_t key = key_at(i);
         if (key == vk) ++my_eq;
         else if (key > vk && key < my_min) my_min = key;
     }
@@ -217,8 +233,14 @@ extern "C" int ds_update_launch(const ds_update_desc* dp, cudaStream_t stream) {
     const long long n4ps = d.n_per_sample / 4;
     const long long n4 = n4ps * d.B;
     if (n4 == 0) return 0;
+    if (d.out_u8 && (d.u8_HW % 4 || (long long)d.u8_C * d.u8_HW != d.n_per_sample)) return -2;
     long long blocks = (n4 + 255) / 256;
-    const long long cap = 148LL * 16;
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    const long long cap = (long long)(sms[dev] > 0 ? sms[dev] : 148) * 16;
     const int grid = (int)(blocks < cap ? blocks : cap);
     int rc;
     switch (d.nhist) {
@@ -234,13 +256,22 @@ extern "C" int ds_update_launch(const ds_update_desc* dp, cudaStream_t stream) {
 }
 
 extern "C" int ds_threshold_launch(const ds_threshold_desc* d, cudaStream_t stream) {
+    if (d->B <= 0 || d->row_len <= 0) return -2;
     const size_t smem = (size_t)d->row_len * sizeof(uint32_t);
-    if (smem > 200 * 1024) return -2;
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr = true;
+    if (smem > 200 * 1024) {                       // long rows: keys stay in global memory / L2
+        threshold_kernel<false><<<d->B, 256, 0, stream>>>(*d);
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
-    threshold_kernel<<<d->B, 256, smem, stream>>>(*d);
+    if (smem > 48 * 1024) {
+        // the opt-in shared-memory limit is a per-device function attribute: set it on every device this process uses
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+            if (cudaFuncSetAttribute(threshold_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return -3;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        }
+    }
+    threshold_kernel<true><<<d->B, 256, smem, stream>>>(*d);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }

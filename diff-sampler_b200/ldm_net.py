@@ -67,6 +67,9 @@ class B200LDMNet:
         """Compile a reference CFGPrecond (net.model.model.diffusion_model is the UNetModel; net.model.alphas_cumprod the schedule)."""
         unet = net.model.model.diffusion_model if hasattr(net.model, 'model') else net.model.u
         sd = OrderedDict(unet.state_dict())
+        nh = getattr(unet, 'num_heads', num_heads)          # openaimodel.py:466 (-1 when the config gives num_head_channels instead)
+        if isinstance(nh, int) and nh > 0:
+            num_heads = nh
         return cls(sd, img_resolution=net.img_resolution, img_channels=net.img_channels, num_heads=num_heads,
                    alphas_cumprod=net.model.alphas_cumprod, guidance_type=net.guidance_type, guidance_rate=net.guidance_rate, **kw)
 

@@ -79,16 +79,30 @@ def _chk_dev(*ts):
 
 
 def solver_update(out_x, xb, coef, *, mode=S.DS_M_NONE, D=None, xs=None, hist=(), out_m=None, thr=None, t=1.0, t_dev=None,
-                  coef_dev=None):
+                  coef_dev=None, out_u8=None):
     """out_x = coef[0]*xb + coef[1]*m0 + sum_k coef[2+k]*hist[k], with m0 derived per `mode` (include/diffsampler_b200.h).
-    One kernel launch, one pass over HBM."""
+    One kernel launch, one pass over HBM.  out_u8 ([B, H, W, C] uint8): also write the finished images as sample.py:311 does
+    ((x * 127.5 + 128).clip(0, 255).uint8, NHWC) in the same pass."""
     lib = _lib.load()
-    hist = [h for h in hist if h is not None]
+    hist = list(hist)
+    if any(h is None for h in hist):
+        raise ValueError('solver_update: a history buffer is None (coefficients would shift onto the wrong buffers)')
+    if len(hist) > 4 or len(coef) > 2 + 4 or (coef_dev is None and len(coef) > 2 and len(coef) - 2 != len(hist)):
+        raise ValueError(f'solver_update: {len(coef)} coefficients for {len(hist)} history buffers')
     _chk_dev(out_x, xb, D, xs, out_m, thr, t_dev, coef_dev, *hist)
     cf = (C.c_float * 6)(*([float(c) for c in coef] + [0.0] * (6 - len(coef))))
     hp = (C.c_void_p * 4)(*([h.data_ptr() for h in hist] + [None] * (4 - len(hist))))
     B = xb.shape[0]
     n = xb[0].numel()
+    if out_u8 is not None:
+        if out_u8.dtype != torch.uint8 or out_u8.device != xb.device or not out_u8.is_contiguous() or xb.dim() != 4 or \
+                tuple(out_u8.shape) != (B, xb.shape[2], xb.shape[3], xb.shape[1]):
+            raise _lib.DsError('solver_update: out_u8 must be a contiguous uint8 [B, H, W, C] tensor on the same device')
+        rc = lib.ds_solver_update_u8(_ptr(out_x), _ptr(out_m), out_u8.data_ptr(), xb.shape[1], xb.shape[2] * xb.shape[3], _ptr(xb), _ptr(xs),
+                                     _ptr(D), hp, len(hist), _ptr(thr), int(mode), float(t), _ptr(t_dev), cf, _ptr(coef_dev), n, B, _stream(xb))
+        _lib.check(rc, 'ds_solver_update_u8')
+        LAUNCHES[0] += 1
+        return out_x
     rc = lib.ds_solver_update(_ptr(out_x), _ptr(out_m), _ptr(xb), _ptr(xs), _ptr(D), hp, len(hist), _ptr(thr), int(mode), float(t),
                               _ptr(t_dev), cf, _ptr(coef_dev), n, B, _stream(xb))
     _lib.check(rc, 'ds_solver_update')

@@ -19,24 +19,58 @@ from .solver_utils import (dpm_pp_coefs, dyn_threshold, get_schedule, solver_upd
 _NATIVE_CLASSES = ('SongUNet', 'DhariwalUNet')
 
 
+def _weights_fingerprint(module):
+    """Cheap identity of a torch module's weights: storage address and in-place version counter of every tensor of its state_dict
+    (load_state_dict / optimiser / EMA updates bump the version; re-assignment changes the address)."""
+    return tuple((v.data_ptr(), v._version) for v in module.state_dict(keep_vars=True).values())
+
+
+def invalidate_native(net):
+    """Drop the compiled snapshot `as_native` cached on a reference module (it is re-compiled on the next call)."""
+    try:
+        object.__delattr__(net, '_b200_native')
+    except AttributeError:
+        pass
+
+
 def as_native(net, precision=None):
-    """B200Net for `net`: itself, a cached compilation of a reference EDMPrecond module, or — for anything else
-    (e.g. CFGPrecond / foreign callables) — the object unchanged (its D(x, sigma) is then consumed by the native update kernels)."""
+    """The native denoiser for `net`:
+      * a B200Net / B200LDMNet                      -> itself;
+      * a reference EDMPrecond over SongUNet / DhariwalUNet (networks_edm.py:459-496) -> B200Net.from_reference, compiled once and
+        cached on the module together with a fingerprint of its weights (a later load_state_dict / EMA update re-compiles);
+      * a reference CFGPrecond over a latent-diffusion UNetModel (networks_edm.py:630-759) -> B200LDMNet.from_reference, same cache;
+      * anything else (VP/VE/iDDPM preconditioners, foreign callables) -> the object unchanged: its D(x, sigma) is evaluated by
+        PyTorch and consumed by the native update kernels.  Other preconditioners are NOT compiled: their c_skip / c_out / c_noise
+        differ from EDM's and evaluating them as EDMPrecond would be silently wrong."""
     if isinstance(net, (B200Net, B200LDMNet)):
         return net
-    cached = getattr(net, '_b200_native', None)
-    if cached is not None:
-        return cached
+    if not hasattr(net, 'state_dict'):
+        return net
     inner = getattr(net, 'model', None)
-    if inner is not None and type(inner).__name__ in _NATIVE_CLASSES and hasattr(net, 'state_dict'):
-        dev = next(net.parameters()).device
-        nat = B200Net.from_reference(net, device=dev if dev.type == 'cuda' else 'cuda', **({'precision': precision} if precision else {}))
-        try:
-            object.__setattr__(net, '_b200_native', nat)
-        except Exception:
-            pass
-        return nat
-    return net
+    kind = None
+    if type(net).__name__ == 'EDMPrecond' and inner is not None and type(inner).__name__ in _NATIVE_CLASSES:
+        kind = 'edm'
+    elif type(net).__name__ == 'CFGPrecond' and hasattr(net, 'guidance_type'):
+        unet = getattr(getattr(inner, 'model', None), 'diffusion_model', None)
+        if unet is not None and type(unet).__name__ == 'UNetModel':
+            kind = 'ldm'
+    if kind is None:
+        return net
+    fp = _weights_fingerprint(net)
+    cached = getattr(net, '_b200_native', None)
+    if cached is not None and cached[0] == fp and (precision is None or cached[1].precision == precision):
+        return cached[1]
+    dev = next(net.parameters()).device
+    kw = dict(device=dev if dev.type == 'cuda' else 'cuda', **({'precision': precision} if precision else {}))
+    if kind == 'edm':
+        nat = B200Net.from_reference(net, **kw)
+    else:
+        nat = B200LDMNet.from_reference(net, **kw)
+    try:
+        object.__setattr__(net, '_b200_native', (fp, nat))
+    except Exception:
+        pass
+    return nat
 
 
 def get_denoised(net, x, t, class_labels=None, condition=None, unconditional_condition=None):
@@ -71,6 +105,20 @@ class _Loop:
         self.x = self._slot(0)
         solver_update(self.x, self.latents, [self.t[0]], mode=S.DS_M_NONE)      # x_next = latents * t_steps[0]  (solvers.py:68)
         self.D = torch.empty_like(self.latents)
+        self.u8, self.u8_done = None, False
+
+    def want_uint8(self, kwargs):
+        """`images_uint8=` (an extra keyword the reference's samplers swallow in **kwargs): a [B, H, W, C] uint8 tensor that receives the
+        finished images as sample.py:311 computes them, written by the LAST update kernel of the run (no separate pass over the state)."""
+        self.u8 = kwargs.get('images_uint8')
+        return self
+
+    def u8_at(self, i):
+        """The byte image rides on the update that produces x_{N-1} (not when a final denoise-to-zero evaluation follows)."""
+        if self.u8 is None or self.denoise_to_zero or i != self.n - 2:
+            return None
+        self.u8_done = True
+        return self.u8
 
     def _slot(self, i):
         return self.inters[i] if self.inters is not None else torch.empty_like(self.latents)
@@ -103,6 +151,9 @@ class _Loop:
             x = self.denoise(x, self.n - 1, out=(self.inters[self.n] if self.inters is not None else None))
             if self.inters is not None and x.data_ptr() != self.inters[self.n].data_ptr():
                 self.inters[self.n].copy_(x)
+        if self.u8 is not None and not self.u8_done:          # paths without a fused final update (denoise_to_zero, AMED variants)
+            from .dist_utils import to_uint8_nhwc
+            self.u8.copy_(to_uint8_nhwc(x))
         if self.return_inters:
             if self.return_eps and self.eps is not None:
                 return self.inters, self.eps
@@ -123,16 +174,16 @@ def euler_sampler(net, latents, class_labels=None, condition=None, unconditional
     """Euler sampler (= DDIM).  Reference: solvers.py:18-96.  Per step: x+ = x + (t+ - t) * (x - D)/t  [AFS first step:
     d = x / sqrt(1 + t^2), no network call]."""
     L = _Loop(net, latents, class_labels, condition, unconditional_condition, num_steps, sigma_min, sigma_max, schedule_type,
-              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero)
+              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero).want_uint8(kwargs)
     t = L.t
     for i in range(L.n - 1):
         h = t[i + 1] - t[i]
         out, dm = L.next_slot(i), L.d_slot(i, None)
         if afs and i == 0:
-            solver_update(out, L.x, [1.0, h], mode=S.DS_M_DIV, t=_afs_div(t[i]), out_m=dm)
+            solver_update(out, L.x, [1.0, h], mode=S.DS_M_DIV, t=_afs_div(t[i]), out_m=dm, out_u8=L.u8_at(i))
         else:
             D = L.denoise(L.x, i)
-            solver_update(out, L.x, [1.0, h], mode=S.DS_M_EPS, D=D, t=t[i], out_m=dm)
+            solver_update(out, L.x, [1.0, h], mode=S.DS_M_EPS, D=D, t=t[i], out_m=dm, out_u8=L.u8_at(i))
         L.x = out
     return L.finish()
 
@@ -143,7 +194,7 @@ def heun_sampler(net, latents, class_labels=None, condition=None, unconditional_
                  return_eps=False, t_steps=None, **kwargs):
     """Heun's 2nd-order sampler (EDM).  Reference: solvers.py:100-183.  Euler predictor + trapezoidal corrector, 2 NFE/step."""
     L = _Loop(net, latents, class_labels, condition, unconditional_condition, num_steps, sigma_min, sigma_max, schedule_type,
-              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero)
+              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero).want_uint8(kwargs)
     t = L.t
     xp = torch.empty_like(L.latents)
     d_buf = torch.empty_like(L.latents)
@@ -158,7 +209,7 @@ def heun_sampler(net, latents, class_labels=None, condition=None, unconditional_
         D2 = L.denoise(xp, i + 1)
         out = L.next_slot(i)
         # x+ = x + h*(0.5*d + 0.5*d'),  d' = (x_pred - D')/t+       (solvers.py:166-168)
-        solver_update(out, L.x, [1.0, 0.5 * h, 0.5 * h], mode=S.DS_M_EPS, D=D2, xs=xp, t=t[i + 1], hist=[d])
+        solver_update(out, L.x, [1.0, 0.5 * h, 0.5 * h], mode=S.DS_M_EPS, D=D2, xs=xp, t=t[i + 1], hist=[d], out_u8=L.u8_at(i))
         L.x = out
     return L.finish()
 
@@ -169,7 +220,7 @@ def dpm_2_sampler(net, latents, class_labels=None, condition=None, unconditional
                   return_eps=False, r=0.5, t_steps=None, **kwargs):
     """DPM-Solver-2.  Reference: solvers.py:187-273.  Midpoint at t_mid = t+^r * t^(1-r)."""
     L = _Loop(net, latents, class_labels, condition, unconditional_condition, num_steps, sigma_min, sigma_max, schedule_type,
-              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero)
+              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero).want_uint8(kwargs)
     t = L.t
     xp = torch.empty_like(L.latents)
     d_buf = torch.empty_like(L.latents)
@@ -184,7 +235,7 @@ def dpm_2_sampler(net, latents, class_labels=None, condition=None, unconditional
             solver_update(xp, L.x, [1.0, t_mid - t[i]], mode=S.DS_M_EPS, D=D, t=t[i], out_m=d)
         D2 = L.denoise(xp, sigma=torch.tensor([t_mid], device=xp.device, dtype=torch.float32))
         out = L.next_slot(i)
-        solver_update(out, L.x, [1.0, h * (1 / (2 * r)), h * (1 - 1 / (2 * r))], mode=S.DS_M_EPS, D=D2, xs=xp, t=t_mid, hist=[d])
+        solver_update(out, L.x, [1.0, h * (1 / (2 * r)), h * (1 - 1 / (2 * r))], mode=S.DS_M_EPS, D=D2, xs=xp, t=t_mid, hist=[d], out_u8=L.u8_at(i))
         L.x = out
     return L.finish()
 
@@ -200,12 +251,14 @@ def _multistep(L, afs, max_order, coef_fn, afs_first_by_index=True):
         c = coef_fn(i, order)                                   # [c_cur, c_prev1, ...]
         d_new = L.d_slot(i, spare[i % len(spare)])
         out = L.next_slot(i)
-        first = (i == 0) if afs_first_by_index else (len(hist) == 0)
+        # AFS replaces the FIRST evaluation only.  ipndm_v / deis decide it by "history is empty" (solvers.py:445,570); with
+        # max_order == 1 nothing is ever pushed, so the step index decides there (the reference raises IndexError for that case).
+        first = (i == 0) if (afs_first_by_index or max_order == 1) else (len(hist) == 0)
         if afs and first:
-            solver_update(out, L.x, [1.0] + c, mode=S.DS_M_DIV, t=_afs_div(t[i]), hist=hist[:order - 1], out_m=d_new)
+            solver_update(out, L.x, [1.0] + c, mode=S.DS_M_DIV, t=_afs_div(t[i]), hist=hist[:order - 1], out_m=d_new, out_u8=L.u8_at(i))
         else:
             D = L.denoise(L.x, i)
-            solver_update(out, L.x, [1.0] + c, mode=S.DS_M_EPS, D=D, t=t[i], hist=hist[:order - 1], out_m=d_new)
+            solver_update(out, L.x, [1.0] + c, mode=S.DS_M_EPS, D=D, t=t[i], hist=hist[:order - 1], out_m=d_new, out_u8=L.u8_at(i))
         L.x = out
         if max_order > 1:
             hist = ([d_new] + hist)[:max_order - 1]
@@ -220,7 +273,7 @@ def ipndm_sampler(net, latents, class_labels=None, condition=None, unconditional
     Note: the reference indexes an empty list when max_order == 1 (solvers.py:358-361); here max_order == 1 is plain Euler."""
     assert max_order >= 1 and max_order <= 4
     L = _Loop(net, latents, class_labels, condition, unconditional_condition, num_steps, sigma_min, sigma_max, schedule_type,
-              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero)
+              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero).want_uint8(kwargs)
     AB = {1: [1.0], 2: [3 / 2, -1 / 2], 3: [23 / 12, -16 / 12, 5 / 12], 4: [55 / 24, -59 / 24, 37 / 24, -9 / 24]}
     return _multistep(L, afs, max_order, lambda i, order: [(L.t[i + 1] - L.t[i]) * a for a in AB[order]])
 
@@ -254,7 +307,7 @@ def ipndm_v_sampler(net, latents, class_labels=None, condition=None, uncondition
     """Variable-step Adams-Bashforth.  Reference: solvers.py:378-499."""
     assert max_order >= 1 and max_order <= 4
     L = _Loop(net, latents, class_labels, condition, unconditional_condition, num_steps, sigma_min, sigma_max, schedule_type,
-              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero)
+              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero).want_uint8(kwargs)
     return _multistep(L, afs, max_order, lambda i, order: [(L.t[i + 1] - L.t[i]) * a for a in _abv(L.t, i, order)],
                       afs_first_by_index=False)
 
@@ -267,7 +320,7 @@ def deis_sampler(net, latents, class_labels=None, condition=None, unconditional_
     assert max_order >= 1 and max_order <= 4
     assert coeff_list is not None
     L = _Loop(net, latents, class_labels, condition, unconditional_condition, num_steps, sigma_min, sigma_max, schedule_type,
-              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero)
+              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero).want_uint8(kwargs)
 
     def coefs(i, order):
         if order == 1:
@@ -284,7 +337,7 @@ def dpm_pp_sampler(net, latents, class_labels=None, condition=None, unconditiona
     solver_utils.py:90-163.  As in the reference, `num_steps` is read for lower_order_final even when t_steps is given."""
     assert max_order >= 1 and max_order <= 3
     L = _Loop(net, latents, class_labels, condition, unconditional_condition, num_steps, sigma_min, sigma_max, schedule_type,
-              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero)
+              schedule_rho, t_steps, return_inters, return_eps, denoise_to_zero).want_uint8(kwargs)
     t = L.t
     if num_steps is None:
         num_steps = L.n
@@ -318,10 +371,10 @@ def dpm_pp_sampler(net, latents, class_labels=None, condition=None, unconditiona
                 dyn_threshold(D, out=thr)
                 if L.eps is not None:      # GITS-style callers also want d_cur = (x - D)/t
                     solver_update(None, L.x, [0.0, 0.0], mode=S.DS_M_EPS, D=D, t=t[i], out_m=L.eps[i])
-                solver_update(out, L.x, coef, mode=S.DS_M_X0, D=D, thr=thr, hist=hist[:order - 1], out_m=m_new)
+                solver_update(out, L.x, coef, mode=S.DS_M_X0, D=D, thr=thr, hist=hist[:order - 1], out_m=m_new, out_u8=L.u8_at(i))
             else:
                 m_new = L.d_slot(i, m_new)
-                solver_update(out, L.x, coef, mode=S.DS_M_EPS, D=D, t=t[i], hist=hist[:order - 1], out_m=m_new)
+                solver_update(out, L.x, coef, mode=S.DS_M_EPS, D=D, t=t[i], hist=hist[:order - 1], out_m=m_new, out_u8=L.u8_at(i))
         L.x = out
         hist = ([m_new] + hist)[:3]
         hist_t = ([t[i]] + hist_t)[:3]
@@ -336,7 +389,7 @@ def unipc_sampler(net, latents, class_labels=None, condition=None, unconditional
     network evaluation sits between two launches of the same fused update kernel."""
     assert max_order > 0 and max_order < 4
     L = _Loop(net, latents, class_labels, condition, unconditional_condition, num_steps, sigma_min, sigma_max, schedule_type,
-              schedule_rho, t_steps, return_inters, False, denoise_to_zero)
+              schedule_rho, t_steps, return_inters, False, denoise_to_zero).want_uint8(kwargs)
     t = L.t
     if num_steps is None:
         num_steps = L.n
@@ -392,5 +445,7 @@ def unipc_sampler(net, latents, class_labels=None, condition=None, unconditional
         else:
             if i < num_steps - 2:
                 hist = ([m_t] + hist)[:max_order]
+            else:                               # the reference shifts without storing: [a, b, c] -> [b, c, c] (solvers.py:805-810)
+                hist = ([hist[0]] + hist)[:max_order]
             hist_t = ([t[i + 1]] + hist_t)[:max_order]
     return L.finish()

@@ -79,6 +79,13 @@ int ds_solver_update(float* out_x, float* out_m, const float* xb, const float* x
                      const float* const* hist, int nhist, const float* thr, int mode, float t, const float* t_dev,
                      const float* coef6, const float* coef_dev, int64_t n_per_sample, int B, void* stream);
 
+/* Same update with the image epilogue of sample.py:311 fused in (the LAST step of a sampling run):
+ *   out_u8[n][hw][c] = uint8(clip(out * 127.5 + 128, 0, 255))   NCHW fp32 -> NHWC uint8, in the same pass over the state.
+ * C * HW == n_per_sample, HW % 4 == 0; out_x may be NULL when only the byte image is wanted. */
+int ds_solver_update_u8(float* out_x, float* out_m, unsigned char* out_u8, int C, int HW, const float* xb, const float* xs, const float* D,
+                        const float* const* hist, int nhist, const float* thr, int mode, float t, const float* t_dev,
+                        const float* coef6, const float* coef_dev, int64_t n_per_sample, int B, void* stream);
+
 /* ---- dynamic thresholding: replaces torch.quantile(|x0|, 0.995) per sample ---------------------
  * solver_utils.py:77-86.  thr[b] = max(quantile_linear(|x0[b]|, q), floor_val).  Exact selection. */
 int ds_dyn_threshold(const float* x0, float* thr, int B, int row_len, float q, float floor_val, void* stream);

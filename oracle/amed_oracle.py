@@ -39,10 +39,22 @@ def predictor_forward(W, cfg, bottleneck, t_cur, t_next):
 
 @torch.no_grad()
 def sample_amed(net, latents, solver, W, cfg, num_steps, afs=False, max_order=None, predict_x0=True, lower_order_final=True,
-                sigma_min=0.002, sigma_max=80, schedule_type='polynomial', schedule_rho=7, bottleneck_block='enc.8x8_block3'):
-    """solver in {'amed', 'euler', 'ipndm', 'dpm_2', 'dpm_pp'} (solvers_amed.py:69-159, 163-257, 262-396, 400-494, 498-631)."""
-    t_steps = get_schedule(num_steps, sigma_min, sigma_max, schedule_type=schedule_type, schedule_rho=schedule_rho)
+                sigma_min=0.002, sigma_max=80, schedule_type='polynomial', schedule_rho=7, bottleneck_block=None, class_labels=None,
+                condition=None, unconditional_condition=None):
+    """solver in {'amed', 'euler', 'ipndm', 'dpm_2', 'dpm_pp'} (solvers_amed.py:69-159, 163-257, 262-396, 400-494, 498-631).
+    Bottleneck tap (solvers_amed.py:7-27): EDM nets -> enc['8x8_block2'] with class labels, enc['8x8_block3'] without (:16);
+    latent-diffusion nets (guidance_type) -> middle_block output (:12), and under classifier-free guidance the conditional half
+    [B:] of the doubled batch (:24-25)."""
+    is_ldm = hasattr(net, 'guidance_type')
+    t_steps = get_schedule(num_steps, sigma_min, sigma_max, schedule_type=schedule_type, schedule_rho=schedule_rho, net=net)
     B = latents.shape[0]
+    if bottleneck_block is None:
+        bottleneck_block = 'middle_block.2' if is_ldm else ('enc.8x8_block2' if class_labels is not None else 'enc.8x8_block3')
+
+    def call(x, t):
+        if is_ldm:
+            return net(x, t, condition=condition, unconditional_condition=unconditional_condition)
+        return net(x, t, class_labels=class_labels)
     x_next = latents * t_steps[0]
     hist, hist_t = [], []
     total = 2 * num_steps - 1
@@ -50,9 +62,11 @@ def sample_amed(net, latents, solver, W, cfg, num_steps, afs=False, max_order=No
 
     def D_tap(x, t):
         net.taps = {}
-        den = net(x, t)
+        den = call(x, t)
         enc = torch.mean(net.taps[bottleneck_block], dim=1)
         net.taps = None
+        if is_ldm and net.guidance_type == 'classifier-free' and enc.shape[0] == 2 * B:
+            enc = enc[B:]
         return den, enc
 
     def push(d):
@@ -87,7 +101,7 @@ def sample_amed(net, latents, solver, W, cfg, num_steps, afs=False, max_order=No
         t_mid = (tn ** r) * (tc ** (1 - r))
         if solver in ('amed', 'euler', 'dpm_2'):
             x_mid = x_cur + (t_mid - tc) * d_cur
-            d_mid = (x_mid - net(x_mid, st * t_mid)) / t_mid
+            d_mid = (x_mid - call(x_mid, st * t_mid)) / t_mid
             if solver == 'amed':
                 x_next = x_cur + sd * (tn - tc) * d_mid
             elif solver == 'euler':
@@ -99,7 +113,7 @@ def sample_amed(net, latents, solver, W, cfg, num_steps, afs=False, max_order=No
             x_mid = x_cur + (t_mid - tc) * ab(d_cur, order)
             push(d_cur)
             order = min(max_order, len(hist) + 1)
-            d_mid = (x_mid - net(x_mid, st * t_mid)) / t_mid
+            d_mid = (x_mid - call(x_mid, st * t_mid)) / t_mid
             x_next = x_mid + sd * (tn - t_mid) * ab(d_mid, order)
             push(d_mid)
         elif solver == 'dpm_pp':
@@ -109,7 +123,7 @@ def sample_amed(net, latents, solver, W, cfg, num_steps, afs=False, max_order=No
             order = (step if step < max_order else min(max_order, total - step)) if lower_order_final else min(max_order, step)
             x_mid = dpm_pp_update(x_cur, hist, hist_t, t_mid, order, predict_x0=predict_x0)
             step += 1
-            den2 = net(x_mid, st * t_mid)
+            den2 = call(x_mid, st * t_mid)
             hist.append(dynamic_thresholding(den2) if predict_x0 else (x_mid - den2) / t_mid)
             hist_t.append(t_mid)
             order = (step if step < max_order else min(max_order, total - step)) if lower_order_final else min(step, max_order)

@@ -46,6 +46,10 @@ def main():
                                              encoder_type='standard', decoder_type='standard', channel_mult_noise=1, resample_filter=[1, 1])),
         'adm_fp16': dict(cls=EDMPrecond, kw=dict(img_resolution=8, img_channels=3, label_dim=10, use_fp16=True, model_type='DhariwalUNet',
                                                  model_channels=8, channel_mult=[1, 2], num_blocks=1, attn_resolutions=[4])),
+        # 64-channel net: the smallest the native kernels run (channel counts are multiples of 64), for the GPU from_pickle test
+        'song64': dict(cls=EDMPrecond, kw=dict(img_resolution=8, img_channels=3, label_dim=0, model_type='SongUNet', model_channels=64,
+                                               channel_mult=[1], num_blocks=1, attn_resolutions=[8], augment_dim=9, embedding_type='positional',
+                                               encoder_type='standard', decoder_type='standard', channel_mult_noise=1, resample_filter=[1, 1])),
         # not an EDMPrecond: the importer must refuse it (a bare U-Net has no preconditioning to drop in for)
         'bare_unet': dict(cls=SongUNet, kw=dict(img_resolution=8, in_channels=3, out_channels=3, model_channels=8, channel_mult=[1],
                                                 num_blocks=1, attn_resolutions=[], resample_filter=[1, 1])),

@@ -211,6 +211,98 @@ np.savez_compressed(sys.argv[1], **G)
     return out
 
 
+def amed_taps_part():
+    """AMED samplers on the two bottleneck taps ref_amed.npz does not cover (amed-solver-main/solvers_amed.py:11-16, :24-26):
+      * class-conditional EDM net -> hook on enc['8x8_block2'] (tiny_adm3, labels given);
+      * latent-diffusion net under classifier-free guidance -> hook on model.model.diffusion_model.middle_block, channel mean,
+        conditional half [B:] (tiny_ldm, CFG 7.5) with the Stable-Diffusion launch flags (launch.sh:57-61).
+    Child interpreter with amed-solver-main on the path; writes tests/golden/ref_amed_taps.npz."""
+    code = r"""
+import sys, types, numpy as np, torch
+sys.path.insert(0, "/root/reference/amed-solver-main")
+sys.path.insert(0, "%s")
+oc = types.ModuleType("omegaconf"); lc = types.ModuleType("omegaconf.listconfig")
+lc.ListConfig = type("ListConfig", (list,), {}); oc.listconfig = lc
+sys.modules.setdefault("omegaconf", oc); sys.modules.setdefault("omegaconf.listconfig", lc)
+import solvers_amed as RA
+import solver_utils as RU
+from training.networks import AMED_predictor
+from oracle import edm_oracle as O
+from oracle import ldm_oracle as LO
+from oracle.gen_golden import build_ref_net
+G = {}
+# ---- class-conditional EDM net: 8x8_block2 tap
+net = build_ref_net("tiny_adm3", dezero=True)
+B = 3
+lat = O.stacked_randn(range(B), (3, net.img_resolution, net.img_resolution))
+lab = torch.eye(net.label_dim)[torch.tensor([1, 7, 4])]
+G["adm/labels"] = lab.numpy()
+for ci, (fn, kw, pk) in enumerate([
+    ("amed_sampler", dict(num_steps=4), dict(sampler_stu="amed", scale_dir=0.01, scale_time=0.2)),
+    ("dpm_pp_sampler", dict(num_steps=4, max_order=2, predict_x0=True, afs=True), dict(sampler_stu="dpmpp", scale_dir=0.01, scale_time=0.2)),
+    ("ipndm_sampler", dict(num_steps=4, max_order=4, afs=True), dict(sampler_stu="ipndm", scale_dir=0.01, scale_time=0.0)),
+]):
+    torch.manual_seed(200 + ci)
+    pred = AMED_predictor(sampler_tea="heun", num_steps=kw["num_steps"], **pk).eval().requires_grad_(False)
+    for k, v in pred.state_dict().items():
+        G[f"adm/{ci}/pred/{k}"] = v.numpy()
+    with torch.no_grad():
+        out = getattr(RA, fn)(net, lat, class_labels=lab, AMED_predictor=pred, sigma_min=0.002, sigma_max=80, schedule_type="polynomial",
+                              schedule_rho=7, **kw)
+    G[f"adm/{ci}/out"] = out.numpy()
+# ---- latent-diffusion net, classifier-free guidance: middle_block tap, conditional half
+from models.ldm.modules.diffusionmodules.openaimodel import UNetModel
+from models.networks_edm import CFGPrecond
+P, cfg = LO.make_params("tiny_ldm", seed=0)
+unet = UNetModel(image_size=32, in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], model_channels=cfg["model_channels"],
+                 attention_resolutions=list(cfg["attention_resolutions"]), num_res_blocks=cfg["num_res_blocks"],
+                 channel_mult=list(cfg["channel_mult"]), num_heads=cfg["num_heads"], use_spatial_transformer=True,
+                 transformer_depth=1, context_dim=cfg["context_dim"], use_checkpoint=False, legacy=False).eval().requires_grad_(False)
+unet.load_state_dict(P)
+class Inner(torch.nn.Module):
+    def __init__(self, u):
+        super().__init__()
+        self.diffusion_model = u
+class Shim(torch.nn.Module):
+    def __init__(self, u):
+        super().__init__()
+        self.model = Inner(u)
+        self.alphas_cumprod = LO.make_alphas_cumprod()
+    def apply_model(self, x, t, cond):
+        return self.model.diffusion_model(x, t, context=cond)
+R = cfg["img_resolution"]
+B = 2
+lat = O.stacked_randn(range(B), (cfg["in_channels"], R, R))
+g = torch.Generator().manual_seed(9)
+c = torch.randn(B, 77, cfg["context_dim"], generator=g)
+uc = torch.randn(B, 77, cfg["context_dim"], generator=g)
+G["ldm/c"], G["ldm/uc"] = c.numpy(), uc.numpy()
+for ci, (guidance, kw, pk) in enumerate([
+    (7.5, dict(num_steps=4, afs=True, max_order=2, predict_x0=False, lower_order_final=True), dict(sampler_stu="dpmpp", scale_dir=0.0, scale_time=0.2)),
+    (7.5, dict(num_steps=3, afs=False, max_order=3, predict_x0=False, lower_order_final=True), dict(sampler_stu="dpmpp", scale_dir=0.01, scale_time=0.2)),
+    # (guidance 1.0 cannot be recorded: the reference multiplies c_in[B] * x without a reshape on that branch, networks_edm.py:685,
+    #  and the AMED second evaluation always carries a per-sample sigma)
+]):
+    net = CFGPrecond(Shim(unet), img_resolution=R, img_channels=cfg["in_channels"], guidance_rate=guidance,
+                     guidance_type="classifier-free", label_dim=True).eval()
+    torch.manual_seed(300 + ci)
+    pred = AMED_predictor(sampler_tea="dpmpp", num_steps=kw["num_steps"], **pk).eval().requires_grad_(False)
+    for k, v in pred.state_dict().items():
+        G[f"ldm/{ci}/pred/{k}"] = v.numpy()
+    with torch.no_grad():
+        out = RA.dpm_pp_sampler(net, lat, condition=c, unconditional_condition=uc, AMED_predictor=pred, sigma_min=net.sigma_min,
+                                sigma_max=net.sigma_max, schedule_type="discrete", schedule_rho=1, **kw)
+    G[f"ldm/{ci}/out"] = out.numpy()
+np.savez_compressed(sys.argv[1], **G)
+""" % ROOT
+    out = os.path.join(OUT, 'ref_amed_taps.npz')
+    r = subprocess.run([sys.executable, '-c', code, out], capture_output=True, text=True, env=dict(os.environ))
+    if r.returncode != 0:
+        print(r.stdout[-2000:], r.stderr[-4000:])
+        raise SystemExit('AMED tap golden generation failed')
+    return out
+
+
 def ldm_part():
     """Stable-Diffusion-style eps-net + CFGPrecond from the real reference, loaded with oracle/ldm_oracle.make_params weights."""
     import types
@@ -281,6 +373,9 @@ def ldm_part():
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
+    if len(sys.argv) > 1 and sys.argv[1] == 'amed_taps':      # only the round-2 addition (the other fixtures are unchanged)
+        print('wrote', amed_taps_part())
+        raise SystemExit(0)
     G, meta = core()
     gits_part(G, meta)
     G['meta_json'] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
@@ -288,3 +383,4 @@ if __name__ == '__main__':
     print('wrote ref_core.npz with', len(G), 'arrays')
     print('wrote', amed_part())
     print('wrote', ldm_part())
+    print('wrote', amed_taps_part())

@@ -24,7 +24,7 @@ def digest(sd):
     return h.hexdigest()
 
 
-@pytest.mark.parametrize('name', ['song', 'adm_fp16'])
+@pytest.mark.parametrize('name', ['song', 'adm_fp16', 'song64'])
 def test_snapshot_matches_reference_state_dict(name):
     m = META[name]
     params, meta = CK.load_edm_pickle(os.path.join(GOLD, m['file']))
@@ -37,6 +37,10 @@ def test_snapshot_matches_reference_state_dict(name):
     spec = edm_nets.spec_from_params(params, meta['img_resolution'], meta['img_channels'], meta['label_dim'])
     assert spec.kind == ('song' if meta['model_type'] == 'SongUNet' else 'adm')
     assert len(spec.enc + spec.dec) > 0
+    if name == 'song64':        # wide enough for the native kernels: the snapshot lowers to a plan (what B200Net.from_pickle runs on the GPU)
+        wb, info = planner.pack_weights(spec, params)
+        pl = planner.compile_plan(spec, wb, info, 4, 1, 0)
+        assert pl.n_ops > 20 and pl.meta['n_gemm'] > 8
 
 
 def test_file_object_and_missing_key():

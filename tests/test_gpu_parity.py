@@ -223,8 +223,6 @@ def test_sampler_parity(name, solver, kw):
     from oracle import edm_oracle as O
     from oracle import solvers_oracle as SO
     from diff_sampler_b200 import solvers, solver_utils
-    if name == 'tiny_adm' and solver not in ('euler', 'dpm_pp', 'ipndm'):
-        pytest.skip('class-conditional net exercised on a subset of solvers')
     on, P, S = _oracle(name)
     nat = _native(P, S)
     B = 4
@@ -579,6 +577,278 @@ def test_sd15_fullsize_parity():
     err = (got - ref).abs().max().item()
     print(f'sd15 cfg 7.5 batch 1: err {err:.3e} (max|D| {ref.abs().max().item():.2f}); build+native {t1 - t0:.0f}s, oracle {time.time() - t1:.0f}s')
     assert err < TOL * max(1.0, ref.abs().max().item())
+
+
+def test_fused_uint8_image_epilogue_in_the_last_update():
+    """f1: `images_uint8=` makes the LAST update kernel of a sampling run also write (x * 127.5 + 128).clip(0, 255).uint8 in NHWC
+    (sample.py:311) -- bit-exact against the torch expression on the fp32 images the same call returns; samplers without a fused
+    final update (denoise_to_zero, UniPC) fall back to the one-pass conversion kernel with the same result."""
+    from oracle import edm_oracle as O
+    from diff_sampler_b200 import solvers
+    on, P, S = _oracle('tiny_song')
+    nat = _native(P, S)
+    B = 5
+    lat = O.stacked_randn(range(B), (3, 16, 16)).to(_dev())
+    for fn, kw in (('heun_sampler', dict(num_steps=4)), ('euler_sampler', dict(num_steps=4)), ('ipndm_sampler', dict(num_steps=5, max_order=3)),
+                   ('dpm_pp_sampler', dict(num_steps=5, max_order=2)), ('dpm_2_sampler', dict(num_steps=3)),
+                   ('euler_sampler', dict(num_steps=4, denoise_to_zero=True)), ('unipc_sampler', dict(num_steps=5))):
+        u8 = torch.full((B, 16, 16, 3), 7, dtype=torch.uint8, device=_dev())
+        l0 = __import__('diff_sampler_b200.solver_utils', fromlist=['LAUNCHES']).LAUNCHES[0]
+        img = getattr(solvers, fn)(nat, lat, images_uint8=u8, **kw)
+        n_launch = __import__('diff_sampler_b200.solver_utils', fromlist=['LAUNCHES']).LAUNCHES[0] - l0
+        plain = getattr(solvers, fn)(nat, lat, **kw)
+        assert torch.equal(img, plain)                                           # the fp32 result is unchanged
+        want = (img * 127.5 + 128).clip(0, 255).to(torch.uint8).permute(0, 2, 3, 1)
+        assert torch.equal(u8, want), (fn, kw, (u8.int() - want.int()).abs().max().item())
+        print(f'{fn} {kw}: uint8 image epilogue bit-exact ({n_launch} solver-kernel launches)')
+
+
+# --------------------------------------------------------------------------------------------- BASELINE configs as configured
+def test_config3_ffhq_ipndm_fullsize_sampler_parity():
+    """BASELINE config 3: EDM FFHQ-64 net (full size), iPNDM num_steps=7 (NFE=6), max_order=4 (4-term multistep history), final
+    images against the CPU oracle.  Checked for the library default (fp16x3) and for the mode bench.py runs this config in."""
+    import bench
+    from oracle import edm_oracle as O
+    from oracle import solvers_oracle as SO
+    from diff_sampler_b200 import solvers
+    from diff_sampler_b200.net import B200Net
+    on, P, S = _oracle('ffhq')
+    B = 2
+    lat = O.stacked_randn(range(B), (3, 64, 64))
+    kw = dict(num_steps=7, max_order=4, sigma_min=0.002, sigma_max=80, schedule_type='polynomial', schedule_rho=7)
+    ref = SO.sample(on, lat, 'ipndm', **kw)
+    modes = [('fp16x3', 0)]
+    bm = (bench.PRECISION_FOR['ffhq'], bench.F8_MIN_CHANNELS_FOR.get('ffhq', 0))
+    if bm not in modes:
+        modes.append(bm)
+    for prec, fmin in modes:
+        nat = B200Net(P, 64, 3, 0, precision=prec, f8_min_channels=fmin, device=_dev())
+        got = solvers.ipndm_sampler(nat, lat.to(_dev()), **kw).cpu()
+        err = (got - ref).abs().max().item()
+        print(f'ffhq ipndm NFE=6 {prec} f8_min_channels={fmin}: final-image max-abs err {err:.3e} (max|x| {ref.abs().max().item():.2f})')
+        assert err < TOL
+        del nat
+
+
+def test_config4_imagenet64_dpmpp_on_gits_schedule_parity():
+    """BASELINE config 4: ImageNet-64 class-conditional ADM net (full size), DPM-Solver++(2M) NFE=10 on a GITS schedule: t_steps are
+    picked from the 61-point polynomial teacher grid by the DP over the native teacher trajectories (gits_utils.get_dp_list, coeff 1.15),
+    so the grid is non-uniform; final images against the CPU oracle on the same t_steps, in the precision bench.py runs this config in."""
+    import bench
+    from oracle import edm_oracle as O
+    from oracle import solvers_oracle as SO
+    from diff_sampler_b200 import gits_utils, solver_utils, solvers
+    on, P, S = _oracle('imagenet64')
+    nat = _native(P, S, bench.PRECISION_FOR['imagenet64'])
+    kw = dict(dataset_name='imagenet64', num_warmup=4, max_batch_size=4, sigma_min=0.002, sigma_max=80, num_steps=11, num_steps_tea=61,
+              schedule_type='polynomial', schedule_rho=7, afs=False, metric='dev', coeff=1.15, model_source='edm', solver='dpmpp',
+              solver_tea='dpmpp', max_order=2, deis_mode='tab', prompt=None, guidance_rate=1.0, predict_x0=True, lower_order_final=True)
+    torch.manual_seed(0)
+    dp_list = gits_utils.get_dp_list(nat, _dev(), **kw)
+    print('GITS dp_list', dp_list)
+    assert len(dp_list) == 11 and dp_list[0] == 0 and dp_list[-1] == 60 and dp_list == sorted(set(dp_list))
+    t_steps = solver_utils.get_schedule(61, 0.002, 80, device=_dev(), schedule_type='polynomial', schedule_rho=7, dp_list=dp_list)
+    poly = solver_utils.get_schedule(11, 0.002, 80, device=_dev())
+    assert (t_steps - poly).abs().max().item() > 1e-3                      # not the plain 11-point polynomial grid
+    t_ref = SO.get_schedule(61, 0.002, 80, dp_list=dp_list)
+    assert torch.equal(t_steps.cpu(), t_ref)                               # integer gather: bit-exact
+    B = 2
+    lat = O.stacked_randn(range(B), (3, 64, 64))
+    lab = _labels(S, B)
+    skw = dict(num_steps=11, max_order=2, predict_x0=True, lower_order_final=True)
+    ref = SO.sample(on, lat, 'dpm_pp', class_labels=lab, t_steps=t_ref, **skw)
+    got = solvers.dpm_pp_sampler(nat, lat.to(_dev()), class_labels=lab.to(_dev()), t_steps=t_steps, **skw).cpu()
+    err = (got - ref).abs().max().item()
+    print(f'imagenet64 dpm_pp(2M) NFE=10 on GITS t_steps ({nat.precision}): final-image max-abs err {err:.3e} (max|x| {ref.abs().max().item():.2f})')
+    assert err < TOL
+
+
+AMED_ADM_CASES = [
+    ('amed', 'amed_sampler', dict(num_steps=4), dict(scale_dir=0.01, scale_time=0.2)),
+    ('dpm_pp', 'dpm_pp_sampler', dict(num_steps=4, max_order=2, predict_x0=True, afs=True), dict(scale_dir=0.01, scale_time=0.2)),
+    ('ipndm', 'ipndm_sampler', dict(num_steps=4, max_order=4, afs=True), dict(scale_dir=0.01, scale_time=0.0)),
+]
+AMED_LDM_CASES = [
+    (7.5, dict(num_steps=4, afs=True, max_order=2, predict_x0=False, lower_order_final=True), dict(scale_dir=0.0, scale_time=0.2)),
+    (7.5, dict(num_steps=3, afs=False, max_order=3, predict_x0=False, lower_order_final=True), dict(scale_dir=0.01, scale_time=0.2)),
+]
+
+
+def _amed_tap_case(group, ci):
+    import numpy as np
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_amed_taps.npz'))
+    pre = f'{group}/{ci}/pred/'
+    W = {k[len(pre):]: torch.from_numpy(d[k]) for k in d.files if k.startswith(pre)}
+    return d, W, torch.from_numpy(d[f'{group}/{ci}/out'])
+
+
+@pytest.mark.parametrize('ci', range(len(AMED_ADM_CASES)))
+def test_amed_class_conditional_tap_parity(ci):
+    """AMED samplers on a class-conditional EDM net: the predictor reads enc['8x8_block2'] (solvers_amed.py:16).  Native vs the oracle and
+    vs the REAL reference's recorded output (tests/golden/ref_amed_taps.npz)."""
+    from oracle import amed_oracle as AO
+    from oracle import edm_oracle as O
+    from diff_sampler_b200 import solvers_amed
+    from diff_sampler_b200.amed_predictor import AMEDPredictor
+    osolver, fn, kw, cfg = AMED_ADM_CASES[ci]
+    d, W, rec = _amed_tap_case('adm', ci)
+    on, P, S = _oracle('tiny_adm3')
+    nat = _native(P, S)
+    assert nat.spec.bottleneck_block.endswith('8x8_block2')
+    lat = O.stacked_randn(range(3), (3, 16, 16))
+    lab = torch.from_numpy(d['adm/labels'])
+    ref = AO.sample_amed(on, lat, osolver, W, cfg, class_labels=lab, **kw)
+    pred = AMEDPredictor(W, **cfg).to(_dev())
+    got = getattr(solvers_amed, fn)(nat, lat.to(_dev()), class_labels=lab.to(_dev()), AMED_predictor=pred, **kw).cpu()
+    e_or, e_ref = (got - ref).abs().max().item(), (got - rec).abs().max().item()
+    print(f'AMED {fn} on tiny_adm3 (8x8_block2 tap) {kw}: vs oracle {e_or:.3e}, vs recorded reference {e_ref:.3e}')
+    assert e_or < TOL and e_ref < TOL
+
+
+@pytest.mark.parametrize('ci', range(len(AMED_LDM_CASES)))
+def test_config5_amed_dpmpp_ldm_cfg_tap_parity(ci):
+    """BASELINE config 5's sampler/net pair: solvers_amed.dpm_pp_sampler (AMED plug-in on DPM-Solver++, afs, eps-prediction, 'discrete'
+    schedule rho=1; launch.sh:57-61) on a latent-diffusion net under classifier-free guidance 7.5: the predictor reads the channel mean
+    of middle_block's output, conditional half of the doubled batch (solvers_amed.py:11-12, :24-26).  Native vs oracle vs the REAL
+    reference's recorded output."""
+    from oracle import amed_oracle as AO
+    from oracle import edm_oracle as O
+    from diff_sampler_b200 import solvers_amed
+    from diff_sampler_b200.amed_predictor import AMEDPredictor
+    guidance, kw, cfg = AMED_LDM_CASES[ci]
+    d, W, rec = _amed_tap_case('ldm', ci)
+    on, nat, lcfg = _ldm_pair(guidance=guidance)
+    lat = O.stacked_randn(range(2), (4, 16, 16))
+    c, uc = torch.from_numpy(d['ldm/c']), torch.from_numpy(d['ldm/uc'])
+    common = dict(schedule_type='discrete', schedule_rho=1)
+    ref = AO.sample_amed(on, lat, 'dpm_pp', W, cfg, condition=c, unconditional_condition=uc, sigma_min=on.sigma_min, sigma_max=on.sigma_max,
+                         **common, **kw)
+    pred = AMEDPredictor(W, **cfg).to(_dev())
+    got = solvers_amed.dpm_pp_sampler(nat, lat.to(_dev()), condition=c.to(_dev()), unconditional_condition=uc.to(_dev()), AMED_predictor=pred,
+                                      sigma_min=nat.sigma_min, sigma_max=nat.sigma_max, **common, **kw).cpu()
+    scale = max(1.0, ref.abs().max().item())
+    e_or, e_ref = (got - ref).abs().max().item(), (got - rec).abs().max().item()
+    print(f'AMED dpm_pp on tiny_ldm cfg {guidance} {kw}: vs oracle {e_or:.3e}, vs recorded reference {e_ref:.3e} (max|x| {scale:.1f})')
+    assert e_or < TOL * scale and e_ref < TOL * scale
+
+
+# --------------------------------------------------------------------------------------------- the drop-in entry points
+def _module_from_params(P, cls_name, sub=None):
+    """An nn.Module stand-in carrying a flat parameter dict under the reference's state_dict names (class NAME as the reference's, which
+    is what as_native inspects).  `sub` = {dotted child path: class name} renames inner modules (e.g. {'model': 'SongUNet'})."""
+    import torch.nn as nn
+    sub = sub or {}
+    root = type(cls_name, (nn.Module,), {})()
+    for k, v in P.items():
+        parts = k.split('.')
+        m, path = root, ''
+        for part in parts[:-1]:
+            path = part if not path else path + '.' + part
+            if part not in m._modules:
+                m.add_module(part, type(sub.get(path, 'Node'), (nn.Module,), {})())
+            m = m._modules[part]
+        m.register_parameter(parts[-1], nn.Parameter(v.clone(), requires_grad=False))
+    return root
+
+
+@pytest.mark.parametrize('name', ['tiny_song', 'tiny_adm'])
+def test_dropin_as_native_and_from_reference(name):
+    """sample.py hands the samplers a torch EDMPrecond module (sample.py:301): `solvers.<x>_sampler(net, ...)` must compile it once
+    (as_native -> B200Net.from_reference), cache it, notice weight updates, and give the same images as B200Net(P, ...)."""
+    from oracle import edm_oracle as O
+    from diff_sampler_b200 import solvers
+    from diff_sampler_b200.net import B200Net
+    on, P, S = _oracle(name)
+    mod = _module_from_params(P, 'EDMPrecond', {'model': 'SongUNet' if S['kind'] == 'song' else 'DhariwalUNet'}).to(_dev())
+    mod.img_resolution, mod.img_channels, mod.label_dim = S['img_resolution'], S['img_channels'], S['label_dim']
+    mod.sigma_min, mod.sigma_max, mod.sigma_data, mod.use_fp16 = 0.002, 80.0, 0.5, False
+    direct = _native(P, S)
+    nat = solvers.as_native(mod)
+    assert isinstance(nat, B200Net) and solvers.as_native(mod) is nat                       # compiled once, cached on the module
+    viaref = B200Net.from_reference(mod, device=_dev())
+    B = 3
+    lat = O.stacked_randn(range(B), (3, 16, 16)).to(_dev())
+    lab = _labels(S, B)
+    labd = None if lab is None else lab.to(_dev())
+    a = solvers.heun_sampler(direct, lat, class_labels=labd, num_steps=4)
+    b = solvers.heun_sampler(mod, lat, class_labels=labd, num_steps=4)                      # the torch module itself, as sample.py passes it
+    c = solvers.heun_sampler(viaref, lat, class_labels=labd, num_steps=4)
+    assert torch.equal(a, b) and torch.equal(a, c)
+    ref = __import__('oracle.solvers_oracle', fromlist=['sample']).sample(on, lat.cpu(), 'heun', class_labels=lab, num_steps=4)
+    assert (b.cpu() - ref).abs().max().item() < TOL
+    # a weight update invalidates the cached snapshot (fingerprint = storage address + version counter of every tensor)
+    with torch.no_grad():
+        next(iter(mod.parameters())).mul_(1.0)
+    assert solvers.as_native(mod) is not nat
+    # other preconditioners are not compiled as EDM (their c_skip / c_out / c_noise differ): the object is returned unchanged
+    vp = _module_from_params(P, 'VPPrecond', {'model': 'SongUNet'})
+    assert solvers.as_native(vp) is vp
+
+
+def test_dropin_from_pickle():
+    """`B200Net.from_pickle(network-snapshot.pkl)` (what sample.py:81-82 unpickles) on the GPU: same denoiser output as B200Net built
+    from the snapshot's state_dict, and equal to the oracle on those weights.  The fixture (64-channel DDPM++ net, the narrowest the
+    native kernels run) was written by the real reference classes through torch_utils/persistence.py (oracle/gen_edm_pickle.py)."""
+    import json
+    from oracle import edm_oracle as O
+    from diff_sampler_b200 import checkpoint as CK
+    from diff_sampler_b200 import solvers
+    from diff_sampler_b200.net import B200Net
+    gold = os.path.join(os.path.dirname(__file__), 'golden')
+    meta = json.load(open(os.path.join(gold, 'edm_snapshot.json')))['song64']
+    path = os.path.join(gold, meta['file'])
+    net = B200Net.from_pickle(path, device=_dev())
+    params, m = CK.load_edm_pickle(path)
+    net2 = B200Net(params, m['img_resolution'], m['img_channels'], m['label_dim'], device=_dev())
+    R = m['img_resolution']
+    x = O.stacked_randn(range(4), (3, R, R)) * 2.0
+    sig = torch.tensor(2.0)
+    a = net(x.to(_dev()), sig.to(_dev())).cpu()
+    b = net2(x.to(_dev()), sig.to(_dev())).cpu()
+    assert torch.equal(a, b)
+    _, S = O.make_songunet(img_resolution=R, in_channels=3, out_channels=3, augment_dim=9, model_channels=64, channel_mult=(1,), num_blocks=1,
+                           attn_resolutions=(8,))
+    S['sigma_data'], S['sigma_min'], S['sigma_max'] = 0.5, 0.002, 80.0
+    on = O.OracleNet(params, S)
+    err = (a - on(x, sig)).abs().max().item()
+    print(f'from_pickle song64: D err vs oracle {err:.3e}')
+    assert err < TOL
+    lat = O.stacked_randn(range(4), (3, R, R))
+    from oracle import solvers_oracle as SO
+    got = solvers.euler_sampler(net, lat.to(_dev()), num_steps=5).cpu()
+    assert (got - SO.sample(on, lat, 'euler', num_steps=5)).abs().max().item() < TOL
+    assert (net.sigma_min, net.sigma_max) == (0.002, 80.0) and net.checkpoint_meta['class_name'] == 'EDMPrecond'
+
+
+def test_dropin_ldm_from_reference_and_as_native():
+    """A torch CFGPrecond module (net.model.model.diffusion_model = UNetModel, net.model.alphas_cumprod) handed to the samplers is
+    compiled by as_native -> B200LDMNet.from_reference and gives the images of B200LDMNet(P, ...)."""
+    from oracle import edm_oracle as O
+    from oracle import ldm_oracle as LO
+    from diff_sampler_b200 import solvers
+    from diff_sampler_b200.ldm_net import B200LDMNet
+    on, direct, cfg = _ldm_pair()
+    P, _ = LO.make_params('tiny_ldm')
+    mod = _module_from_params({'model.model.diffusion_model.' + k: v for k, v in P.items()}, 'CFGPrecond',
+                              {'model.model.diffusion_model': 'UNetModel'}).to(_dev())
+    mod.model.model.diffusion_model.num_heads = cfg['num_heads']
+    mod.model.alphas_cumprod = LO.make_alphas_cumprod()
+    mod.img_resolution, mod.img_channels, mod.label_dim = cfg['img_resolution'], cfg['in_channels'], True
+    mod.guidance_type, mod.guidance_rate = 'classifier-free', 7.5
+    nat = solvers.as_native(mod)
+    assert isinstance(nat, B200LDMNet) and solvers.as_native(mod) is nat
+    mod.sigma_min, mod.sigma_max = nat.sigma_min, nat.sigma_max
+    mod.sigma, mod.sigma_inv = nat.sigma, nat.sigma_inv                      # CFGPrecond methods the 'discrete' schedule calls (solver_utils.py:42-48)
+    B, R = 2, cfg['img_resolution']
+    lat = O.stacked_randn(range(B), (4, R, R)).to(_dev())
+    g = torch.Generator().manual_seed(7)
+    c = torch.randn(B, 77, cfg['context_dim'], generator=g).to(_dev())
+    uc = torch.randn(B, 77, cfg['context_dim'], generator=g).to(_dev())
+    kw = dict(condition=c, unconditional_condition=uc, num_steps=4, sigma_min=nat.sigma_min, sigma_max=nat.sigma_max, schedule_type='discrete',
+              schedule_rho=1, max_order=2, predict_x0=False)
+    a = solvers.dpm_pp_sampler(direct, lat, **kw)
+    b = solvers.dpm_pp_sampler(mod, lat, **kw)
+    assert torch.equal(a, b)
 
 
 # --------------------------------------------------------------------------------------------- first-stage decoder (opt-in)

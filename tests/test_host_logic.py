@@ -338,3 +338,54 @@ def float_eq(a, b):
         return float(a) == float(b)
     except ValueError:
         return False
+
+
+def test_as_native_compiles_only_known_preconditioners_and_tracks_weight_updates(monkeypatch):
+    """solvers.as_native (the drop-in entry sample.py's `sampler_fn(net, ...)` goes through): EDMPrecond over SongUNet/DhariwalUNet and
+    CFGPrecond over a UNetModel are compiled once and cached with a weight fingerprint; other preconditioners are left alone."""
+    import torch.nn as nn
+    from diff_sampler_b200 import solvers
+    from diff_sampler_b200.ldm_net import B200LDMNet
+    from diff_sampler_b200.net import B200Net
+
+    def mk(cls_name, inner_name, path='model'):
+        root = type(cls_name, (nn.Module,), {})()
+        m = root
+        parts = path.split('.')
+        for i, part in enumerate(parts):
+            child = type(inner_name if i == len(parts) - 1 else 'Node', (nn.Module,), {})()
+            m.add_module(part, child)
+            m = child
+        m.register_parameter('w', nn.Parameter(torch.ones(3), requires_grad=False))
+        return root
+    made = []
+    monkeypatch.setattr(B200Net, 'from_reference', classmethod(lambda cls, net, **kw: made.append(('edm', kw)) or object.__new__(B200Net)))
+    monkeypatch.setattr(B200LDMNet, 'from_reference', classmethod(lambda cls, net, **kw: made.append(('ldm', kw)) or object.__new__(B200LDMNet)))
+    edm = mk('EDMPrecond', 'SongUNet')
+    a = solvers.as_native(edm)
+    assert isinstance(a, B200Net) and solvers.as_native(edm) is a and len(made) == 1
+    with torch.no_grad():
+        edm.model.w.add_(1.0)                                   # in-place update (optimizer / EMA / load_state_dict): version counter moves
+    b = solvers.as_native(edm)
+    assert b is not a and len(made) == 2
+    solvers.invalidate_native(edm)
+    assert solvers.as_native(edm) is not b and len(made) == 3
+    for other in ('VPPrecond', 'VEPrecond', 'iDDPMPrecond'):    # different c_skip / c_out / c_noise: never evaluated as EDM
+        m = mk(other, 'SongUNet')
+        assert solvers.as_native(m) is m
+    assert len(made) == 3
+    cfg = mk('CFGPrecond', 'UNetModel', 'model.model.diffusion_model')
+    cfg.guidance_type = 'classifier-free'
+    c = solvers.as_native(cfg)
+    assert isinstance(c, B200LDMNet) and made[-1][0] == 'ldm' and solvers.as_native(cfg) is c
+    fn = lambda x, s: x
+    assert solvers.as_native(fn) is fn
+
+
+def test_solver_update_rejects_missing_history_and_miscounted_coefficients():
+    from diff_sampler_b200 import solver_utils as U
+    x = torch.zeros(2, 4)
+    with pytest.raises(ValueError, match='None'):
+        U.solver_update(x, x, [1.0, 0.0, 0.5], hist=[None])
+    with pytest.raises(ValueError, match='coefficients'):
+        U.solver_update(x, x, [1.0, 0.0, 0.5, 0.5], hist=[x])

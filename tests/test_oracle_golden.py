@@ -161,6 +161,54 @@ def test_amed_samplers_match_reference(ci):
     assert err <= 2e-5 * max(1.0, np.abs(ref).max()), (solver, kw, err)
 
 
+# AMED on the two other bottleneck taps (round 2): class-conditional EDM net -> enc['8x8_block2']; latent diffusion under
+# classifier-free guidance -> middle_block, conditional half (amed-solver-main/solvers_amed.py:11-16, :24-26).
+AMED_ADM_CASES = [
+    ('amed', dict(num_steps=4), dict(scale_dir=0.01, scale_time=0.2)),
+    ('dpm_pp', dict(num_steps=4, max_order=2, predict_x0=True, afs=True), dict(scale_dir=0.01, scale_time=0.2)),
+    ('ipndm', dict(num_steps=4, max_order=4, afs=True), dict(scale_dir=0.01, scale_time=0.0)),
+]
+AMED_LDM_CASES = [
+    (7.5, dict(num_steps=4, afs=True, max_order=2, predict_x0=False, lower_order_final=True), dict(scale_dir=0.0, scale_time=0.2)),   # launch.sh:57-61
+    (7.5, dict(num_steps=3, afs=False, max_order=3, predict_x0=False, lower_order_final=True), dict(scale_dir=0.01, scale_time=0.2)),
+]
+
+
+def load_amed_tap_case(group, ci):
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_amed_taps.npz'))
+    pre = f'{group}/{ci}/pred/'
+    W = {k[len(pre):]: torch.from_numpy(d[k]) for k in d.files if k.startswith(pre)}
+    return d, W, d[f'{group}/{ci}/out']
+
+
+@pytest.mark.parametrize('ci', range(len(AMED_ADM_CASES)))
+def test_amed_class_conditional_tap_matches_reference(ci):
+    from oracle import amed_oracle as AO
+    solver, kw, cfg = AMED_ADM_CASES[ci]
+    d, W, ref = load_amed_tap_case('adm', ci)
+    P, S = O.make_net('tiny_adm3', seed=0, dezero=True)
+    net = O.OracleNet(P, S)
+    lat = O.stacked_randn(range(3), (3, 16, 16))
+    got = AO.sample_amed(net, lat, solver, W, cfg, class_labels=torch.from_numpy(d['adm/labels']), **kw).numpy()
+    err = np.abs(got - ref).max()
+    assert err <= 2e-5 * max(1.0, np.abs(ref).max()), (solver, kw, err)
+
+
+@pytest.mark.parametrize('ci', range(len(AMED_LDM_CASES)))
+def test_amed_ldm_cfg_tap_matches_reference(ci):
+    from oracle import amed_oracle as AO
+    from oracle import ldm_oracle as LO
+    guidance, kw, cfg = AMED_LDM_CASES[ci]
+    d, W, ref = load_amed_tap_case('ldm', ci)
+    P, lcfg = LO.make_params('tiny_ldm')
+    net = LO.OracleCFGNet(P, lcfg, guidance_rate=guidance)
+    lat = O.stacked_randn(range(2), (4, 16, 16))
+    got = AO.sample_amed(net, lat, 'dpm_pp', W, cfg, condition=torch.from_numpy(d['ldm/c']), unconditional_condition=torch.from_numpy(d['ldm/uc']),
+                         sigma_min=net.sigma_min, sigma_max=net.sigma_max, schedule_type='discrete', schedule_rho=1, **kw).numpy()
+    err = np.abs(got - ref).max()
+    assert err <= 2e-5 * max(1.0, np.abs(ref).max()), (kw, err)
+
+
 def test_ldm_oracle_matches_reference():
     """Stable-Diffusion-style eps-net + CFGPrecond (tiny config, same structure as v1.5) vs outputs of the real reference classes."""
     from oracle import ldm_oracle as LO
