@@ -47,7 +47,7 @@ class GnStatsDesc(C.Structure):
 class GnApplyDesc(C.Structure):
     _fields_ = [('src0', P), ('src1', P), ('C0', I32), ('C1', I32), ('H', I32), ('W', I32), ('B', I32), ('groups', I32),
                 ('sums', P), ('gamma', P), ('beta', P), ('eps', F32), ('silu', I32), ('ada', P), ('ada_stride', I64),
-                ('resample', I32), ('nplanes', I32), ('out_act', P), ('out_raw', P), ('out_raw_f32', P), ('fmt', I32), ('pad0', I32)]
+                ('resample', I32), ('nplanes', I32), ('out_act', P), ('out_raw', P), ('out_raw_f32', P), ('fmt', I32), ('pad0', I32), ('coef', P)]
 
 
 class SoftmaxDesc(C.Structure):
@@ -83,7 +83,7 @@ class GegluDesc(C.Structure):
 
 class GnFinalizeDesc(C.Structure):
     _fields_ = [('quads0', P), ('quads1', P), ('C0', I32), ('C1', I32), ('slabs_per_sample', I32), ('B', I32), ('groups', I32),
-                ('pad0', I32), ('sums', P)]
+                ('pad0', I32), ('sums', P), ('gamma', P), ('beta', P), ('ada', P), ('ada_stride', I64), ('eps', F32), ('HW', I32), ('coef', P)]
 
 
 class AttnDesc(C.Structure):

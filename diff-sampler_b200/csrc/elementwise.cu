@@ -69,24 +69,55 @@ __global__ void gn_stats_kernel(ds_gn_stats_desc d, int pix_per_cta) {
 // it over the sample's slabs in fp64 (coalesced along t).  Step 2: thread j < 2*groups adds the cpg/4 quads of its group.
 __global__ void __launch_bounds__(256) gn_finalize_kernel(ds_gn_finalize_desc d) {
     extern __shared__ double s_cols[];
+    __shared__ float s_mu[64], s_rstd[64];
     const int n = blockIdx.x;
-    const int w0 = d.C0 / 2, w1 = d.C1 / 2;           // floats per partial row of each source
-    for (int t = threadIdx.x; t < w0 + w1; t += blockDim.x) {
-        const float* src = (t < w0) ? d.quads0 + (long long)n * d.slabs_per_sample * w0 + t
-                                    : d.quads1 + (long long)n * d.slabs_per_sample * w1 + (t - w0);
-        const int pitch = (t < w0) ? w0 : w1;
-        double acc = 0.0;
+    const int C = d.C0 + d.C1;
+    if (d.quads0) {
+        const int w0 = d.C0 / 2, w1 = d.C1 / 2;           // floats per partial row of each source
+        for (int t = threadIdx.x; t < w0 + w1; t += blockDim.x) {
+            const float* src = (t < w0) ? d.quads0 + (long long)n * d.slabs_per_sample * w0 + t
+                                        : d.quads1 + (long long)n * d.slabs_per_sample * w1 + (t - w0);
+            const int pitch = (t < w0) ? w0 : w1;
+            double acc = 0.0;
 #pragma unroll 8
-        for (int sl = 0; sl < d.slabs_per_sample; ++sl) acc += (double)__ldg(src + (long long)sl * pitch);
-        s_cols[t] = acc;
+            for (int sl = 0; sl < d.slabs_per_sample; ++sl) acc += (double)__ldg(src + (long long)sl * pitch);
+            s_cols[t] = acc;
+        }
+        __syncthreads();
+        const int qpg = C / d.groups / 4;                 // quads per group
+        for (int j = threadIdx.x; j < 2 * d.groups; j += blockDim.x) {
+            const int g = j >> 1, k = j & 1;
+            double acc = 0.0;
+            for (int q = g * qpg; q < (g + 1) * qpg; ++q) acc += s_cols[2 * q + k];
+            d.sums[((long long)n * d.groups + g) * 2 + k] = acc;
+        }
+        __syncthreads();
+    }
+    if (!d.coef) return;
+    // second product: y = x * a + b per (sample, channel), so that gn_apply starts streaming without an fp64 prologue per thread
+    const double cnt = (double)(C / d.groups) * d.HW;
+    for (int g = threadIdx.x; g < d.groups; g += blockDim.x) {
+        const double s = d.sums[((long long)n * d.groups + g) * 2 + 0];
+        const double q = d.sums[((long long)n * d.groups + g) * 2 + 1];
+        const double mu = s / cnt;
+        double var = q / cnt - mu * mu;
+        if (var < 0.0) var = 0.0;
+        s_mu[g] = (float)mu;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)d.eps));
     }
     __syncthreads();
-    const int qpg = (d.C0 + d.C1) / d.groups / 4;     // quads per group
-    for (int j = threadIdx.x; j < 2 * d.groups; j += blockDim.x) {
-        const int g = j >> 1, k = j & 1;
-        double acc = 0.0;
-        for (int q = g * qpg; q < (g + 1) * qpg; ++q) acc += s_cols[2 * q + k];
-        d.sums[((long long)n * d.groups + g) * 2 + k] = acc;
+    const int cpg = C / d.groups;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / cpg;
+        float aa = s_rstd[g] * __ldg(d.gamma + c);
+        float bb = __ldg(d.beta + c);
+        if (d.ada) {
+            const float sc = d.ada[(long long)n * d.ada_stride + c] + 1.0f;
+            const float sh = d.ada[(long long)n * d.ada_stride + C + c];
+            aa *= sc;
+            bb = bb * sc + sh;
+        }
+        reinterpret_cast<float2*>(d.coef)[(long long)n * C + c] = make_float2(aa, fmaf(-s_mu[g], aa, bb));
     }
 }
 
@@ -364,6 +395,53 @@ __global__ void __launch_bounds__(512) gn_apply_v2_kernel(ds_gn_apply_desc d, in
     int po = p_begin + prow;
     for (; po + 3 * rows < p_end; po += 4 * rows) gn_v2_pixels<4>(d, base, pitch, n, npix, C, c, plane, po, rows, norm, a, b, oact, oraw);
     for (; po < p_end; po += rows) gn_v2_pixels<1>(d, base, pitch, n, npix, C, c, plane, po, rows, norm, a, b, oact, oraw);
+}
+
+// Round 2 (resample == 0 with precomputed coefficients, ds_gn_apply_desc.coef): the v2 inner loop inside a PERSISTENT, EVENLY SPLIT grid.
+// v2 launched one CTA per (sample, 16-pixels-per-thread chunk): 4096 CTAs over 148 x 8 slots = 3.46 waves (a 13 % tail), each thread
+// paying an fp64 mean / rsqrt prologue for 16 pixels of work -- 76 % of the copy bandwidth.  Here the (sample, pixel
+// row) space is cut into gridDim.x equal ranges (+-1 row), the grid is exactly the number of co-resident CTAs, and a thread fetches its
+// 16 coefficients (4 x 16 B, L2-resident table written by gn_finalize) only when its range crosses into another sample.
+__global__ void __launch_bounds__(512) gn_apply_v3_kernel(ds_gn_apply_desc d, int nc8, int rows, int units_per_sample, long long total_units) {
+    const int C = d.C0 + d.C1;
+    const int c8 = threadIdx.x % nc8;
+    const int prow = threadIdx.x / nc8;
+    const int c = c8 * 8;
+    const int npix = d.H * d.W;
+    const long long plane = (long long)d.B * npix * C;
+    const float* base0;
+    int pitch, cc;
+    if (c < d.C0) { base0 = d.src0; pitch = d.C0; cc = c; }
+    else { base0 = d.src1; pitch = d.C1; cc = c - d.C0; }
+    __half* oact = reinterpret_cast<__half*>(d.out_act);
+    __half* oraw = reinterpret_cast<__half*>(d.out_raw);
+    long long u = total_units * blockIdx.x / gridDim.x;
+    const long long u_end = total_units * (blockIdx.x + 1) / gridDim.x;
+    float a[8], b[8];
+    while (u < u_end) {
+        const int n = (int)(u / units_per_sample);
+        const int uin = (int)(u - (long long)n * units_per_sample);
+        long long seg_end = (long long)(n + 1) * units_per_sample;
+        if (seg_end > u_end) seg_end = u_end;
+        const int nun = (int)(seg_end - u);
+        {
+            const float4* cf = reinterpret_cast<const float4*>(d.coef + ((long long)n * C + c) * 2);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = __ldg(cf + j);
+                a[2 * j] = t.x; b[2 * j] = t.y; a[2 * j + 1] = t.z; b[2 * j + 1] = t.w;
+            }
+        }
+        const float* base = base0 + (long long)n * npix * pitch + cc;
+        int po = uin * rows + prow;                      // pixel of this thread in the first unit of the segment
+        int k = 0;
+        // whole units only: the last unit of a sample may be partial when rows does not divide H*W
+        const int full = ((uin + nun) * rows <= npix) ? nun : nun - 1;
+        for (; k + 4 <= full; k += 4, po += 4 * rows) gn_v2_pixels<4>(d, base, pitch, n, npix, C, c, plane, po, rows, true, a, b, oact, oraw);
+        for (; k < full; ++k, po += rows) gn_v2_pixels<1>(d, base, pitch, n, npix, C, c, plane, po, rows, true, a, b, oact, oraw);
+        if (k < nun && po < npix) gn_v2_pixels<1>(d, base, pitch, n, npix, C, c, plane, po, rows, true, a, b, oact, oraw);
+        u = seg_end;
+    }
 }
 
 // ------------------------------------------------------------------------------------------ softmax
@@ -790,8 +868,11 @@ extern "C" int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream
 
 extern "C" int ds_gn_finalize_launch(const ds_gn_finalize_desc* d, cudaStream_t stream) {
     const int C = d->C0 + d->C1;
-    if (d->C0 % 4 || d->C1 % 4 || d->groups <= 0 || C % d->groups || (C / d->groups) % 4 || (d->C1 > 0 && !d->quads1)) return -2;
-    gn_finalize_kernel<<<d->B, 256, (size_t)(C / 2) * sizeof(double), stream>>>(*d);
+    if (d->groups <= 0 || d->groups > 64 || C % d->groups) return -2;
+    if (d->quads0 && (d->C0 % 4 || d->C1 % 4 || (C / d->groups) % 4 || (d->C1 > 0 && !d->quads1))) return -2;
+    if (!d->quads0 && !d->coef) return -2;               // nothing to do
+    if (d->coef && (!d->gamma || !d->beta || d->HW <= 0)) return -2;
+    gn_finalize_kernel<<<d->B, 256, (size_t)(C / 2 + 1) * sizeof(double), stream>>>(*d);
     return ok();
 }
 
@@ -812,6 +893,29 @@ extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream
     while (pix_per_cta > rows && (long long)((npix + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
     const int chunks = (npix + pix_per_cta - 1) / pix_per_cta;
     dim3 grid(chunks, d->B);
+    if (d->coef && d->resample == 0 && d->sums == nullptr) {
+        // persistent variant: grid = co-resident CTAs (occupancy query per block size and device, cached)
+        static int occ[64][17] = {};
+        static int sms[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64) dev = 0;
+        const int slot = threads / 32;
+        if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        if (!occ[dev][slot]) {
+            int nb = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_apply_v3_kernel, threads, 0) != cudaSuccess || nb < 1) nb = 1;
+            occ[dev][slot] = nb;
+        }
+        const int ups = (npix + rows - 1) / rows;
+        const long long total_units = (long long)ups * d->B;
+        long long g3 = (long long)sms[dev] * occ[dev][slot];
+        const long long min_units = 8;                        // at least ~8 pixel rows per CTA
+        if (g3 > (total_units + min_units - 1) / min_units) g3 = (total_units + min_units - 1) / min_units;
+        if (g3 < 1) g3 = 1;
+        gn_apply_v3_kernel<<<(unsigned)g3, threads, 0, stream>>>(*d, nc8, rows, ups, total_units);
+        return ok();
+    }
     static const int use_v2 = [] { const char* e = getenv("DSB_GN_APPLY_V2"); return e ? atoi(e) : 1; }();
     if (use_v2 && d->resample == 0) {
         gn_apply_v2_kernel<<<grid, threads, 0, stream>>>(*d, pix_per_cta, nc8, rows);

@@ -61,6 +61,15 @@ struct ds_unet {
     bool profiling = false;
     std::vector<cudaEvent_t> ev0, ev1;
     std::vector<char> ev_used;
+    // optional CUDA-graph replay of the op list (ds_unet_enable_graph): the io slots are staged through fixed device buffers so that one
+    // instantiated graph serves every call; [0] = without, [1] = with the bottleneck read-out
+    bool graph_on = false;
+    void* stage[DS_IO_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[DS_IO_COUNT] = {0, 0, 0, 0, 0, 0};
+    cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+    int gnodes[2] = {0, 0};
+    int warm_runs = 0;
+    cudaStream_t cap_stream = nullptr;
 };
 
 template <class F>
@@ -76,7 +85,7 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_GN_STATS: { auto& d = op.u.gn_stats; P(d.src0); P(d.src1); P(d.sums); break; }
         case DS_OP_GN_APPLY: {
             auto& d = op.u.gn_apply;
-            P(d.src0); P(d.src1); P(d.sums); P(d.gamma); P(d.beta); P(d.ada); P(d.out_act); P(d.out_raw); P(d.out_raw_f32);
+            P(d.src0); P(d.src1); P(d.sums); P(d.gamma); P(d.beta); P(d.ada); P(d.out_act); P(d.out_raw); P(d.out_raw_f32); P(d.coef);
             break;
         }
         case DS_OP_SOFTMAX: { auto& d = op.u.softmax; P(d.S); P(d.P); break; }
@@ -87,7 +96,7 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_MEMSET: { auto& d = op.u.memset; P(d.ptr); break; }
         case DS_OP_LAYERNORM: { auto& d = op.u.layernorm; P(d.src); P(d.gamma); P(d.beta); P(d.out); break; }
         case DS_OP_GEGLU: { auto& d = op.u.geglu; P(d.src); P(d.out); break; }
-        case DS_OP_GN_FINALIZE: { auto& d = op.u.gn_finalize; P(d.quads0); P(d.quads1); P(d.sums); break; }
+        case DS_OP_GN_FINALIZE: { auto& d = op.u.gn_finalize; P(d.quads0); P(d.quads1); P(d.sums); P(d.gamma); P(d.beta); P(d.ada); P(d.coef); break; }
         case DS_OP_ATTN: { auto& d = op.u.attn; P(d.q); P(d.k); P(d.vt); P(d.out); break; }
         default: break;
     }
@@ -220,6 +229,9 @@ void ds_unet_destroy(ds_unet* u) {
     if (!u) return;
     for (auto e : u->ev0) cudaEventDestroy(e);
     for (auto e : u->ev1) cudaEventDestroy(e);
+    for (int v = 0; v < 2; ++v) if (u->gexec[v]) cudaGraphExecDestroy(u->gexec[v]);
+    for (int k = 0; k < DS_IO_COUNT; ++k) if (u->stage[k]) cudaFree(u->stage[k]);
+    if (u->cap_stream) cudaStreamDestroy(u->cap_stream);
     cudaFree(u->arena);
     delete u;
 }
@@ -232,12 +244,8 @@ int ds_unet_forward(ds_unet* u, const float* x, const float* sigma, const float*
     return ds_unet_forward_io(u, io, DS_IO_COUNT, stream);
 }
 
-int ds_unet_forward_io(ds_unet* u, const void* const* io_in, int n_io, void* stream) {
-    if (!u) return fail(-1, "ds_unet_forward: null handle");
-    NvtxRange nvtx_range("ds_unet_forward");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const void* io[DS_IO_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    for (int k = 0; k < n_io && k < DS_IO_COUNT; ++k) io[k] = io_in[k];
+// Launch the op list on `s` with the io slots bound to `io`.  Returns the number of launches, or a negative code.
+static int run_ops(ds_unet* u, const void* const* io, cudaStream_t s, bool profiling) {
     for (const IoFix& fx : u->fixes) {
         if (fx.slot < 0 || fx.slot >= DS_IO_COUNT) return fail(-7, "ds_unet_forward: bad io slot");
         void** field = reinterpret_cast<void**>(reinterpret_cast<char*>(&u->ops[fx.op]) + fx.field_off);
@@ -255,9 +263,9 @@ int ds_unet_forward_io(ds_unet* u, const void* const* io_in, int n_io, void* str
             kp = al;
         }
         if (op.type == DS_OP_CHANMEAN && op.u.chanmean.out == nullptr) continue;   // bottleneck tap not requested
-        if (u->profiling) { cudaEventRecord(u->ev0[i], s); u->ev_used[i] = 1; }
+        if (profiling) { cudaEventRecord(u->ev0[i], s); u->ev_used[i] = 1; }
         int rc = launch_op(op, kp, s);
-        if (u->profiling) cudaEventRecord(u->ev1[i], s);
+        if (profiling) cudaEventRecord(u->ev1[i], s);
         if (rc) {
             char buf[160];
             snprintf(buf, sizeof buf, "ds_unet_forward: op %zu (type %d tag %d) failed rc=%d cuda=%s", i, op.type, op.tag, rc,
@@ -266,7 +274,90 @@ int ds_unet_forward_io(ds_unet* u, const void* const* io_in, int n_io, void* str
         }
         ++launches;
     }
+    return launches;
+}
+
+// Capture the op list (io slots bound to the staging buffers) into a graph on the private capture stream and instantiate it.
+static int build_graph(ds_unet* u, int variant, const void* const* staged_io) {
+    if (!u->cap_stream && cudaStreamCreateWithFlags(&u->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return fail(-20, "ds_unet_forward: cannot create the capture stream");
+    if (cudaStreamBeginCapture(u->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        return fail(-21, std::string("ds_unet_forward: cudaStreamBeginCapture failed: ") + cudaGetErrorString(cudaGetLastError()));
+    const int n = run_ops(u, staged_io, u->cap_stream, false);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(u->cap_stream, &g);
+    if (n < 0 || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        if (n < 0) return n;
+        return fail(-22, std::string("ds_unet_forward: stream capture failed: ") + cudaGetErrorString(e));
+    }
+    cudaGraphExec_t ex = nullptr;
+    const cudaError_t ei = cudaGraphInstantiate(&ex, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) return fail(-23, std::string("ds_unet_forward: cudaGraphInstantiate failed: ") + cudaGetErrorString(ei));
+    u->gexec[variant] = ex;
+    u->gnodes[variant] = n;
+    return 0;
+}
+
+int ds_unet_forward_io(ds_unet* u, const void* const* io_in, int n_io, void* stream) {
+    if (!u) return fail(-1, "ds_unet_forward: null handle");
+    NvtxRange nvtx_range("ds_unet_forward");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const void* io[DS_IO_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < n_io && k < DS_IO_COUNT; ++k) io[k] = io_in[k];
+    if (!u->graph_on || u->profiling) {
+        const int n = run_ops(u, io, s, u->profiling);
+        if (n < 0) return n;
+        u->last_launches = n;
+        return 0;
+    }
+    // ---- graph replay: inputs -> staging (device-to-device, same stream), one cudaGraphLaunch, staging -> outputs
+    static const bool is_input[DS_IO_COUNT] = {true, false, true, true, false, true};       // X, D, SIGMA, LABELS, BOTTLENECK, CTX
+    const void* staged[DS_IO_COUNT];
+    for (int k = 0; k < DS_IO_COUNT; ++k) {
+        staged[k] = (io[k] && u->stage[k]) ? u->stage[k] : nullptr;
+        if (io[k] && !u->stage[k]) return fail(-24, "ds_unet_forward: io slot used without a staging buffer (ds_unet_enable_graph sizes)");
+        if (io[k] && is_input[k] &&
+            cudaMemcpyAsync(u->stage[k], io[k], u->stage_bytes[k], cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            return fail(-25, "ds_unet_forward: staging copy failed");
+    }
+    const int variant = io[DS_IO_BOTTLENECK] ? 1 : 0;
+    int launches = 0;
+    if (!u->gexec[variant]) {
+        if (u->warm_runs < 1) {
+            // first call: plain launches (sets the per-device function attributes outside any capture)
+            launches = run_ops(u, staged, s, false);
+            if (launches < 0) return launches;
+            ++u->warm_runs;
+        } else {
+            const int rc = build_graph(u, variant, staged);
+            if (rc) return rc;
+        }
+    }
+    if (u->gexec[variant]) {
+        if (cudaGraphLaunch(u->gexec[variant], s) != cudaSuccess)
+            return fail(-26, std::string("ds_unet_forward: cudaGraphLaunch failed: ") + cudaGetErrorString(cudaGetLastError()));
+        launches = u->gnodes[variant];
+    }
+    for (int k = 0; k < DS_IO_COUNT; ++k)
+        if (io[k] && !is_input[k] &&
+            cudaMemcpyAsync(const_cast<void*>(io[k]), u->stage[k], u->stage_bytes[k], cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+            return fail(-25, "ds_unet_forward: staging copy failed");
     u->last_launches = launches;
+    return 0;
+}
+
+int ds_unet_enable_graph(ds_unet* u, const size_t* io_bytes, int n_io) {
+    if (!u || !io_bytes) return fail(-1, "ds_unet_enable_graph: null argument");
+    if (u->graph_on) return 0;
+    for (int k = 0; k < n_io && k < DS_IO_COUNT; ++k) {
+        if (!io_bytes[k]) continue;
+        if (cudaMalloc(&u->stage[k], io_bytes[k]) != cudaSuccess)
+            return fail(-2, std::string("ds_unet_enable_graph: cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError()));
+        u->stage_bytes[k] = io_bytes[k];
+    }
+    u->graph_on = true;
     return 0;
 }
 
@@ -374,6 +465,15 @@ int ds_gits_cost(const float* traj, const float* eps, const float* t_steps, doub
     d.traj = traj; d.eps = eps; d.t = t_steps; d.out = out; d.N = N; d.B = B; d.n = n_per_sample;
     int rc = ds_gits_cost_launch(&d, static_cast<cudaStream_t>(stream));
     if (rc) return fail(rc, std::string("ds_gits_cost: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+int ds_amed_predict(const float* weights, const int* dims6, const float* bottleneck, const float* t_cur, const float* t_next,
+                    float scale_dir, float scale_time, float* out4, int B, void* stream) {
+    if (!weights || !dims6 || !t_cur || !t_next || !out4) return fail(-1, "ds_amed_predict: null argument");
+    NvtxRange nvtx_range("ds_amed_predict");
+    int rc = ds_amed_predict_launch(weights, dims6, bottleneck, t_cur, t_next, scale_dir, scale_time, out4, B, static_cast<cudaStream_t>(stream));
+    if (rc) return fail(rc, std::string("ds_amed_predict: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
 

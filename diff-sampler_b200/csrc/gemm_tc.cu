@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------ CTA-pair variant (opt-in: DSB_GEMM_2CTA=1)
+// ------------------------------------------------------------------------------------------ CTA-pair variant (large convolutions; DSB_GEMM_2CTA=0 disables)
 // Same roles and pipelines over a cluster of two CTAs (one TPC): the pair owns 256 output rows (M tiles 2*pm + rank) x BN columns; each
 // CTA loads its own 128-row A tile and HALF of the B tile, the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) whose
 // accumulator halves land in the two CTAs' TMEM, and each CTA's epilogue warps drain their own half.  Per 64-channel K block a pair pulls
@@ -758,7 +758,9 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     int stage_bytes = kATileBytes + d->BN * 128;
     // CTA-pair variant (opt-in): convolution GEMMs with at least two full waves of row pairs and an N tile that splits into two
     // whole 32-row halves; everything else keeps the single-CTA kernel
-    static const int pair_env = [] { const char* e = getenv("DSB_GEMM_2CTA"); return e ? atoi(e) : 0; }();
+    // default ON since round 2: bit-identical to the single-CTA kernel (tests/test_gpu_kernels.py::test_conv_pair_kernel) and +2.8 % images/s on the
+    // power-capped sustained bench (profiles/r02b: 513.2 vs 499.0): a third fewer operand bytes through L2 / shared memory per FLOP.
+    static const int pair_env = [] { const char* e = getenv("DSB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
     const bool pair_forced = (d->f8 & 2) != 0;          // bit 1 of ds_gemm_desc.f8: request the pair kernel for this launch (tests, A/B)
     if ((pair_forced || (pair_env && d->m_tiles >= 4 * 148 && d->BN >= 64)) && d->a_mode == 0 && d->num_z == 1 && d->BN % 32 == 0 &&
         all_tap_cb_zero(d)) {

@@ -138,6 +138,10 @@ typedef struct ds_gn_apply_desc {
     float* out_raw_f32;     // fp32 raw input at output resolution; may be NULL
     int32_t fmt;            // 0: fp16 hi/lo planes.  1: operand layout of an f8 GEMM (ds_gemm_desc.f8), for out_act and out_raw
     int32_t pad0;
+    // Precomputed per-(sample, channel) coefficients [B][C][2] = {a, b} with y = x * a + b  (a = rstd * gamma * (1 + ada_scale),
+    // b = beta * (1 + ada_scale) + ada_shift - mean * a), written by ds_gn_finalize.  When set (resample == 0 only) the kernel reads
+    // them instead of deriving them from `sums` in an fp64 prologue per thread, and runs the persistent, evenly split variant.
+    const float* coef;
 } ds_gn_apply_desc;
 
 // GroupNorm statistics from the quad partials written by the producing GEMM epilogues (ds_gemm_desc.st_quads) of the one or two
@@ -149,9 +153,17 @@ typedef struct ds_gn_finalize_desc {
     int32_t C0, C1;
     int32_t slabs_per_sample;   // H*W / 32
     int32_t B;
-    int32_t groups;         // (C0 + C1) / groups must be a multiple of 4
+    int32_t groups;         // (C0 + C1) / groups must be a multiple of 4 (when quads0 != NULL)
     int32_t pad0;
-    double* sums;           // [B][groups][2], overwritten
+    double* sums;           // [B][groups][2]: overwritten from the quads; with quads0 == NULL it is the INPUT (written by ds_gn_stats)
+    // optional second product (coef != NULL): the per-(sample, channel) coefficients ds_gn_apply_desc.coef describes
+    const float* gamma;
+    const float* beta;
+    const float* ada;       // adaptive [nE][2*C] (scale | shift), NULL if unused
+    int64_t ada_stride;
+    float eps;
+    int32_t HW;             // pixels per sample (statistics count = HW * C / groups)
+    float* coef;            // [B][C0 + C1][2]
 } ds_gn_finalize_desc;
 
 // Fused softmax attention, head dim padded to 64 (attention.cu): out[b][l][h*64 + c] = sum_k softmax_k(scale * q_l . k_k) v_k[c].
@@ -306,6 +318,8 @@ typedef struct ds_gits_cost_desc {
 } ds_gits_cost_desc;
 
 int ds_gits_cost_launch(const ds_gits_cost_desc* d, cudaStream_t stream);
+int ds_amed_predict_launch(const float* w, const int* dims6, const float* bott, const float* t_cur, const float* t_next, float scale_dir,
+                           float scale_time, float* out, int B, cudaStream_t stream);
 int ds_to_uint8_launch(const float* x, unsigned char* out, int B, int Cc, int HW, cudaStream_t stream);
 int ds_update_launch(const ds_update_desc* d, cudaStream_t stream);
 int ds_threshold_launch(const ds_threshold_desc* d, cudaStream_t stream);

@@ -197,6 +197,76 @@ __global__ void __launch_bounds__(256) gits_cost_kernel(ds_gits_cost_desc d) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ AMED predictor
+// The whole predictor (amed-solver-main/training/networks.py:121-155) for one sample per CTA: time embeddings of t_cur and t_next
+// (PositionalEmbedding(8, endpoint=True) with the sin/cos swap, map_layer0, SiLU), bottleneck MLP (in -> hidden -> z, SiLU between),
+// the sigmoid heads, and the geometric intermediate time t_mid = t_next^r * t_cur^(1-r) (solvers_amed.py:119).  Replaces ~25 ATen
+// launches per sampling step.  Weights: one packed fp32 buffer (amed_predictor.pack): map_layer0 W[nc][nc], b[nc]; enc_layer0 W[hid][in],
+// b[hid]; enc_layer1 W[z][hid], b[z]; fc_r W[z + 2 nc], b; then fc_scale_dir and fc_scale_time (W, b each) if present.
+struct AmedDims { int in_dim, hid, z, nc, has_dir, has_time; };
+
+__global__ void __launch_bounds__(256) amed_predict_kernel(const float* __restrict__ w, AmedDims dm, const float* __restrict__ bott,
+                                                           const float* __restrict__ t_cur_p, const float* __restrict__ t_next_p,
+                                                           float scale_dir, float scale_time, float* __restrict__ out, int B) {
+    __shared__ float s_x[256], s_h[256], s_feat[64];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int nc = dm.nc, half = nc / 2;
+    const float* w_map = w;
+    const float* b_map = w_map + nc * nc;
+    const float* w0 = b_map + nc;
+    const float* b0 = w0 + dm.hid * dm.in_dim;
+    const float* w1 = b0 + dm.hid;
+    const float* b1 = w1 + dm.z * dm.hid;
+    const int nf = dm.z + 2 * nc;
+    const float* w_r = b1 + dm.z;
+    const float t_cur = *t_cur_p, t_next = *t_next_p;
+    if (tid < dm.in_dim) s_x[tid] = bott ? bott[(long long)b * dm.in_dim + tid] : 0.f;
+    // time embeddings: e = [sin(t f_i) | cos(t f_i)], f_i = (1/10000)^(i / (half - 1)); feat[z + k] (t_cur), feat[z + nc + k] (t_next)
+    if (tid < 2 * nc) {
+        const int which = tid / nc, k = tid % nc;
+        const float t = which ? t_next : t_cur;
+        float acc = b_map[k];
+        for (int i = 0; i < nc; ++i) {
+            const int fi = i % half;
+            const float f = powf(1.0f / 10000.0f, (float)fi / (float)(half - 1));
+            const float e = (i < half) ? sinf(t * f) : cosf(t * f);
+            acc = fmaf(w_map[k * nc + i], e, acc);
+        }
+        s_feat[dm.z + which * nc + k] = acc / (1.0f + expf(-acc));
+    }
+    __syncthreads();
+    if (tid < dm.hid) {
+        float acc = b0[tid];
+        const float* row = w0 + (long long)tid * dm.in_dim;
+        for (int i = 0; i < dm.in_dim; ++i) acc = fmaf(row[i], s_x[i], acc);
+        s_h[tid] = acc / (1.0f + expf(-acc));
+    }
+    __syncthreads();
+    if (tid < dm.z) {
+        float acc = b1[tid];
+        const float* row = w1 + (long long)tid * dm.hid;
+        for (int j = 0; j < dm.hid; ++j) acc = fmaf(row[j], s_h[j], acc);
+        s_feat[tid] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        auto head = [&](const float* wh) {
+            float acc = wh[nf];
+            for (int i = 0; i < nf; ++i) acc = fmaf(wh[i], s_feat[i], acc);
+            return 1.0f / (1.0f + expf(-acc));
+        };
+        const float r = head(w_r);
+        const float* wn = w_r + nf + 1;
+        float sd = 1.0f, st = 1.0f;
+        if (dm.has_dir) { sd = head(wn) / (1.0f / (2.0f * scale_dir)) + (1.0f - scale_dir); wn += nf + 1; }
+        if (dm.has_time) st = head(wn) / (1.0f / (2.0f * scale_time)) + (1.0f - scale_time);
+        out[0 * B + b] = r;
+        out[1 * B + b] = sd;
+        out[2 * B + b] = st;
+        out[3 * B + b] = powf(t_next, r) * powf(t_cur, 1.0f - r);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ image epilogue
 // (x * 127.5 + 128).clip(0, 255) -> uint8, NCHW -> NHWC  (sample.py:311): one pass instead of five ATen launches.
 __global__ void to_uint8_nhwc_kernel(const float* x, unsigned char* out, int B, int Cc, int HW) {
@@ -213,6 +283,15 @@ __global__ void to_uint8_nhwc_kernel(const float* x, unsigned char* out, int B, 
 }  // namespace dsb
 
 using namespace dsb;
+
+extern "C" int ds_amed_predict_launch(const float* w, const int* dims6, const float* bott, const float* t_cur, const float* t_next,
+                                      float scale_dir, float scale_time, float* out, int B, cudaStream_t stream) {
+    AmedDims dm = {dims6[0], dims6[1], dims6[2], dims6[3], dims6[4], dims6[5]};
+    if (dm.in_dim <= 0 || dm.in_dim > 256 || dm.hid <= 0 || dm.hid > 256 || dm.z <= 0 || dm.nc < 4 || dm.nc % 2 || dm.z + 2 * dm.nc > 64 || B <= 0)
+        return -2;
+    amed_predict_kernel<<<B, 256, 0, stream>>>(w, dm, bott, t_cur, t_next, scale_dir, scale_time, out, B);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
 
 extern "C" int ds_to_uint8_launch(const float* x, unsigned char* out, int B, int Cc, int HW, cudaStream_t stream) {
     const long long total = (long long)B * HW;
@@ -262,7 +341,7 @@ extern "C" int ds_threshold_launch(const ds_threshold_desc* d, cudaStream_t stre
         threshold_kernel<false><<<d->B, 256, 0, stream>>>(*d);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
-    if (smem > 48 * 1024) {
+    if (smem > 40 * 1024) {      // dynamic + ~1.1 KB static must stay under the 48 KB default, else opt in
         // the opt-in shared-memory limit is a per-device function attribute: set it on every device this process uses
         static bool attr_set[64] = {};
         int dev = 0;

@@ -27,7 +27,7 @@ def make_alphas_cumprod(linear_start=0.00085, linear_end=0.0120, n=1000):
 
 class B200LDMNet:
     def __init__(self, params, img_resolution=64, img_channels=4, num_heads=8, alphas_cumprod=None, guidance_type='classifier-free',
-                 guidance_rate=1.0, epsilon_t=1e-3, precision=None, device='cuda', flash_attn=True, f8_linear=None):
+                 guidance_rate=1.0, epsilon_t=1e-3, precision=None, device='cuda', flash_attn=True, f8_linear=None, cuda_graph=None):
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise _lib.DsError('B200LDMNet needs a CUDA device (no CPU fallback)')
@@ -40,12 +40,17 @@ class B200LDMNet:
         self.precision = precision
         self.npass = PRECISIONS[precision]
         self.f8 = precision == 'fp16f8'
-        # opt-in (not yet run on hardware): with fp16f8, also run proj_in / attn2.to_q / GEGLU ff / proj_out in the f8 GEMM mode
+        # with fp16f8, proj_in / attn2.to_q / GEGLU ff / proj_out also run in the f8 GEMM mode (default since round 2: parity green on
+        # hardware, profiles/r02b; DSB_LDM_F8_LINEAR=0 or f8_linear=False keeps them fp16x3)
         if f8_linear is None:
             import os
-            f8_linear = os.environ.get('DSB_LDM_F8_LINEAR') == '1'
+            f8_linear = os.environ.get('DSB_LDM_F8_LINEAR', '1') != '0'
         self.f8_linear = bool(f8_linear) and self.f8
         self.flash_attn = bool(flash_attn)
+        if cuda_graph is None:
+            from .net import default_cuda_graph
+            cuda_graph = default_cuda_graph()
+        self.cuda_graph = bool(cuda_graph)
         self.st = ldm_plan.ldm_structure(params, num_heads)
         self.wb, self.info = ldm_plan.pack_ldm_weights(self.st, params, f8=self.f8, f8_linear=self.f8_linear)
         blob = self.wb.bytes()
@@ -115,6 +120,11 @@ class B200LDMNet:
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.ds_unet_create(self._wh, C.cast(pl.ops_array, C.c_void_p), pl.n_ops, C.sizeof(S.PlanOp), pl.arena_bytes,
                                                    C.byref(h)), 'ds_unet_create')
+                if self.cuda_graph:
+                    px = self.img_channels * self.img_resolution ** 2 * 4
+                    T, cd = pl.meta['ctx_tokens'], self.info['ctx_dim']
+                    io_bytes = (C.c_size_t * 6)(B * px, Bt * px, nT * 4, (B if nT > 1 else 1) * 16, Bt * 64 * 4, Bt * T * cd * 4)
+                    _lib.check(self.lib.ds_unet_enable_graph(h, io_bytes, 6), 'ds_unet_enable_graph')
             ent = (h, pl)
             self._plans[key] = ent
         return ent
@@ -190,6 +200,8 @@ class B200LDMNet:
             buf = (C.c_float * pl.n_ops)()
             n = self.lib.ds_unet_get_profile(h, buf, pl.n_ops)
             self.lib.ds_unet_set_profiling(h, 0)
+            if not any(buf[i] > 0 for i in range(n)):          # a cached plan of another (batch, sigma-mode) that this call did not run
+                continue
             for i in range(n):
                 t = self.lib.ds_unet_op_type(h, i)
                 c, ms = out.get(t, (0, 0.0))

@@ -459,5 +459,5 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
         arr[i].type = S.OP_TYPE_OF[type(desc)]
         arr[i].tag = tg
         setattr(arr[i].u, S.UNION_FIELD[arr[i].type], desc)
-    meta = dict(B=B, Bt=Bt, nT=nT, npass=npass, n_ops=len(ops), n_gemm=sum(1 for i in range(len(ops)) if arr[i].type == S.DS_OP_GEMM))
+    meta = dict(B=B, Bt=Bt, nT=nT, npass=npass, ctx_tokens=ctx_tokens, n_ops=len(ops), n_gemm=sum(1 for i in range(len(ops)) if arr[i].type == S.DS_OP_GEMM))
     return Plan(arr, len(ops), total, dict(A.offsets), meta)

@@ -28,9 +28,15 @@ def default_precision():
     return p
 
 
+def default_cuda_graph():
+    """Replay each denoiser evaluation as ONE CUDA graph (ds_unet_enable_graph) unless DSB_CUDA_GRAPH=0."""
+    import os
+    return os.environ.get('DSB_CUDA_GRAPH', '1') != '0'
+
+
 class B200Net:
     def __init__(self, params, img_resolution, img_channels, label_dim=0, sigma_min=0.002, sigma_max=80.0, sigma_data=0.5,
-                 precision=None, device='cuda', fuse_stats=True, flash_attn=True, f8_min_channels=None):
+                 precision=None, device='cuda', fuse_stats=True, flash_attn=True, f8_min_channels=None, cuda_graph=None):
         self.device = torch.device(device)
         precision = precision or default_precision()
         if self.device.type != 'cuda':
@@ -47,6 +53,7 @@ class B200Net:
         self.f8_min_channels = int(f8_min_channels)          # fp16f8 only: blocks narrower than this stay fp16x3 (plan.pack_weights)
         self.fuse_stats = bool(fuse_stats)
         self.flash_attn = bool(flash_attn)
+        self.cuda_graph = default_cuda_graph() if cuda_graph is None else bool(cuda_graph)
         self.spec = edm_nets.spec_from_params(params, img_resolution, img_channels, label_dim)
         self.spec.sigma_data = sigma_data
         self.wb, self.winfo = planner.pack_weights(self.spec, params, f8=self.f8, f8_min_channels=self.f8_min_channels)
@@ -93,12 +100,17 @@ class B200Net:
         key = (B, nsig, nlab)
         ent = self._plans.get(key)
         if ent is None:
+            import os
             pl = planner.compile_plan(self.spec, self.wb, self.winfo, B, nsig, nlab, npass=self.npass, fuse_stats=self.fuse_stats,
-                                           flash_attn=self.flash_attn, f8=self.f8)
+                                           flash_attn=self.flash_attn, f8=self.f8, gn_coef=os.environ.get('DSB_GN_COEF', '1') != '0')
             h = C.c_void_p()
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.ds_unet_create(self._wh, C.cast(pl.ops_array, C.c_void_p), pl.n_ops, C.sizeof(S.PlanOp),
                                                    pl.arena_bytes, C.byref(h)), 'ds_unet_create')
+                if self.cuda_graph:
+                    img = B * self.img_channels * self.img_resolution ** 2 * 4
+                    io_bytes = (C.c_size_t * 6)(img, img, nsig * 4, nlab * self.label_dim * 4, B * 64 * 4, 0)
+                    _lib.check(self.lib.ds_unet_enable_graph(h, io_bytes, 6), 'ds_unet_enable_graph')
             ent = (h, pl)
             self._plans[key] = ent
         return ent

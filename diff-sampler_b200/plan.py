@@ -166,10 +166,10 @@ class Plan:
         self.meta = meta
 
 
-def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash_attn=True, f8=False):
+def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash_attn=True, f8=False, gn_coef=True):
     """Lower the forward pass for batch B.  nsig in {1, B}: number of sigma values (embedding rows);
     nlab in {0, 1, B}: rows of class labels supplied.  f8: the block convolutions run in the f8 GEMM mode (weights must have been
-    packed with pack_weights(f8=True))."""
+    packed with pack_weights(f8=True)).  gn_coef: GroupNorm coefficient tables + persistent gn_apply (False = the round-1 lowering)."""
     assert nsig in (1, B) and nlab in (0, 1, B)
     assert not f8 or npass == 3
 
@@ -210,8 +210,11 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
             return d
         emit(materialise)
 
-    def need_stats(slot, parts, hw):
-        """GroupNorm statistics over the (virtually concatenated) fp32 tensors `parts` = [(buffer, channels), ...] for `slot`."""
+    def need_stats(slot, parts, hw, norm=None):
+        """GroupNorm statistics over the (virtually concatenated) fp32 tensors `parts` = [(buffer, channels), ...] for `slot`.
+        norm = dict(gamma, beta, eps, ada, ada_stride) (weight / arena references as callables of R) additionally asks for the
+        per-(sample, channel) coefficient table y = x * a + b in the scratch buffer 'gncoef' (ds_gn_finalize_desc.coef), which lets
+        gn_apply skip its fp64 prologue and run the persistent variant; returns True when the table is produced."""
         assert len(parts) <= 2
         c_total = sum(c for _, c in parts)
         g = _groups(c_total)
@@ -219,9 +222,21 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
         (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
         fusable = (fuse_stats and hw % 32 == 0 and cpg % 4 == 0 and all(c % 4 == 0 for _, c in parts)
                    and all(name in prod_of and prod_of[name][1] == c for name, c in parts))
+        want_coef = norm is not None and gn_coef
+        if want_coef:
+            A.need('gncoef', B * c_total * 2 * F4)
+
+        def coef_args(R):
+            if not want_coef:
+                return {}
+            return dict(gamma=norm['gamma'](R), beta=norm['beta'](R), ada=norm['ada'](R) if norm.get('ada') else 0,
+                        ada_stride=norm.get('ada_stride', 0), eps=norm['eps'], HW=hw, coef=R('gncoef'))
         if not fusable:
             emit(lambda R: S.GnStatsDesc(src0=R(n0), src1=R(n1) if n1 else 0, C0=c0, C1=c1, HW=hw, B=B, groups=g, sums=R('stats', slot)))
-            return
+            if want_coef:       # coefficient table from the sums the separate statistics pass accumulated
+                emit(lambda R: S.GnFinalizeDesc(quads0=0, quads1=0, C0=c0, C1=c1, slabs_per_sample=0, B=B, groups=g, sums=R('stats', slot),
+                                                **coef_args(R)))
+            return want_coef
         bufs = []
         for name, c in parts:
             pid, cout, m_rows = prod_of[name]
@@ -229,10 +244,12 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
                 quads_of[pid] = A.need('quads:' + name, (m_rows // 32) * (cout // 4) * 2 * F4)
             bufs.append(quads_of[pid])
         emit(lambda R: S.GnFinalizeDesc(quads0=R(bufs[0]), quads1=R(bufs[1]) if len(bufs) > 1 else 0, C0=c0, C1=c1,
-                                        slabs_per_sample=hw // 32, B=B, groups=g, sums=R('stats', slot)))
+                                        slabs_per_sample=hw // 32, B=B, groups=g, sums=R('stats', slot), **coef_args(R)))
+        return want_coef
 
-    def stat_args(R, slot):
-        return dict(sums=R('stats', slot))
+    def stat_args(R, slot, coef=False):
+        """gn_apply reads either the coefficient table (resample == 0 uses) or the fp64 sums."""
+        return dict(sums=0, coef=R('gncoef')) if coef else dict(sums=R('stats', slot))
 
     # ---------------- embedding ----------------------------------------------------------------------------------
     A.need('coef', nsig * 4 * F4)
@@ -313,7 +330,8 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
         resample = 1 if b.down else (2 if b.up else 0)
         Mo = B * Ho * Ho
         s0 = stats_slot()
-        need_stats(s0, [(x0, c0)] + ([(x1, c1)] if x1 else []), Hi * Hi)
+        k0 = need_stats(s0, [(x0, c0)] + ([(x1, c1)] if x1 else []), Hi * Hi,
+                        norm=dict(gamma=lambda R: W(n + '.norm0:g'), beta=lambda R: W(n + '.norm0:b'), eps=b.eps) if resample == 0 else None)
         A.need('act', npl * Mo * max(cin, cout) * H2)
         want_raw = b.skip == 'conv'
         want_rawf = b.skip == 'resample'
@@ -321,7 +339,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
             A.need('raw', npl * Mo * cin * H2)
         if want_rawf:
             A.need('rawf', Mo * cin * F4)
-        emit(lambda R: S.GnApplyDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, H=Hi, W=Hi, B=B, groups=_groups(cin), **stat_args(R, s0),
+        emit(lambda R: S.GnApplyDesc(src0=R(x0), src1=R(x1) if x1 else 0, C0=c0, C1=c1, H=Hi, W=Hi, B=B, groups=_groups(cin), **stat_args(R, s0, k0),
                                      gamma=W(n + '.norm0:g'), beta=W(n + '.norm0:b'), eps=b.eps, silu=1, ada=0, ada_stride=0,
                                      resample=resample, nplanes=npl, out_act=R('act'), out_raw=R('raw') if want_raw else 0,
                                      out_raw_f32=R('rawf') if want_rawf else 0, fmt=1 if is_f8(n + '.conv0') else 0))
@@ -330,8 +348,11 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
                                                  bias=W(n + '.conv0:b'), rowvec=0 if b.adaptive_scale else R('aff', b.aff_off * F4),
                                                  rowvec_stride=aff_stride, **f8_args(n + '.conv0'))[0])
         s1 = stats_slot()
-        need_stats(s1, [('y', cout)], Ho * Ho)
-        emit(lambda R: S.GnApplyDesc(src0=R('y'), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), **stat_args(R, s1),
+        k1 = need_stats(s1, [('y', cout)], Ho * Ho,
+                        norm=dict(gamma=lambda R: W(n + '.norm1:g'), beta=lambda R: W(n + '.norm1:b'), eps=b.eps,
+                                  ada=(lambda R: R('aff', b.aff_off * F4)) if b.adaptive_scale else None,
+                                  ada_stride=aff_stride if b.adaptive_scale else 0))
+        emit(lambda R: S.GnApplyDesc(src0=R('y'), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), **stat_args(R, s1, k1),
                                      gamma=W(n + '.norm1:g'), beta=W(n + '.norm1:b'), eps=b.eps, silu=1,
                                      ada=R('aff', b.aff_off * F4) if b.adaptive_scale else 0,
                                      ada_stride=aff_stride if b.adaptive_scale else 0, resample=0, nplanes=npl, out_act=R('act'),
@@ -354,8 +375,8 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
             d = cout // nh
             L = Ho * Ho
             s2 = stats_slot()
-            need_stats(s2, [(mid, cout)], L)
-            emit(lambda R: S.GnApplyDesc(src0=R(mid), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), **stat_args(R, s2),
+            k2 = need_stats(s2, [(mid, cout)], L, norm=dict(gamma=lambda R: W(n + '.norm2:g'), beta=lambda R: W(n + '.norm2:b'), eps=b.eps))
+            emit(lambda R: S.GnApplyDesc(src0=R(mid), src1=0, C0=cout, C1=0, H=Ho, W=Ho, B=B, groups=_groups(cout), **stat_args(R, s2, k2),
                                          gamma=W(n + '.norm2:g'), beta=W(n + '.norm2:b'), eps=b.eps, silu=0, ada=0, ada_stride=0,
                                          resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0))
             A.need('qk', npl * B * L * 2 * cout * H2)
@@ -406,8 +427,9 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
     sh = stats_slot()
     A.need('act', npl * B * HW0 * cur_c * H2)
     fin, fin_c = cur, cur_c
-    need_stats(sh, [(fin, fin_c)], HW0)
-    emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=_groups(fin_c), **stat_args(R, sh),
+    kh = need_stats(sh, [(fin, fin_c)], HW0, norm=dict(gamma=lambda R: W(spec.head_norm + ':g'), beta=lambda R: W(spec.head_norm + ':b'),
+                                                       eps=spec.head_eps))
+    emit(lambda R: S.GnApplyDesc(src0=R(fin), src1=0, C0=fin_c, C1=0, H=R0, W=R0, B=B, groups=_groups(fin_c), **stat_args(R, sh, kh),
                                  gamma=W(spec.head_norm + ':g'), beta=W(spec.head_norm + ':b'), eps=spec.head_eps, silu=1, ada=0,
                                  ada_stride=0, resample=0, nplanes=npl, out_act=R('act'), out_raw=0, out_raw_f32=0,
                                  fmt=1 if is_f8(spec.head_conv) else 0))

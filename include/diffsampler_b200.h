@@ -58,6 +58,12 @@ int ds_unet_forward(ds_unet* u, const float* x, const float* sigma, const float*
  * coefficient table [B][4] holding c_in, and the text context [Bt, 77, context_dim]; out_D receives eps in NCHW. */
 int ds_unet_forward_io(ds_unet* u, const void* const* io, int n_io, void* stream);
 
+/* CUDA-graph replay of the op list (the per-NFE launch list as one graph).  io_bytes[k] = size of io slot k
+ * {x, out_D, sigma, labels, out_bottleneck, context} for this plan (0 = slot unused).  After this call ds_unet_forward[_io] stages the
+ * inputs into fixed device buffers (device-to-device copies on the caller's stream), replays ONE instantiated graph of all kernels
+ * (captured on the second call, after a plain warm-up run) and copies the outputs back: 257 (EDM) / 520 (SD) launches become one. */
+int ds_unet_enable_graph(ds_unet* u, const size_t* io_bytes, int n_io);
+
 /* Debug/test access to the workspace arena (device -> host copy, synchronises the stream). */
 int ds_unet_debug_read(ds_unet* u, size_t arena_offset, void* host_dst, size_t bytes, void* stream);
 /* Number of kernels launched by the last ds_unet_forward on this handle. */
@@ -95,6 +101,14 @@ int ds_dyn_threshold(const float* x0, float* thr, int B, int row_len, float q, f
  *   x_ij = traj[i] + (t[j]-t[i])*eps[i];  out[i][j][b] = { sum|x_ij-traj[j]|, sum(x_ij-traj[j])^2, sum(c-x_ij)^2, sum(c-x_ij)(c-b0) }
  * with b0 = traj[0], c = traj[N-1].  traj [N][B][n], eps [N-1][B][n] fp32; out [N][N][B][4] fp64 (entries i >= j untouched). */
 int ds_gits_cost(const float* traj, const float* eps, const float* t_steps, double* out, int N, int B, int64_t n_per_sample, void* stream);
+
+/* ---- AMED predictor: replaces AMED_predictor.forward + the t_mid formula ------------------------------------------
+ * amed-solver-main/training/networks.py:121-155, solvers_amed.py:22-55,:119.  One launch per sampling step:
+ *   out4[0][b] = r, out4[1][b] = scale_dir, out4[2][b] = scale_time, out4[3][b] = t_mid = t_next^r * t_cur^(1-r)
+ * weights: packed fp32 buffer (diff-sampler_b200/amed_predictor.py:pack); dims6 = {bottleneck_dim, hidden, z, noise_channels, has_dir,
+ * has_time}; bottleneck [B][bottleneck_dim] or NULL (analytical first step: zeros, solvers_amed.py:24); t_cur / t_next: device scalars. */
+int ds_amed_predict(const float* weights, const int* dims6, const float* bottleneck, const float* t_cur, const float* t_next,
+                    float scale_dir, float scale_time, float* out4, int B, void* stream);
 
 /* ---- image epilogue: replaces (images * 127.5 + 128).clip(0, 255).to(uint8).permute(0, 2, 3, 1) -------------
  * sample.py:311.  images [B, C, H*W] fp32 NCHW -> out [B, H*W, C] uint8 NHWC (what is written to PNG / gathered for FID). */

@@ -288,19 +288,47 @@ def _gn_stats(mem, d):
 def _gn_finalize(mem, d):
     B, G, slabs = int(d.B), int(d.groups), int(d.slabs_per_sample)
     C0, C1 = int(d.C0), int(d.C1)
-    q = mem.view(d.quads0, torch.float32, B * slabs * (C0 // 4) * 2).reshape(B, slabs, C0 // 4, 2).double().sum(dim=1)
-    if C1:
-        q1 = mem.view(d.quads1, torch.float32, B * slabs * (C1 // 4) * 2).reshape(B, slabs, C1 // 4, 2).double().sum(dim=1)
-        q = torch.cat([q, q1], dim=1)
-    qpg = (C0 + C1) // G // 4
-    mem.view(d.sums, torch.float64, B * G * 2)[:] = q.reshape(B, G, qpg, 2).sum(dim=2).reshape(-1)
+    C = C0 + C1
+    if d.quads0:
+        q = mem.view(d.quads0, torch.float32, B * slabs * (C0 // 4) * 2).reshape(B, slabs, C0 // 4, 2).double().sum(dim=1)
+        if C1:
+            q1 = mem.view(d.quads1, torch.float32, B * slabs * (C1 // 4) * 2).reshape(B, slabs, C1 // 4, 2).double().sum(dim=1)
+            q = torch.cat([q, q1], dim=1)
+        qpg = C // G // 4
+        mem.view(d.sums, torch.float64, B * G * 2)[:] = q.reshape(B, G, qpg, 2).sum(dim=2).reshape(-1)
+    if d.coef:
+        # per-(sample, channel) {a, b}: y = x * a + b, in fp32 as the kernel computes them (elementwise.cu gn_finalize_kernel)
+        s = mem.view(d.sums, torch.float64, B * G * 2).reshape(B, G, 2)
+        cnt = (C // G) * int(d.HW)
+        mu = s[:, :, 0] / cnt
+        var = (s[:, :, 1] / cnt - mu * mu).clamp_min(0.0)
+        rstd = (1.0 / torch.sqrt(var + float(d.eps))).float()
+        mu_c = mu.float().repeat_interleave(C // G, dim=1)
+        a = rstd.repeat_interleave(C // G, dim=1) * mem.view(d.gamma, torch.float32, C)[None, :]
+        b = mem.view(d.beta, torch.float32, C)[None, :].expand(B, C).clone()
+        if d.ada:
+            st = int(d.ada_stride)
+            ada = mem.view(d.ada, torch.float32, (B - 1) * st + 2 * C)
+            ada = _strided(ada, (B, 2 * C), (st, 1))
+            sc, sh = ada[:, :C] + 1.0, ada[:, C:]
+            a = a * sc
+            b = b * sc + sh
+        out = mem.view(d.coef, torch.float32, B * C * 2).reshape(B, C, 2)
+        out[:, :, 0] = a
+        out[:, :, 1] = b - mu_c * a
 
 
 def _gn_apply(mem, d):
     B, H, W, C, G = int(d.B), int(d.H), int(d.W), int(d.C0) + int(d.C1), int(d.groups)
     x = _src_cat(mem, d, B * H * W).reshape(B, H, W, C)
     y = None
-    if d.sums:
+    if d.coef:
+        assert int(d.resample) == 0 and not d.sums
+        cf = mem.view(d.coef, torch.float32, B * C * 2).reshape(B, C, 2).double()
+        y = x * cf[:, None, None, :, 0] + cf[:, None, None, :, 1]
+        if d.silu:
+            y = y * torch.sigmoid(y)
+    elif d.sums:
         s = mem.view(d.sums, torch.float64, B * G * 2).reshape(B, G, 2)
         cnt = (C // G) * H * W
         mu = s[:, :, 0] / cnt

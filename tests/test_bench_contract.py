@@ -29,12 +29,13 @@ def test_precision_auto_resolves_per_net(monkeypatch):
     spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    for net, want in (('cifar10', 'fp16f8'), ('imagenet64', 'fp16f8'), ('ffhq', 'fp16x3'), ('sd15', 'fp16x3')):
+    for net, want, fmin in (('cifar10', 'fp16f8', 0), ('imagenet64', 'fp16f8', 0), ('ffhq', 'fp16f8', 256), ('sd15', bench.PRECISION_FOR['sd15'], 0)):
         monkeypatch.setattr(sys, 'argv', ['bench.py', '--net', net])
         a = bench.parse()
-        assert (a.precision, a.precision_requested) == (want, 'auto')
+        assert (a.precision, a.precision_requested, a.f8_min_channels) == (want, 'auto', fmin)
     monkeypatch.setattr(sys, 'argv', ['bench.py', '--net', 'ffhq', '--precision', 'fp16f8'])
-    assert bench.parse().precision == 'fp16f8'
+    a = bench.parse()
+    assert a.precision == 'fp16f8' and a.f8_min_channels == 0          # an explicit precision keeps f8_min_channels as given
 
 
 def test_f8_operand_model_error_budget():

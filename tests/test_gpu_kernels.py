@@ -443,7 +443,11 @@ def test_fused_stats_rejects_partial_slabs(lib):
 
 # --------------------------------------------------------------------------------------------- fused attention
 @pytest.mark.parametrize('B,nh,L,Lk,d', [(2, 3, 256, 256, 64), (1, 2, 192, 77, 40), (3, 1, 64, 64, 64), (1, 8, 1024, 1024, 40),
-                                         (2, 2, 320, 200, 64)])
+                                         (2, 2, 320, 200, 64),
+                                         # round 2 (persistent kernel, two softmax groups over alternate 64-key blocks): more tiles than SMs
+                                         # (192 > 148: CTAs walk several tiles), an odd block count (3), a single block (group 1 idle),
+                                         # many short tiles per CTA (L = 64: 300 tiles)
+                                         (4, 6, 1024, 1024, 64), (2, 2, 320, 192, 64), (1, 3, 128, 64, 64), (50, 6, 64, 64, 64), (3, 5, 200, 130, 40)])
 def test_fused_attention(lib, B, nh, L, Lk, d):
     """attn_kernel (QK^T -> online softmax -> PV in one kernel, head dim padded to 64) against float64 softmax attention on the
     same fp16 hi+lo operands: self-attention shapes, a cross-attention shape (77 keys, pitch 80), partial query / key tiles."""
@@ -488,6 +492,91 @@ def test_fused_attention(lib, B, nh, L, Lk, d):
     pad = got[..., d:].abs().max().item() if d < 64 else 0.0
     print(f'fused attention B{B} nh{nh} L{L} Lk{Lk} d{d}: err {err:.3e} (max {ref.abs().max().item():.2f}), pad {pad:.1e}')
     assert err < 2e-5 * max(1.0, ref.abs().max().item()) and pad == 0.0
+
+
+@pytest.mark.parametrize('C0,C1,H,W,ada,fmt,Bn', [(128, 0, 16, 16, False, 0, 3), (256, 128, 8, 8, False, 0, 5), (192, 0, 16, 16, True, 0, 3),
+                                                  (256, 0, 32, 32, False, 1, 40), (576, 384, 8, 8, True, 1, 7), (1344, 0, 8, 8, False, 0, 2),
+                                                  (320, 0, 32, 32, False, 0, 16)])
+def test_groupnorm_coefficient_table_and_persistent_apply(lib, C0, C1, H, W, ada, fmt, Bn):
+    """Round 2: gn_finalize also writes the per-(sample, channel) coefficients y = x * a + b (ds_gn_finalize_desc.coef), and gn_apply with
+    ds_gn_apply_desc.coef runs the persistent, evenly split kernel (gn_apply_v3) without the fp64 prologue.  The arithmetic is the one of
+    the sums-based kernel (a = rstd * gamma * (1 + scale), b = beta * (1 + scale) + shift - mean * a in fp32), so the outputs must be
+    IDENTICAL to the round-1 path on the same statistics -- for hi/lo planes and for the f8 operand image, with and without a second
+    source, for channel counts whose 8-channel thread columns do not divide the 256-thread block evenly (192, 1344) and for 10-channel
+    groups (C = 320: the LDM GroupNorm32 case, statistics from the separate pass)."""
+    from diff_sampler_b200 import _cstructs as S
+    torch.manual_seed(16)
+    Cc, G = C0 + C1, 32
+    x0 = torch.randn(Bn, H, W, C0, device=dev()) * 1.7 + 0.3
+    x1 = torch.randn(Bn, H, W, C1, device=dev()) * 0.6 - 0.2 if C1 else None
+    gamma, beta = torch.randn(Cc, device=dev()), torch.randn(Cc, device=dev())
+    adav = torch.randn(Bn, 2 * Cc, device=dev()) * 0.3 if ada else None
+    sums = torch.zeros(Bn, G, 2, dtype=torch.float64, device=dev())
+    lib.op_launch(S.GnStatsDesc(src0=x0.data_ptr(), src1=x1.data_ptr() if C1 else 0, C0=C0, C1=C1, HW=H * W, B=Bn, groups=G, sums=sums.data_ptr()))
+    coef = torch.full((Bn, Cc, 2), float('nan'), device=dev())
+    lib.op_launch(S.GnFinalizeDesc(quads0=0, quads1=0, C0=C0, C1=C1, slabs_per_sample=0, B=Bn, groups=G, sums=sums.data_ptr(),
+                                   gamma=gamma.data_ptr(), beta=beta.data_ptr(), ada=adav.data_ptr() if ada else 0, ada_stride=2 * Cc if ada else 0,
+                                   eps=1e-6, HW=H * W, coef=coef.data_ptr()))
+    outs = []
+    for use_coef in (False, True):
+        act = torch.zeros(2, Bn, H, W, Cc, dtype=torch.float16, device=dev())
+        raw = torch.zeros(2, Bn, H, W, Cc, dtype=torch.float16, device=dev())
+        lib.op_launch(S.GnApplyDesc(src0=x0.data_ptr(), src1=x1.data_ptr() if C1 else 0, C0=C0, C1=C1, H=H, W=W, B=Bn, groups=G,
+                                    sums=0 if use_coef else sums.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(), eps=1e-6, silu=1,
+                                    ada=adav.data_ptr() if ada else 0, ada_stride=2 * Cc if ada else 0, resample=0, nplanes=2,
+                                    out_act=act.data_ptr(), out_raw=raw.data_ptr(), out_raw_f32=0, fmt=fmt, coef=coef.data_ptr() if use_coef else 0))
+        sync()
+        outs.append((act, raw))
+    assert torch.equal(outs[0][0].view(torch.int16), outs[1][0].view(torch.int16)), 'normalised planes differ between the sums and the coefficient path'
+    assert torch.equal(outs[0][1].view(torch.int16), outs[1][1].view(torch.int16))
+    # and the table itself against float64 GroupNorm algebra
+    xc = (torch.cat([x0, x1], dim=-1) if C1 else x0).double().reshape(Bn, H * W, G, Cc // G)
+    mu = xc.mean(dim=(1, 3))
+    var = xc.var(dim=(1, 3), unbiased=False)
+    rstd = (1.0 / torch.sqrt(var + 1e-6)).repeat_interleave(Cc // G, dim=1)
+    a = rstd * gamma.double()[None]
+    b = beta.double()[None].expand(Bn, Cc)
+    if ada:
+        a = a * (adav[:, :Cc].double() + 1)
+        b = b * (adav[:, :Cc].double() + 1) + adav[:, Cc:].double()
+    b = b - mu.repeat_interleave(Cc // G, dim=1) * a
+    ea, eb = (coef[:, :, 0].double() - a).abs().max().item(), (coef[:, :, 1].double() - b).abs().max().item()
+    print(f'gn coef C{C0}+{C1} {H}x{W} B{Bn} ada{ada} fmt{fmt}: identical planes; table err a {ea:.2e} b {eb:.2e}')
+    assert ea < 1e-5 * a.abs().max().item() and eb < 1e-5 * max(1.0, b.abs().max().item())
+
+
+@pytest.mark.parametrize('sd,st', [(0.01, 0.2), (0.0, 0.2), (0.05, 0.0), (0.0, 0.0)])
+def test_amed_predictor_kernel(lib, sd, st):
+    """ds_amed_predict: the whole AMED predictor + t_mid in one launch, against the torch forward of the same weights
+    (amed-solver-main/training/networks.py:121-155; solvers_amed.py:119 for t_mid)."""
+    from diff_sampler_b200.amed_predictor import AMEDPredictor
+    g = torch.Generator().manual_seed(31)
+    W = {'map_layer0.weight': torch.randn(8, 8, generator=g) * 0.5, 'map_layer0.bias': torch.randn(8, generator=g) * 0.1,
+         'enc_layer0.weight': torch.randn(128, 64, generator=g) * 0.2, 'enc_layer0.bias': torch.randn(128, generator=g) * 0.1,
+         'enc_layer1.weight': torch.randn(4, 128, generator=g) * 0.2, 'enc_layer1.bias': torch.randn(4, generator=g) * 0.1,
+         'fc_r.weight': torch.randn(1, 20, generator=g) * 0.4, 'fc_r.bias': torch.randn(1, generator=g) * 0.1}
+    if sd:
+        W.update({'fc_scale_dir.weight': torch.randn(1, 20, generator=g) * 0.4, 'fc_scale_dir.bias': torch.randn(1, generator=g) * 0.1})
+    if st:
+        W.update({'fc_scale_time.weight': torch.randn(1, 20, generator=g) * 0.4, 'fc_scale_time.bias': torch.randn(1, generator=g) * 0.1})
+    pred = AMEDPredictor(W, scale_dir=sd, scale_time=st).to(dev())
+    B = 7
+    ts = torch.tensor([80.0, 14.6, 3.1, 0.5, 0.03, 0.002], device=dev())
+    for i in range(len(ts) - 1):
+        for afs in (False, True):
+            enc = None if afs else torch.randn(B, 8, 8, generator=g).to(dev()) * 0.7
+            got = pred.predict_native(enc, ts[i], ts[i + 1], B)
+            ref = pred(enc if enc is not None else torch.zeros(B, 8, 8, device=dev()), ts[i].reshape(-1, 1, 1, 1), ts[i + 1].reshape(-1, 1, 1, 1))
+            ref = list(ref) if isinstance(ref, (tuple, list)) else [ref]
+            r = ref[0].reshape(-1)
+            rsd = ref[1].reshape(-1) if sd else torch.ones(B, device=dev())
+            rst = ref[-1].reshape(-1) if st else torch.ones(B, device=dev())
+            tmid = (ts[i + 1] ** r) * (ts[i] ** (1 - r))
+            for name, a, b in (('r', got[0], r), ('scale_dir', got[1], rsd), ('scale_time', got[2], rst), ('t_mid', got[3], tmid)):
+                err = ((a - b).abs() / b.abs().clamp_min(1e-3)).max().item()
+                assert err < 2e-5, (name, i, afs, err)
+    sync()
+    print(f'amed predictor kernel scale_dir={sd} scale_time={st}: r / scale_dir / scale_time / t_mid within 2e-5 (relative) of the torch forward')
 
 
 # --------------------------------------------------------------------------------------------- LDM (Stable Diffusion) building blocks
@@ -705,9 +794,8 @@ def test_groupnorm_apply_f8_layout(lib, C0, C1, H, W, resample):
         assert e_h8 < 0.07                  # e4m3: 2^-4 relative
 
 
-# --------------------------------------------------------------------------------------------- CTA-pair GEMM variant (opt-in)
-pair_opt_in = pytest.mark.skipif(os.environ.get('DSB_PAIR_TESTS') != '1',
-                                 reason='CTA-pair GEMM kernel is opt-in until it has a green run on hardware: set DSB_PAIR_TESTS=1')
+# --------------------------------------------------------------------------------------------- CTA-pair GEMM variant
+# (green on hardware since profiles/r01f and r02b; default for the large convolutions since round 2: +2.8 % images/s in the sustained bench)
 
 
 def _time_launch(lib, d, n=5):
@@ -722,7 +810,6 @@ def _time_launch(lib, d, n=5):
     return e0.elapsed_time(e1) / n
 
 
-@pair_opt_in
 @pytest.mark.parametrize('f8', [False, True])
 @pytest.mark.parametrize('Bn,H,W,Cin,Cout,C2', [(80, 32, 32, 256, 256, 0), (75, 32, 32, 64, 128, 64), (300, 16, 16, 128, 192, 0),
                                                 (1185, 8, 8, 128, 128, 0), (3, 16, 16, 128, 256, 0)])
@@ -779,12 +866,9 @@ def test_conv_pair_kernel(lib, f8, Bn, H, W, Cin, Cout, C2):
     assert dif <= tol * scale
 
 
-# --------------------------------------------------------------------------------------------- LayerNorm / GEGLU writing the f8 operand image (opt-in)
-ldm_f8_linear_opt_in = pytest.mark.skipif(os.environ.get('DSB_LDM_F8_LINEAR_TESTS') != '1',
-                                          reason='f8 operand image from LayerNorm / GEGLU is opt-in until it has a green run on hardware')
+# --------------------------------------------------------------------------------------------- LayerNorm / GEGLU writing the f8 operand image
 
 
-@ldm_f8_linear_opt_in
 def test_layernorm_geglu_f8_image(lib):
     from diff_sampler_b200 import _cstructs as S
     from diff_sampler_b200 import gemm_desc as G

@@ -485,7 +485,6 @@ def test_ldm_cfg_denoiser_parity_f8_mode():
         assert err < TOL * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.skipif(os.environ.get('DSB_LDM_F8_LINEAR_TESTS') != '1', reason='opt-in until it has a green run on hardware')
 def test_ldm_cfg_denoiser_parity_f8_linear():
     """fp16f8 with f8_linear=True: ResBlock convolutions and the single-consumer transformer linears in the f8 GEMM mode."""
     from oracle import edm_oracle as O
@@ -577,6 +576,63 @@ def test_sd15_fullsize_parity():
     err = (got - ref).abs().max().item()
     print(f'sd15 cfg 7.5 batch 1: err {err:.3e} (max|D| {ref.abs().max().item():.2f}); build+native {t1 - t0:.0f}s, oracle {time.time() - t1:.0f}s')
     assert err < TOL * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize('name', ['tiny_song', 'tiny_adm'])
+def test_cuda_graph_replay_matches_plain_launches(name):
+    """ds_unet_enable_graph: every denoiser evaluation after the first two is ONE cudaGraphLaunch of the captured op list over staged io
+    buffers.  Same bits as the plain launch loop for changing inputs / sigmas / labels, with and without the AMED bottleneck read-out,
+    and through a sampler run."""
+    from oracle import edm_oracle as O
+    from diff_sampler_b200 import solvers
+    from diff_sampler_b200.net import B200Net
+    on, P, S = _oracle(name)
+    mk = lambda g: B200Net(P, S['img_resolution'], S['img_channels'], S['label_dim'], device=_dev(), cuda_graph=g)
+    plain, graph = mk(False), mk(True)
+    B = 4
+    lab = _labels(S, B)
+    labd = None if lab is None else lab.to(_dev())
+    for k, sigma in enumerate((80.0, 7.0, 1.3, 0.4, 0.02)):
+        x = (O.stacked_randn(range(k, k + B), (3, 16, 16)) * sigma).to(_dev())
+        sig = torch.tensor(sigma, device=_dev())
+        bott_p, bott_g = torch.zeros(B, 64, device=_dev()), torch.zeros(B, 64, device=_dev())
+        want_b = k >= 2
+        a = plain(x, sig, class_labels=labd, bottleneck=bott_p if want_b else None)
+        b = graph(x, sig, class_labels=labd, bottleneck=bott_g if want_b else None)
+        assert torch.equal(a, b), (k, (a - b).abs().max().item())
+        if want_b:
+            assert torch.equal(bott_p, bott_g) and bott_g.abs().sum().item() > 0
+    assert graph.launches_last_forward == plain.launches_last_forward
+    lat = O.stacked_randn(range(B), (3, 16, 16)).to(_dev())
+    a = solvers.heun_sampler(plain, lat, class_labels=labd, num_steps=5)
+    b = solvers.heun_sampler(graph, lat, class_labels=labd, num_steps=5)
+    assert torch.equal(a, b)
+    # per-sample sigma uses another plan (and its own graph)
+    sigs = torch.tensor([3.0, 0.4, 11.0, 0.9], device=_dev())
+    x = lat * sigs[:, None, None, None]
+    for _ in range(3):
+        assert torch.equal(plain(x, sigs, class_labels=labd), graph(x, sigs, class_labels=labd))
+
+
+def test_cuda_graph_replay_ldm():
+    from oracle import edm_oracle as O
+    from oracle import ldm_oracle as LO
+    from diff_sampler_b200.ldm_net import B200LDMNet
+    P, cfg = LO.make_params('tiny_ldm')
+    mk = lambda g: B200LDMNet(P, img_resolution=cfg['img_resolution'], img_channels=cfg['in_channels'], num_heads=cfg['num_heads'],
+                              guidance_rate=7.5, device=_dev(), cuda_graph=g)
+    plain, graph = mk(False), mk(True)
+    B, R = 2, cfg['img_resolution']
+    g = torch.Generator().manual_seed(6)
+    c = torch.randn(B, 77, cfg['context_dim'], generator=g).to(_dev())
+    uc = torch.randn(B, 77, cfg['context_dim'], generator=g).to(_dev())
+    for k, sigma in enumerate((10.0, 2.0, 0.5, 0.1)):
+        x = (O.stacked_randn(range(k, k + B), (4, R, R)) * sigma).to(_dev())
+        sig = torch.tensor([sigma], device=_dev())
+        bp, bg = torch.zeros(B, 64, device=_dev()), torch.zeros(B, 64, device=_dev())
+        a = plain(x, sig, condition=c, unconditional_condition=uc, bottleneck=bp if k % 2 else None)
+        b = graph(x, sig, condition=c, unconditional_condition=uc, bottleneck=bg if k % 2 else None)
+        assert torch.equal(a, b) and torch.equal(bp, bg)
 
 
 def test_fused_uint8_image_epilogue_in_the_last_update():
@@ -851,8 +907,7 @@ def test_dropin_ldm_from_reference_and_as_native():
     assert torch.equal(a, b)
 
 
-# --------------------------------------------------------------------------------------------- first-stage decoder (opt-in)
-@pytest.mark.skipif(os.environ.get('DSB_VAE_TESTS') != '1', reason='VAE decoder path is opt-in until it has a green run on hardware: set DSB_VAE_TESTS=1')
+# --------------------------------------------------------------------------------------------- first-stage decoder
 @pytest.mark.parametrize('name,R', [('tiny_vae', 8), ('wide_vae', 64)])
 def test_vae_decoder_parity(name, R):
     """decode_first_stage through B200VAEDecoder vs the CPU oracle (pinned to the reference Decoder): per-module activations and the
