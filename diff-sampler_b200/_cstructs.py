@@ -35,7 +35,7 @@ class GemmDesc(C.Structure):
         ('residual', P), ('ldr', I64), ('scale', F32),
         ('edm_out', I32), ('edm_x', P), ('edm_coef', P), ('edm_coef_stride', I32), ('edm_C', I32), ('edm_D', P),
         ('st_quads', P),
-        ('tap_dh', I32 * 9), ('tap_dw', I32 * 9), ('tap_cb', I32 * 9), ('acc_scale', F32),
+        ('tap_dh', I32 * 9), ('tap_dw', I32 * 9), ('tap_cb', I32 * 9), ('acc_scale', F32), ('st_unit', I32),
     ]
 
 
@@ -83,7 +83,8 @@ class GegluDesc(C.Structure):
 
 class GnFinalizeDesc(C.Structure):
     _fields_ = [('quads0', P), ('quads1', P), ('C0', I32), ('C1', I32), ('slabs_per_sample', I32), ('B', I32), ('groups', I32),
-                ('pad0', I32), ('sums', P), ('gamma', P), ('beta', P), ('ada', P), ('ada_stride', I64), ('eps', F32), ('HW', I32), ('coef', P)]
+                ('unit0', I32), ('sums', P), ('gamma', P), ('beta', P), ('ada', P), ('ada_stride', I64), ('eps', F32), ('HW', I32), ('coef', P),
+                ('unit1', I32), ('pad1', I32)]
 
 
 class AttnDesc(C.Structure):

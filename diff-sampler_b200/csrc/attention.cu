@@ -328,33 +328,114 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attn_kernel(const __grid_cons
 // profiles/r01b_ncu_attention_sd15_L4096.txt: tensor pipe 33 %, no unit saturated -- the block period was the serial chain
 // PV_j -> softmax pass 2 of block j+1 -> PV_{j+1} through ONE P buffer, plus a per-block exchange between the two halves of a row):
 //   * key blocks of 64; TWO softmax groups of four warps (one warp per TMEM lane quadrant each) take alternate key blocks, each with its
-//     own S accumulator, P buffer and P.V accumulator, its own running (max, sum, output row) -- no exchange inside the key loop; the two
-//     partial results of a row are merged once per tile (the usual split-KV combine);
-//   * the MMA warp issues  QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ...  so the tensor pipe always has the next block's scores and the
-//     other group's P.V queued while one group is in its exponentials;
+//     own P buffer and P.V accumulator, its own running (max, sum, output row) -- no exchange inside the key loop; the two partial results
+//     of a row are merged once per tile (the usual split-KV combine);
+//   * every group has TWO S accumulators in TMEM: the MMA warp keeps the scores of a group's NEXT block ready while the group is in its
+//     exponentials (issue order  QK(0..3) | PV(0) QK(4) | PV(1) QK(5) | ...), so a group never waits for the tensor pipe.  First version
+//     of this kernel (one S buffer per group, profiles/r02/ncu_attn2_v0_*.txt): 43 % of the softmax warps' samples were the wait for the
+//     next scores, tensor pipe 24 %;
+//   * the softmax walks its 64 scores in two chunks of 32 TMEM columns (no register spills: the v0 build spilled 136 bytes into the key
+//     loop and half of its stall samples were local-memory loads); key masking only in the partial last block;
 //   * persistent CTAs (grid = #SMs) walk the (sample, head, query tile) list: TMEM allocation, barrier set-up and descriptor prefetch happen
 //     once, and the loads / first QK products of the next tile run under the softmax tail and the combine of the current one;
-//   * K / V^T blocks go through 3-deep rings that are not tied to a group.
+//   * K / V^T blocks go through rings (3 / 4 deep) that are not tied to a group.
 // Same operand contract as v1 (fp16 hi/lo planes, three MMA passes per product, fp32 accumulate, exact fp32 online softmax).
 static constexpr int kA2Threads = 320;              // warp 0 TMA, warp 1 MMA, warps 2..5 softmax group 0, warps 6..9 group 1
-static constexpr int kA2Ring = 3;
+static constexpr int kA2KRing = 3, kA2VRing = 4;
 static constexpr int kA2QBytes = 2 * 16384;         // Q hi, lo: 128 rows x 64 fp16
 static constexpr int kA2KStage = 2 * 8192;          // K block hi, lo: 64 keys x 64 fp16
 static constexpr int kA2VStage = 2 * 8192;          // V^T block hi, lo: 64 d-rows x 64 keys
 static constexpr int kA2PBuf = 2 * 16384;           // P hi, lo: 128 rows x 64 keys (one buffer per group)
 static constexpr int kA2OffK = kA2QBytes;
-static constexpr int kA2OffV = kA2OffK + kA2Ring * kA2KStage;
-static constexpr int kA2OffP = kA2OffV + kA2Ring * kA2VStage;
-static constexpr int kA2OffCtl = kA2OffP + 2 * kA2PBuf;          // 192 KB
+static constexpr int kA2OffV = kA2OffK + kA2KRing * kA2KStage;
+static constexpr int kA2OffP = kA2OffV + kA2VRing * kA2VStage;
+static constexpr int kA2OffCtl = kA2OffP + 2 * kA2PBuf;          // 208 KB
 
 struct Attn2Ctl {
     uint64_t q_full, q_empty;
-    uint64_t k_full[kA2Ring], k_empty[kA2Ring], v_full[kA2Ring], v_empty[kA2Ring];
-    uint64_t s_full[2], s_empty[2], p_full[2], o_full[2], o_empty[2];
+    uint64_t k_full[kA2KRing], k_empty[kA2KRing], v_full[kA2VRing], v_empty[kA2VRing];
+    uint64_t s_full[2][2], s_empty[2][2];   // [group][S slot]
+    uint64_t p_full[2], o_full[2], o_empty[2];
     uint64_t x_full, x_empty;       // group 1 -> group 0 hand-over of the partial result of a tile (through P buffer 1)
     uint32_t tmem_base;
     float xm[128], xl[128];         // group 1's running max / sum per row
 };
+
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void attn2_softmax_block(uint32_t t_s, uint32_t sP, int row, int kvalid, float scale_log2e, float& m, float& l,
+                                                    float (&O)[64], bool have, uint64_t* o_full_bar, uint32_t o_parity, uint32_t t_o,
+                                                    uint64_t* o_empty_bar, int lane) {
+    // pass 1: row maximum over the block's 64 keys, 32 TMEM columns at a time
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        DSB_TMEM_LD_32(t_s + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (!MASKED || c * 32 + i < kvalid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+    }
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    const float m_new = fmaxf(m, mx * scale_log2e);
+    const float alpha = ex2_approx(m - m_new);       // first block: exp2(-inf) = 0
+    if (have) {
+        // P.V of this group's previous block has completed: fold it in (scaled to the new maximum in the same pass), release the
+        // accumulator -- and with it the P buffer this block is about to overwrite
+        mbar_wait(o_full_bar, o_parity);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            DSB_TMEM_LD_32(t_o + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) O[c * 32 + i] = (O[c * 32 + i] + __uint_as_float(v[i])) * alpha;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty_bar);
+        l *= alpha;
+    }
+    // pass 2: p = exp2(s * scale * log2e - m), split into fp16 hi / lo, swizzled K-major store (one 128-byte row per query and plane)
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        DSB_TMEM_LD_32(t_s + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int col = c * 32 + q8 * 8 + 2 * i;
+                float p0 = ex2_approx(fmaf(__uint_as_float(v[q8 * 8 + 2 * i]), scale_log2e, -m_new));
+                float p1 = ex2_approx(fmaf(__uint_as_float(v[q8 * 8 + 2 * i + 1]), scale_log2e, -m_new));
+                if (MASKED) {
+                    if (col >= kvalid) p0 = 0.f;
+                    if (col + 1 >= kvalid) p1 = 0.f;
+                }
+                l4[i] += p0 + p1;
+                const __half2 h2 = __floats2half2_rn(p0, p1);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+                hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            const int chunk = c * 4 + q8;                        // 16-byte chunk of the 128-byte row
+            const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
+            sts128(sP + off, hw[0], hw[1], hw[2], hw[3]);
+            sts128(sP + 16384 + off, lw[0], lw[1], lw[2], lw[3]);
+        }
+    }
+    l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+    m = m_new;
+}
 
 __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_constant__ AttnKernelParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -372,15 +453,19 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
         tma_prefetch_desc(&p.tmV);
         mbar_init(&ctl->q_full, 1);
         mbar_init(&ctl->q_empty, 1);
-        for (int s = 0; s < kA2Ring; ++s) {
+        for (int s = 0; s < kA2KRing; ++s) {
             mbar_init(&ctl->k_full[s], 1);
             mbar_init(&ctl->k_empty[s], 1);
+        }
+        for (int s = 0; s < kA2VRing; ++s) {
             mbar_init(&ctl->v_full[s], 1);
             mbar_init(&ctl->v_empty[s], 1);
         }
         for (int g = 0; g < 2; ++g) {
-            mbar_init(&ctl->s_full[g], 1);
-            mbar_init(&ctl->s_empty[g], 4);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&ctl->s_full[g][s], 1);
+                mbar_init(&ctl->s_empty[g][s], 4);
+            }
             mbar_init(&ctl->p_full[g], 4);
             mbar_init(&ctl->o_full[g], 1);
             mbar_init(&ctl->o_empty[g], 4);
@@ -389,13 +474,13 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
         mbar_init(&ctl->x_empty, 4);
         fence_barrier_init();
     } else if (warp == 1) {
-        tmem_alloc(&ctl->tmem_base, 256);
+        tmem_alloc(&ctl->tmem_base, 512);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
-    // TMEM columns: S[g] at 64 g (64 columns each), per-block P.V result O[g] at 128 + 64 g
+    // TMEM columns: S[g][slot] at 128 g + 64 slot (64 columns each), per-block P.V result O[g] at 256 + 64 g
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -410,15 +495,15 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
                 tma_load_3d(&p.tmQ, &ctl->q_full, smem, p.q_c0 + h * 64, qt * 128, b);
                 tma_load_3d(&p.tmQ, &ctl->q_full, smem + 16384, p.q_c0 + h * 64, qt * 128, p.B + b);
                 for (int j = 0; j < nkv; ++j) {
-                    const int ks = kc % kA2Ring;
-                    mbar_wait(&ctl->k_empty[ks], ((kc / kA2Ring) & 1) ^ 1);
+                    const int ks = kc % kA2KRing;
+                    mbar_wait(&ctl->k_empty[ks], ((kc / kA2KRing) & 1) ^ 1);
                     mbar_arrive_expect_tx(&ctl->k_full[ks], kA2KStage);
                     uint8_t* sk = smem + kA2OffK + ks * kA2KStage;
                     tma_load_3d(&p.tmK, &ctl->k_full[ks], sk, p.k_c0 + h * 64, j * 64, b);
                     tma_load_3d(&p.tmK, &ctl->k_full[ks], sk + 8192, p.k_c0 + h * 64, j * 64, p.B + b);
                     ++kc;
-                    const int vs = vc % kA2Ring;
-                    mbar_wait(&ctl->v_empty[vs], ((vc / kA2Ring) & 1) ^ 1);
+                    const int vs = vc % kA2VRing;
+                    mbar_wait(&ctl->v_empty[vs], ((vc / kA2VRing) & 1) ^ 1);
                     mbar_arrive_expect_tx(&ctl->v_full[vs], kA2VStage);
                     uint8_t* sv = smem + kA2OffV + vs * kA2VStage;
                     tma_load_3d(&p.tmV, &ctl->v_full[vs], sv, j * 64, h * 64, b);
@@ -436,13 +521,14 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
             uint32_t sc0 = 0, sc1 = 0, pc0 = 0, pc1 = 0;    // S products / P.V products issued per group
             auto issue_qk = [&](int j) {
                 const int g = j & 1;
-                const int ks = kc % kA2Ring;
-                mbar_wait(&ctl->k_full[ks], (kc / kA2Ring) & 1);
+                const int ks = kc % kA2KRing;
                 const uint32_t scg = g ? sc1 : sc0;
-                mbar_wait(&ctl->s_empty[g], (scg & 1) ^ 1);
+                const int slot = scg & 1;
+                mbar_wait(&ctl->k_full[ks], (kc / kA2KRing) & 1);
+                mbar_wait(&ctl->s_empty[g][slot], ((scg >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t sk = smem_u32(smem + kA2OffK + ks * kA2KStage);
-                const uint32_t d_tmem = tmem_base + g * 64;
+                const uint32_t d_tmem = tmem_base + g * 128 + slot * 64;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint64_t da = umma_desc_sw128(sq + (pass == 1 ? 16384 : 0));
@@ -451,21 +537,21 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
                     for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&ctl->k_empty[ks]);
-                umma_commit(&ctl->s_full[g]);
+                umma_commit(&ctl->s_full[g][slot]);
                 ++kc;
                 if (g) ++sc1; else ++sc0;
             };
             auto issue_pv = [&](int j) {
                 const int g = j & 1;
-                const int vs = vc % kA2Ring;
-                mbar_wait(&ctl->v_full[vs], (vc / kA2Ring) & 1);
+                const int vs = vc % kA2VRing;
                 const uint32_t pcg = g ? pc1 : pc0;
+                mbar_wait(&ctl->v_full[vs], (vc / kA2VRing) & 1);
                 mbar_wait(&ctl->p_full[g], pcg & 1);
                 mbar_wait(&ctl->o_empty[g], (pcg & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t sv = smem_u32(smem + kA2OffV + vs * kA2VStage);
                 const uint32_t sp = smem_u32(smem + kA2OffP + g * kA2PBuf);
-                const uint32_t d_tmem = tmem_base + 128 + g * 64;
+                const uint32_t d_tmem = tmem_base + 256 + g * 64;
 #pragma unroll
                 for (int pass = 0; pass < 3; ++pass) {
                     const uint64_t da = umma_desc_sw128(sp + (pass == 1 ? 16384 : 0));
@@ -480,14 +566,14 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 mbar_wait(&ctl->q_full, it & 1);
-                issue_qk(0);
-                if (nkv > 1) issue_qk(1);
-                if (nkv <= 2) umma_commit(&ctl->q_empty);            // all S products of this tile are issued: Q may be overwritten once they complete
+                const int ahead = nkv < 4 ? nkv : 4;             // score products run two blocks ahead of each group
+                for (int j = 0; j < ahead; ++j) issue_qk(j);
+                if (nkv <= 4) umma_commit(&ctl->q_empty);        // all S products of this tile are issued: Q may be overwritten once they complete
                 for (int j = 0; j < nkv; ++j) {
                     issue_pv(j);
-                    if (j + 2 < nkv) {
-                        issue_qk(j + 2);
-                        if (j + 3 == nkv) umma_commit(&ctl->q_empty);
+                    if (j + 4 < nkv) {
+                        issue_qk(j + 4);
+                        if (j + 5 == nkv) umma_commit(&ctl->q_empty);
                     }
                 }
             }
@@ -498,9 +584,8 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
         const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;               // query row inside the tile
         const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const uint32_t t_s = t_row + g * 64;
-        const uint32_t t_o = t_row + 128 + g * 64;
-        uint8_t* sP = smem + kA2OffP + g * kA2PBuf;
+        const uint32_t t_o = t_row + 256 + g * 64;
+        const uint32_t sP = smem_u32(smem + kA2OffP + g * kA2PBuf);
         float* xO = reinterpret_cast<float*>(smem + kA2OffP + kA2PBuf);       // group 1's P buffer doubles as the hand-over area [64][128]
         uint32_t bc = 0, it = 0;                        // key blocks processed by this group / tiles processed
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -512,106 +597,46 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 64; ++i) O[i] = 0.f;
             bool have = false;
-            auto add_block_output = [&]() {
-                // P.V of this group's previous block has completed: fold it in, release the accumulator (and with it the P buffer)
-                mbar_wait(&ctl->o_full[g], (bc - 1) & 1);
-                tc_fence_after();
-                uint32_t v[2][32];
-                DSB_TMEM_LD_32(t_o, v[0]);
-                DSB_TMEM_LD_32(t_o + 32, v[1]);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[c][i]);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->o_empty[g]);
-            };
             for (int j = g; j < nkv; j += 2) {
                 if (g == 1 && !have) {
                     // first write of this tile into P buffer 1: group 0 must have read the previous tile's hand-over out of it
                     mbar_wait(&ctl->x_empty, (it & 1) ^ 1);
                 }
-                mbar_wait(&ctl->s_full[g], bc & 1);
+                const int slot = bc & 1;
+                mbar_wait(&ctl->s_full[g][slot], (bc >> 1) & 1);
                 tc_fence_after();
                 const int kvalid = p.Lk - j * 64;        // keys of this block that exist (>= 64: all)
-                // pass 1: row maximum over the block's 64 keys (four independent chains)
-                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                {
-                    uint32_t v[2][32];
-                    DSB_TMEM_LD_32(t_s, v[0]);
-                    DSB_TMEM_LD_32(t_s + 32, v[1]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        if (kvalid >= 64) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (c * 32 + i < kvalid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[c][i]));
-                        }
-                    }
-                }
-                const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-                const float m_new = fmaxf(m, mx * p.scale_log2e);
-                const float alpha = ex2_approx(m - m_new);   // first block: exp2(-inf) = 0
-                if (have) add_block_output();
-                if (alpha != 1.f) {
-#pragma unroll
-                    for (int i = 0; i < 64; ++i) O[i] *= alpha;
-                    l *= alpha;
-                }
-                // pass 2: p = exp2(s * scale * log2e - m), split into fp16 hi / lo, swizzled K-major store (one 128-byte row per query)
-                float l4[4] = {0.f, 0.f, 0.f, 0.f};
-                {
-                    uint32_t v[2][32];
-                    DSB_TMEM_LD_32(t_s, v[0]);
-                    DSB_TMEM_LD_32(t_s + 32, v[1]);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-#pragma unroll
-                        for (int q8 = 0; q8 < 4; ++q8) {
-                            uint32_t hw[4], lw[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int col = c * 32 + q8 * 8 + 2 * i;
-                                float p0 = ex2_approx(fmaf(__uint_as_float(v[c][q8 * 8 + 2 * i]), p.scale_log2e, -m_new));
-                                float p1 = ex2_approx(fmaf(__uint_as_float(v[c][q8 * 8 + 2 * i + 1]), p.scale_log2e, -m_new));
-                                if (kvalid < 64) {
-                                    if (col >= kvalid) p0 = 0.f;
-                                    if (col + 1 >= kvalid) p1 = 0.f;
-                                }
-                                l4[i] += p0 + p1;
-                                const __half2 h2 = __floats2half2_rn(p0, p1);
-                                const float2 hf = __half22float2(h2);
-                                const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
-                                hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
-                                lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
-                            }
-                            const int chunk = c * 4 + q8;                        // 16-byte chunk of the 128-byte row
-                            const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
-                            *reinterpret_cast<uint4*>(sP + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                            *reinterpret_cast<uint4*>(sP + 16384 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                        }
-                    }
-                }
-                l += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-                m = m_new;
+                const uint32_t t_s = t_row + g * 128 + slot * 64;
+                if (kvalid >= 64)
+                    attn2_softmax_block<false>(t_s, sP, row, 64, p.scale_log2e, m, l, O, have, &ctl->o_full[g], (bc - 1) & 1, t_o, &ctl->o_empty[g], lane);
+                else
+                    attn2_softmax_block<true>(t_s, sP, row, kvalid, p.scale_log2e, m, l, O, have, &ctl->o_full[g], (bc - 1) & 1, t_o, &ctl->o_empty[g], lane);
                 have = true;
                 ++bc;
                 tc_fence_before();
                 fence_proxy_async();                    // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(&ctl->s_empty[g]);
+                    mbar_arrive(&ctl->s_empty[g][slot]);
                     mbar_arrive(&ctl->p_full[g]);
                 }
             }
-            if (have) add_block_output();
+            if (have) {
+                // the last block's P.V
+                mbar_wait(&ctl->o_full[g], (bc - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t v[32];
+                    DSB_TMEM_LD_32(t_o + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) O[c * 32 + i] += __uint_as_float(v[i]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->o_empty[g]);
+            }
             // ---- merge the two groups' partial results of this tile (rows are independent: thread `row` of group 1 hands its row to
             //      thread `row` of group 0) and write the output
             if (nkv > 1) {
@@ -662,7 +687,7 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 256);
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------ host

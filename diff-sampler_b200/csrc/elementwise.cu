@@ -73,7 +73,9 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(ds_gn_finalize_desc d)
     const int n = blockIdx.x;
     const int C = d.C0 + d.C1;
     if (d.quads0) {
-        const int w0 = d.C0 / 2, w1 = d.C1 / 2;           // floats per partial row of each source
+        // partial rows: {sum, sumsq} per unit of u0 / u1 channels (4 = quads, 2 = pairs) -> w floats per 32-row slab
+        const int u0 = d.unit0 == 2 ? 2 : 4, u1 = d.unit1 == 2 ? 2 : 4;
+        const int w0 = d.C0 / u0 * 2, w1 = d.C1 / u1 * 2;
         for (int t = threadIdx.x; t < w0 + w1; t += blockDim.x) {
             const float* src = (t < w0) ? d.quads0 + (long long)n * d.slabs_per_sample * w0 + t
                                         : d.quads1 + (long long)n * d.slabs_per_sample * w1 + (t - w0);
@@ -84,11 +86,18 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(ds_gn_finalize_desc d)
             s_cols[t] = acc;
         }
         __syncthreads();
-        const int qpg = C / d.groups / 4;                 // quads per group
+        const int cpg = C / d.groups;
         for (int j = threadIdx.x; j < 2 * d.groups; j += blockDim.x) {
             const int g = j >> 1, k = j & 1;
+            // channels [g * cpg, (g + 1) * cpg): whole units of source 0, then of source 1 (group boundaries fall on unit boundaries,
+            // and C0 is a multiple of cpg or the group straddles the two sources at a unit boundary of each)
             double acc = 0.0;
-            for (int q = g * qpg; q < (g + 1) * qpg; ++q) acc += s_cols[2 * q + k];
+            int c = g * cpg;
+            const int c_end = c + cpg;
+            while (c < c_end) {
+                if (c < d.C0) { acc += s_cols[(c / u0) * 2 + k]; c += u0; }
+                else { acc += s_cols[w0 + ((c - d.C0) / u1) * 2 + k]; c += u1; }
+            }
             d.sums[((long long)n * d.groups + g) * 2 + k] = acc;
         }
         __syncthreads();
@@ -402,7 +411,7 @@ __global__ void __launch_bounds__(512) gn_apply_v2_kernel(ds_gn_apply_desc d, in
 // paying an fp64 mean / rsqrt prologue for 16 pixels of work -- 76 % of the copy bandwidth.  Here the (sample, pixel
 // row) space is cut into gridDim.x equal ranges (+-1 row), the grid is exactly the number of co-resident CTAs, and a thread fetches its
 // 16 coefficients (4 x 16 B, L2-resident table written by gn_finalize) only when its range crosses into another sample.
-__global__ void __launch_bounds__(512) gn_apply_v3_kernel(ds_gn_apply_desc d, int nc8, int rows, int units_per_sample, long long total_units) {
+__global__ void __launch_bounds__(256, 3) gn_apply_v3_kernel(ds_gn_apply_desc d, int nc8, int rows, int units_per_sample, long long total_units) {
     const int C = d.C0 + d.C1;
     const int c8 = threadIdx.x % nc8;
     const int prow = threadIdx.x / nc8;
@@ -869,10 +878,18 @@ extern "C" int ds_gn_stats_launch(const ds_gn_stats_desc* d, cudaStream_t stream
 extern "C" int ds_gn_finalize_launch(const ds_gn_finalize_desc* d, cudaStream_t stream) {
     const int C = d->C0 + d->C1;
     if (d->groups <= 0 || d->groups > 64 || C % d->groups) return -2;
-    if (d->quads0 && (d->C0 % 4 || d->C1 % 4 || (C / d->groups) % 4 || (d->C1 > 0 && !d->quads1))) return -2;
+    if (d->quads0) {
+        const int u0 = d->unit0 == 2 ? 2 : 4, u1 = d->unit1 == 2 ? 2 : 4;
+        const int cpg = C / d->groups;
+        if (d->C0 % u0 || d->C1 % u1 || (d->C1 > 0 && !d->quads1)) return -2;
+        // every group must be a union of whole partial units of the sources it covers
+        const int rem = d->C0 % cpg;                    // channels of a group that straddles the two sources, on the source-0 side
+        if (cpg % u0 || rem % u0) return -2;
+        if (d->C1 > 0 && (cpg % u1 || (rem ? (cpg - rem) % u1 : 0))) return -2;
+    }
     if (!d->quads0 && !d->coef) return -2;               // nothing to do
     if (d->coef && (!d->gamma || !d->beta || d->HW <= 0)) return -2;
-    gn_finalize_kernel<<<d->B, 256, (size_t)(C / 2 + 1) * sizeof(double), stream>>>(*d);
+    gn_finalize_kernel<<<d->B, 256, (size_t)(C + 2) * sizeof(double), stream>>>(*d);
     return ok();
 }
 
@@ -893,6 +910,7 @@ extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream
     while (pix_per_cta > rows && (long long)((npix + pix_per_cta - 1) / pix_per_cta) * d->B < 148 * 4) pix_per_cta /= 2;
     const int chunks = (npix + pix_per_cta - 1) / pix_per_cta;
     dim3 grid(chunks, d->B);
+    if (d->coef && d->resample == 0 && d->sums == nullptr && threads > 256) return -2;      // wider than 2048 channels: use the sums path
     if (d->coef && d->resample == 0 && d->sums == nullptr) {
         // persistent variant: grid = co-resident CTAs (occupancy query per block size and device, cached)
         static int occ[64][17] = {};

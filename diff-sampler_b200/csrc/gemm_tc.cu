@@ -58,6 +58,7 @@ struct alignas(64) GemmKernelParams {
     // fused GroupNorm statistics of the tensor being written (up to two consumers with their own channel grouping):
     // per 32-row slab partial {sum, sumsq} per group, plain stores (no atomics); the consumer adds the slabs of a sample.
     float* st_quads;
+    int st_unit;                         // 4 (quads) or 2 (pairs)
     int tap_dh[9], tap_dw[9], tap_cb[9];
     // CTA-pair variant (gemm_tc_pair_kernel; appended so that the single-CTA kernel's parameter offsets stay put)
     CUtensorMap tmBh, tmB8h;             // B boxes of BN/2 rows: each CTA of a pair loads half of the N tile
@@ -77,7 +78,7 @@ struct SmemCtl {
 // On return v[0] of lane L is the full sum of value index (L >> (5 - log2 NV)) (NV = 16: L >> 1; NV = 8: L >> 2).
 template <int NV>
 __device__ __forceinline__ void warp_sum_multi(float (&v)[NV], int lane) {
-    static_assert(NV == 16 || NV == 8, "NV");
+    static_assert(NV == 32 || NV == 16 || NV == 8, "NV");
     int off = 16;
 #pragma unroll
     for (int n = NV / 2; n >= 1; n >>= 1) {
@@ -161,19 +162,34 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     for (int j = 0; j < W; ++j) r[j] *= p.scale;
 
     if (p.st_quads) {
-        // GroupNorm partials of this 32-row slab: per channel quad {sum, sumsq}, reduced over the warp's 32 rows
-        float q[W / 2];
-#pragma unroll
-        for (int j = 0; j < W; j += 4) {
-            q[j / 2] = (r[j] + r[j + 1]) + (r[j + 2] + r[j + 3]);
-            q[j / 2 + 1] = fmaf(r[j], r[j], r[j + 1] * r[j + 1]) + fmaf(r[j + 2], r[j + 2], r[j + 3] * r[j + 3]);
-        }
         const int lane = threadIdx.x & 31;
-        warp_sum_multi<W / 2>(q, lane);
-        constexpr int kShift = (W == 32) ? 1 : 2;            // lane L holds value L >> kShift = 2 * quad + {0: sum, 1: sumsq}
-        const int vi = lane >> kShift;
-        if ((lane & ((1 << kShift) - 1)) == 0 && col0 + 4 * (vi >> 1) < p.n_valid)
-            p.st_quads[((grow_in_z >> 5) * (long long)(p.n_valid >> 2)) * 2 + (col0 >> 1) + vi] = q[0];
+        if (p.st_unit == 2) {
+            // per channel PAIR {sum, sumsq} (consumers whose groups are even but not multiples of four channels)
+            float q[W];
+#pragma unroll
+            for (int j = 0; j < W; j += 2) {
+                q[j] = r[j] + r[j + 1];
+                q[j + 1] = fmaf(r[j], r[j], r[j + 1] * r[j + 1]);
+            }
+            warp_sum_multi<W>(q, lane);
+            constexpr int kShift = (W == 32) ? 0 : 1;        // lane L holds value L >> kShift = 2 * pair + {0: sum, 1: sumsq}
+            const int vi = lane >> kShift;
+            if ((lane & ((1 << kShift) - 1)) == 0 && col0 + 2 * (vi >> 1) < p.n_valid)
+                p.st_quads[(grow_in_z >> 5) * (long long)p.n_valid + col0 + vi] = q[0];
+        } else {
+            // GroupNorm partials of this 32-row slab: per channel quad {sum, sumsq}, reduced over the warp's 32 rows
+            float q[W / 2];
+#pragma unroll
+            for (int j = 0; j < W; j += 4) {
+                q[j / 2] = (r[j] + r[j + 1]) + (r[j + 2] + r[j + 3]);
+                q[j / 2 + 1] = fmaf(r[j], r[j], r[j + 1] * r[j + 1]) + fmaf(r[j + 2], r[j + 2], r[j + 3] * r[j + 3]);
+            }
+            warp_sum_multi<W / 2>(q, lane);
+            constexpr int kShift = (W == 32) ? 1 : 2;        // lane L holds value L >> kShift = 2 * quad + {0: sum, 1: sumsq}
+            const int vi = lane >> kShift;
+            if ((lane & ((1 << kShift) - 1)) == 0 && col0 + 4 * (vi >> 1) < p.n_valid)
+                p.st_quads[((grow_in_z >> 5) * (long long)(p.n_valid >> 2)) * 2 + (col0 >> 1) + vi] = q[0];
+        }
     }
 
     if (p.edm_out) {
@@ -717,6 +733,8 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     kp->edm_out = d->edm_out; kp->edm_x = d->edm_x; kp->edm_coef = d->edm_coef; kp->edm_coef_stride = d->edm_coef_stride;
     kp->edm_C = d->edm_C; kp->edm_D = d->edm_D;
     kp->st_quads = d->st_quads;
+    kp->st_unit = d->st_unit == 2 ? 2 : 4;
+    if (d->st_unit != 0 && d->st_unit != 2 && d->st_unit != 4) return -14;
     kp->acc_scale = d->acc_scale == 0.f ? 1.f : d->acc_scale;
     if (d->f8 & 1) {
         // e4m3 correction passes: byte planes behind the fp16 plane of each operand (layout: csrc/ops.h)
@@ -754,7 +772,7 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     // image rows wider than one M tile are only handled by the pair kernel's tile -> (w, h, n) mapping
     if (d->a_mode == 0 && d->conv_W > 128 && !((d->f8 & 2) && d->BN % 32 == 0 && d->num_z == 1 && d->conv_W % 128 == 0)) return -13;
     // fused statistics: whole 32-row slabs (row validity is then warp-uniform), whole channel quads, one z slice, fp32 output
-    if (d->st_quads && (d->num_z != 1 || d->m_valid % 32 != 0 || d->n_valid % 4 != 0 || d->edm_out != 0)) return -14;
+    if (d->st_quads && (d->num_z != 1 || d->m_valid % 32 != 0 || d->n_valid % (d->st_unit == 2 ? 2 : 4) != 0 || d->edm_out != 0)) return -14;
     int stage_bytes = kATileBytes + d->BN * 128;
     // CTA-pair variant (opt-in): convolution GEMMs with at least two full waves of row pairs and an N tile that splits into two
     // whole 32-row halves; everything else keeps the single-CTA kernel

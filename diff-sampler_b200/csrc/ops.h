@@ -94,6 +94,9 @@ typedef struct ds_gemm_desc {
     int32_t tap_dw[9];
     int32_t tap_cb[9];
     float acc_scale;        // accumulator pre-scale (0 is read as 1); 2^-S in f8 mode
+    int32_t st_unit;        // channels per statistics partial of st_quads: 4 (default; 0 is read as 4) or 2 (channel PAIRS, for consumers whose
+                            // GroupNorm groups are even but not multiples of 4 channels: the 6-, 18-, 30-channel groups of the ADM net);
+                            // layout st_quads[((row/32) * (n_valid/unit) + channel/unit) * 2 + {0,1}]
 } ds_gemm_desc;
 
 int ds_gemm_launch(const ds_gemm_desc* d, cudaStream_t stream);
@@ -153,8 +156,8 @@ typedef struct ds_gn_finalize_desc {
     int32_t C0, C1;
     int32_t slabs_per_sample;   // H*W / 32
     int32_t B;
-    int32_t groups;         // (C0 + C1) / groups must be a multiple of 4 (when quads0 != NULL)
-    int32_t pad0;
+    int32_t groups;         // (C0 + C1) / groups must be a multiple of the partial units (when quads0 != NULL)
+    int32_t unit0;          // channels per partial of quads0: 4 (0 is read as 4) or 2 (ds_gemm_desc.st_unit of its producer)
     double* sums;           // [B][groups][2]: overwritten from the quads; with quads0 == NULL it is the INPUT (written by ds_gn_stats)
     // optional second product (coef != NULL): the per-(sample, channel) coefficients ds_gn_apply_desc.coef describes
     const float* gamma;
@@ -164,6 +167,8 @@ typedef struct ds_gn_finalize_desc {
     float eps;
     int32_t HW;             // pixels per sample (statistics count = HW * C / groups)
     float* coef;            // [B][C0 + C1][2]
+    int32_t unit1;          // channels per partial of quads1 (as unit0)
+    int32_t pad1;
 } ds_gn_finalize_desc;
 
 // Fused softmax attention, head dim padded to 64 (attention.cu): out[b][l][h*64 + c] = sum_k softmax_k(scale * q_l . k_k) v_k[c].

@@ -166,7 +166,7 @@ class Plan:
         self.meta = meta
 
 
-def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash_attn=True, f8=False, gn_coef=True):
+def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash_attn=True, f8=False, gn_coef=True, pair_stats=True):
     """Lower the forward pass for batch B.  nsig in {1, B}: number of sigma values (embedding rows);
     nlab in {0, 1, B}: rows of class labels supplied.  f8: the block convolutions run in the f8 GEMM mode (weights must have been
     packed with pack_weights(f8=True)).  gn_coef: GroupNorm coefficient tables + persistent gn_apply (False = the round-1 lowering)."""
@@ -198,6 +198,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
     # next block and the decoder block that concatenates it as a skip.  No atomics, no pass over the tensor itself.
     prod_of = {}            # buffer name -> (op index of the GEMM that wrote it, Cout, rows)
     quads_of = {}           # producer op index -> arena name of its quad-partial buffer
+    unit_of = {}            # producer op index -> channels per partial (4 = quads, 2 = pairs: some consumer has 6/18/30-channel groups)
 
     def emit_producer(name, cout, m_rows, build):
         pid = len(ops)
@@ -207,6 +208,7 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
             d = build(R)
             if pid in quads_of:
                 d.st_quads = R(quads_of[pid])
+                d.st_unit = unit_of[pid]
             return d
         emit(materialise)
 
@@ -220,9 +222,14 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
         g = _groups(c_total)
         cpg = c_total // g
         (n0, c0), (n1, c1) = parts[0], (parts[1] if len(parts) > 1 else (None, 0))
-        fusable = (fuse_stats and hw % 32 == 0 and cpg % 4 == 0 and all(c % 4 == 0 for _, c in parts)
+        # partial granularity each producer must write for this consumer: 4 channels (quads) when the groups -- and, for a virtual concat
+        # whose first source does not end on a group boundary, both pieces of the straddling group -- are multiples of 4, else 2 (pairs)
+        rem = c0 % cpg if n1 else 0
+        pieces = [cpg] + ([rem, cpg - rem] if rem else [])
+        unit = 4 if all(p % 4 == 0 for p in pieces) else (2 if all(p % 2 == 0 for p in pieces) and pair_stats else 0)
+        fusable = (fuse_stats and hw % 32 == 0 and unit and all(c % unit == 0 for _, c in parts)
                    and all(name in prod_of and prod_of[name][1] == c for name, c in parts))
-        want_coef = norm is not None and gn_coef
+        want_coef = norm is not None and gn_coef and c_total <= 2048        # the persistent gn_apply covers up to 256 eight-channel columns
         if want_coef:
             A.need('gncoef', B * c_total * 2 * F4)
 
@@ -237,14 +244,17 @@ def compile_plan(spec, wb, winfo, B, nsig, nlab, npass=3, fuse_stats=True, flash
                 emit(lambda R: S.GnFinalizeDesc(quads0=0, quads1=0, C0=c0, C1=c1, slabs_per_sample=0, B=B, groups=g, sums=R('stats', slot),
                                                 **coef_args(R)))
             return want_coef
-        bufs = []
+        bufs, pids = [], []
         for name, c in parts:
             pid, cout, m_rows = prod_of[name]
-            if pid not in quads_of:
-                quads_of[pid] = A.need('quads:' + name, (m_rows // 32) * (cout // 4) * 2 * F4)
+            unit_of[pid] = min(unit_of.get(pid, 4), unit)           # a producer serves all its consumers at the finest unit any of them needs
+            quads_of[pid] = A.need('quads:' + name, (m_rows // 32) * (cout // unit_of[pid]) * 2 * F4)
             bufs.append(quads_of[pid])
+            pids.append(pid)
+        # unit_of is final only once the whole net is lowered: read it when the descriptors are materialised
         emit(lambda R: S.GnFinalizeDesc(quads0=R(bufs[0]), quads1=R(bufs[1]) if len(bufs) > 1 else 0, C0=c0, C1=c1,
-                                        slabs_per_sample=hw // 32, B=B, groups=g, sums=R('stats', slot), **coef_args(R)))
+                                        slabs_per_sample=hw // 32, B=B, groups=g, sums=R('stats', slot), unit0=unit_of[pids[0]],
+                                        unit1=unit_of[pids[1]] if len(pids) > 1 else 4, **coef_args(R)))
         return want_coef
 
     def stat_args(R, slot, coef=False):

@@ -235,8 +235,9 @@ def _gemm(mem, d):
             r = r + _strided(res, (m_valid, n_valid), (ldr, 1)).double()
         r = r * float(d.scale)
         if d.st_quads:
-            assert m_valid % 32 == 0 and n_valid % 4 == 0
-            q = r.reshape(m_valid // 32, 32, n_valid // 4, 4)
+            u = 2 if int(d.st_unit) == 2 else 4
+            assert m_valid % 32 == 0 and n_valid % u == 0
+            q = r.reshape(m_valid // 32, 32, n_valid // u, u)
             part = torch.stack([q.sum(dim=(1, 3)), (q * q).sum(dim=(1, 3))], dim=-1)             # [slabs, quads, 2]
             mem.view(d.st_quads, torch.float32, part.numel())[:] = part.reshape(-1).float()
         if d.edm_out:
@@ -290,12 +291,20 @@ def _gn_finalize(mem, d):
     C0, C1 = int(d.C0), int(d.C1)
     C = C0 + C1
     if d.quads0:
-        q = mem.view(d.quads0, torch.float32, B * slabs * (C0 // 4) * 2).reshape(B, slabs, C0 // 4, 2).double().sum(dim=1)
+        u0, u1 = (2 if int(d.unit0) == 2 else 4), (2 if int(d.unit1) == 2 else 4)
+        # per-channel view of the partials (each unit's sums attributed to its first channel) so that any grouping can be summed
+        def per_channel(ptr, Cx, u):
+            q = mem.view(ptr, torch.float32, B * slabs * (Cx // u) * 2).reshape(B, slabs, Cx // u, 2).double().sum(dim=1)
+            out = torch.zeros(B, Cx, 2, dtype=torch.float64)
+            out[:, ::u, :] = q
+            return out
+        pc = per_channel(d.quads0, C0, u0)
         if C1:
-            q1 = mem.view(d.quads1, torch.float32, B * slabs * (C1 // 4) * 2).reshape(B, slabs, C1 // 4, 2).double().sum(dim=1)
-            q = torch.cat([q, q1], dim=1)
-        qpg = C // G // 4
-        mem.view(d.sums, torch.float64, B * G * 2)[:] = q.reshape(B, G, qpg, 2).sum(dim=2).reshape(-1)
+            pc = torch.cat([pc, per_channel(d.quads1, C1, u1)], dim=1)
+        cpg = C // G
+        rem = C0 % cpg
+        assert cpg % u0 == 0 and rem % u0 == 0 and (not C1 or (cpg % u1 == 0 and (cpg - rem) % u1 == 0 or rem == 0 and cpg % u1 == 0))
+        mem.view(d.sums, torch.float64, B * G * 2)[:] = pc.reshape(B, G, cpg, 2).sum(dim=2).reshape(-1)
     if d.coef:
         # per-(sample, channel) {a, b}: y = x * a + b, in fp32 as the kernel computes them (elementwise.cu gn_finalize_kernel)
         s = mem.view(d.sums, torch.float64, B * G * 2).reshape(B, G, 2)

@@ -423,6 +423,53 @@ def test_conv_epilogue_fused_groupnorm_stats(lib, Bn, H, W, Cout, groups_cat):
     assert e1 < 1e-4 * max(1.0, r1.abs().max().item()) and e2 < 1e-4 * max(1.0, r2.abs().max().item())
 
 
+@pytest.mark.parametrize('Bn,H,W,Cout,C1,u1', [(3, 16, 16, 192, 0, 4), (2, 8, 8, 576, 0, 4), (2, 16, 16, 128, 64, 2), (4, 8, 8, 192, 144, 4), (2, 32, 32, 48, 0, 4)])
+def test_conv_epilogue_pair_partials_for_even_groups(lib, Bn, H, W, Cout, C1, u1):
+    """Round 2: ds_gemm_desc.st_unit = 2 stores the GroupNorm partials per channel PAIR, so that consumers whose groups are even but not
+    multiples of four channels (ADM: 192 / 32 = 6, 576 / 32 = 18; concatenations: (128 + 64) / 32 = 6 with a group straddling the two
+    sources at a pair boundary, (192 + 144) / 28 = 12) get their statistics from the GEMM epilogue too.  The second source may be a
+    quad-partial buffer (a producer keeps quads when all ITS consumers allow them): mixed units in one finalize."""
+    from diff_sampler_b200 import _cstructs as S
+    from diff_sampler_b200 import gemm_desc as G
+    torch.manual_seed(12)
+    Cin = 64
+    M = Bn * H * W
+    slabs = M // 32
+
+    def conv_with_partials(Cc, unit):
+        x = torch.randn(Bn, Cin, H, W, device=dev())
+        w = torch.randn(Cc, Cin, 3, 3, device=dev()) / (3 * Cin ** 0.5)
+        out = torch.zeros(M, Cc, device=dev())
+        part = torch.full((slabs, Cc // unit, 2), float('nan'), device=dev())
+        d, _ = G.conv_gemm(planes(x.permute(0, 2, 3, 1).contiguous()).data_ptr(), Bn, H, W, Cin, G.pack_conv_weight(w.cpu()).to(dev()).data_ptr(), Cc,
+                           taps=9, npass=3, out_f32=out.data_ptr(), scale=0.7)
+        d.st_quads, d.st_unit = part.data_ptr(), unit
+        lib.op_launch(d)
+        sync()
+        y = out.double()
+        ys = y.reshape(slabs, 32, Cc // unit, unit)
+        ref = torch.stack([ys.sum(dim=(1, 3)), (ys ** 2).sum(dim=(1, 3))], dim=-1)
+        err = (part.double() - ref).abs().max().item()
+        assert err < 1e-4 * max(1.0, ref.abs().max().item()), (Cc, unit, err)
+        return y, part
+    y0, p0 = conv_with_partials(Cout, 2)
+    if C1:
+        y1, p1 = conv_with_partials(C1, u1)
+    Cc = Cout + C1
+    groups = min(32, Cc // 4)
+    while Cc % groups:
+        groups -= 1
+    sums = torch.full((Bn, groups, 2), float('nan'), dtype=torch.float64, device=dev())
+    lib.op_launch(S.GnFinalizeDesc(quads0=p0.data_ptr(), quads1=p1.data_ptr() if C1 else 0, C0=Cout, C1=C1, slabs_per_sample=H * W // 32, B=Bn,
+                                   groups=groups, unit0=2, unit1=u1, sums=sums.data_ptr()))
+    sync()
+    yc = (torch.cat([y0, y1], dim=1) if C1 else y0).reshape(Bn, H * W, groups, Cc // groups)
+    ref = torch.stack([yc.sum(dim=(1, 3)), (yc ** 2).sum(dim=(1, 3))], dim=-1)
+    err = (sums - ref).abs().max().item()
+    print(f'pair partials C{Cout}+{C1} groups {groups} ({Cc // groups} channels each): finalize err {err:.3e} (max {ref.abs().max().item():.1f})')
+    assert err < 1e-4 * max(1.0, ref.abs().max().item())
+
+
 def test_fused_stats_rejects_partial_slabs(lib):
     """st_quads needs whole 32-row slabs (here M = 2*4*4 = 32 is fine, 3*4*4 = 48 is not): rc -14, surfaced as DsError."""
     from diff_sampler_b200 import gemm_desc as G
