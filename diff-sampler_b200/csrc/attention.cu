@@ -690,11 +690,403 @@ __global__ void __launch_bounds__(kA2Threads, 1) attn2_kernel(const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------ host
-static bool attn_use_v1() {
-    static const int v = [] { const char* e = getenv("DSB_ATTN_V1"); return e ? atoi(e) : 0; }();
-    return v != 0;
+// ------------------------------------------------------------------------------------------ v3: four softmax groups, output in TMEM
+// ncu of v2 (profiles/r02/ncu_attn2_v1_imagenet64_L1024.txt): tensor pipe 29 %, issue slots 32 % busy, 43 % of the softmax warps' samples in
+// ONE wait -- for the P.V product of their previous block, which they need (a) to fold into the register-resident output row and (b) before
+// they may overwrite their P buffer.  With two warps per scheduler nothing covers that wait, and the exponentials (~8 instructions per
+// score: scale, ex2, sum, fp16 hi/lo split) cannot reach one instruction per cycle.  v3 changes the division of labour:
+//   * FOUR softmax groups (16 warps, one per TMEM lane quadrant and group; blocks j = g, g + 4, ...): four warps per scheduler cover each
+//     other's waits and dependency stalls;
+//   * the running output row stays in TMEM: P.V accumulates across a group's blocks (tcgen05.mma accumulate), so the softmax warps no longer
+//     read 64 output columns per block.  The usual rescaling by exp2(m_old - m_new) is LAZY: a row keeps exponentiating against its
+//     current reference maximum until a block's maximum exceeds it by more than 8 (p <= 2^8: harmless for the fp16 hi/lo split, exact
+//     for the final O / l); only then -- a warp vote -- the group rescales its accumulator in place (tcgen05.ld -> multiply -> tcgen05.st);
+//   * per thread that leaves: row maximum (FMNMX3), p = ex2(s * scale - m), the sum, the hi/lo split and the swizzled stores -- ~6
+//     instructions per score and ~75 live registers, which is what lets 18 warps fit the register file (112 registers per thread);
+//   * one S accumulator per group (4 x 64 TMEM columns) + one output accumulator per group (4 x 64): all 512 columns; K / V rings two deep
+//     with the K loads running two blocks ahead of the V loads; P buffers 4 x 32 KB: 224 KB of shared memory in all;
+//   * the four partial results of a row are merged at the end of a tile in normalised form (O_g / l_g and lambda_g = m_g + log2 l_g).
+// NG softmax groups: 4 (K / V rings two deep) or 3 (rings three deep) -- the same 224 KB either way; DSB_ATTN_GROUPS selects (default below).
+template <int NG> struct A3 {
+    static constexpr int kThreads = 64 + NG * 128;             // warp 0 TMA, warp 1 MMA, then four warps per softmax group
+    static constexpr int kRing = NG == 4 ? 2 : 3;
+    static constexpr int kOffK = kA2QBytes;
+    static constexpr int kOffV = kOffK + kRing * kA2KStage;
+    static constexpr int kOffP = kOffV + kRing * kA2VStage;
+    static constexpr int kOffCtl = kOffP + NG * kA2PBuf;      // 224 KB
+};
+static constexpr float kA3RescaleThreshold = 8.0f;
+
+template <int NG> struct Attn3Ctl {
+    uint64_t q_full, q_empty;
+    uint64_t k_full[A3<NG>::kRing], k_empty[A3<NG>::kRing], v_full[A3<NG>::kRing], v_empty[A3<NG>::kRing];
+    uint64_t s_full[NG], s_empty[NG], p_full[NG], o_full[NG], o_empty[NG];
+    uint64_t x_full[NG], x_empty[NG];
+    uint32_t tmem_base;
+    float xl[NG - 1][128];          // lambda = m + log2(l) of groups 1 .. NG - 1, per row
+};
+static constexpr int kA3SmemBytes = 227 * 1024;      // everything the SM has: 224 KB of tiles + the control block + alignment slack
+
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+
+template <bool MASKED>
+__device__ __forceinline__ float attn3_row_max(uint32_t t_s, int kvalid) {
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        DSB_TMEM_LD_32(t_s + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (!MASKED || c * 32 + i < kvalid) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+    }
+    return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+}
+
+template <bool MASKED>
+__device__ __forceinline__ float attn3_exp_store(uint32_t t_s, uint32_t sP, int row, int kvalid, float scale_log2e, float m_ref) {
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        DSB_TMEM_LD_32(t_s + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int col = c * 32 + q8 * 8 + 2 * i;
+                float p0 = ex2_approx(fmaf(__uint_as_float(v[q8 * 8 + 2 * i]), scale_log2e, -m_ref));
+                float p1 = ex2_approx(fmaf(__uint_as_float(v[q8 * 8 + 2 * i + 1]), scale_log2e, -m_ref));
+                if (MASKED) {
+                    if (col >= kvalid) p0 = 0.f;
+                    if (col + 1 >= kvalid) p1 = 0.f;
+                }
+                l4[i] += p0 + p1;
+                const __half2 h2 = __floats2half2_rn(p0, p1);
+                const float2 hf = __half22float2(h2);
+                const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+                hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            const int chunk = c * 4 + q8;                        // 16-byte chunk of the 128-byte row
+            const uint32_t off = row * 128 + ((chunk ^ (row & 7)) << 4);
+            sts128(sP + off, hw[0], hw[1], hw[2], hw[3]);
+            sts128(sP + 16384 + off, lw[0], lw[1], lw[2], lw[3]);
+        }
+    }
+    return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+}
+
+template <int NG>
+__global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid_constant__ AttnKernelParams p) {
+    constexpr int kA3Groups = NG, kA3Ring = A3<NG>::kRing;
+    constexpr int kA3OffK = A3<NG>::kOffK, kA3OffV = A3<NG>::kOffV, kA3OffP = A3<NG>::kOffP, kA3OffCtl = A3<NG>::kOffCtl;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    Attn3Ctl<NG>* ctl = reinterpret_cast<Attn3Ctl<NG>*>(smem + kA3OffCtl);
+    if (threadIdx.x == 0 && (smem - smem_raw) + kA3OffCtl + (int)sizeof(Attn3Ctl<NG>) > kA3SmemBytes) __trap();
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nkv = (p.Lk + 63) >> 6;
+    const int n_tiles = p.B * p.nh * p.q_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmQ);
+        tma_prefetch_desc(&p.tmK);
+        tma_prefetch_desc(&p.tmV);
+        mbar_init(&ctl->q_full, 1);
+        mbar_init(&ctl->q_empty, 1);
+        for (int s = 0; s < kA3Ring; ++s) {
+            mbar_init(&ctl->k_full[s], 1);
+            mbar_init(&ctl->k_empty[s], 1);
+            mbar_init(&ctl->v_full[s], 1);
+            mbar_init(&ctl->v_empty[s], 1);
+        }
+        for (int g = 0; g < kA3Groups; ++g) {
+            mbar_init(&ctl->s_full[g], 1);
+            mbar_init(&ctl->s_empty[g], 4);
+            mbar_init(&ctl->p_full[g], 4);
+            mbar_init(&ctl->o_full[g], 1);
+            mbar_init(&ctl->o_empty[g], 4);
+            mbar_init(&ctl->x_full[g], 4);
+            mbar_init(&ctl->x_empty[g], 4);
+        }
+        fence_barrier_init();
+    } else if (warp == 1) {
+        tmem_alloc(&ctl->tmem_base, 512);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = ctl->tmem_base;
+    // TMEM columns: S[g] at 64 g, output accumulator O[g] at 256 + 64 g
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        // K and V^T blocks are two independent streams (K is consumed by the score products, which run up to NG blocks ahead of the
+        // P.V products that consume V): the thread polls both rings without blocking on either, so a V stage that is still being read
+        // never holds back the K block the MMA warp is waiting for.
+        if (lane == 0) {
+            uint32_t kc = 0, vc = 0, it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const int qt = tile % p.q_tiles;
+                const int z = tile / p.q_tiles;
+                const int h = z % p.nh, b = z / p.nh;
+                mbar_wait(&ctl->q_empty, (it & 1) ^ 1);
+                mbar_arrive_expect_tx(&ctl->q_full, kA2QBytes);
+                tma_load_3d(&p.tmQ, &ctl->q_full, smem, p.q_c0 + h * 64, qt * 128, b);
+                tma_load_3d(&p.tmQ, &ctl->q_full, smem + 16384, p.q_c0 + h * 64, qt * 128, p.B + b);
+                int kj = 0, vj = 0;
+                long long t0 = clock64();
+                while (kj < nkv || vj < nkv) {
+                    bool progress = false;
+                    if (kj < nkv) {
+                        const int ks = kc % kA3Ring;
+                        if (mbar_try_wait(&ctl->k_empty[ks], ((kc / kA3Ring) & 1) ^ 1)) {
+                            mbar_arrive_expect_tx(&ctl->k_full[ks], kA2KStage);
+                            uint8_t* sk = smem + kA3OffK + ks * kA2KStage;
+                            tma_load_3d(&p.tmK, &ctl->k_full[ks], sk, p.k_c0 + h * 64, kj * 64, b);
+                            tma_load_3d(&p.tmK, &ctl->k_full[ks], sk + 8192, p.k_c0 + h * 64, kj * 64, p.B + b);
+                            ++kc; ++kj;
+                            progress = true;
+                        }
+                    }
+                    if (vj < nkv) {
+                        const int vs = vc % kA3Ring;
+                        if (mbar_try_wait(&ctl->v_empty[vs], ((vc / kA3Ring) & 1) ^ 1)) {
+                            mbar_arrive_expect_tx(&ctl->v_full[vs], kA2VStage);
+                            uint8_t* sv = smem + kA3OffV + vs * kA2VStage;
+                            tma_load_3d(&p.tmV, &ctl->v_full[vs], sv, vj * 64, h * 64, b);
+                            tma_load_3d(&p.tmV, &ctl->v_full[vs], sv + 8192, vj * 64, h * 64, p.B + b);
+                            ++vc; ++vj;
+                            progress = true;
+                        }
+                    }
+                    if (progress) t0 = clock64();
+                    else if (clock64() - t0 > 4000000000LL) __trap();      // bounded like mbar_wait: a protocol bug must not hang the GPU
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_f16(64);
+            const uint32_t sq = smem_u32(smem);
+            uint32_t kc = 0, vc = 0, it = 0;
+            uint32_t s_par = 0, p_par = 0;       // bit g: parity of group g's next S product / P.V product
+            auto issue_qk = [&](int j) {
+                const int g = j % kA3Groups;
+                const int ks = kc % kA3Ring;
+                const uint32_t par = (s_par >> g) & 1;
+                mbar_wait(&ctl->k_full[ks], (kc / kA3Ring) & 1);
+                mbar_wait(&ctl->s_empty[g], par ^ 1);
+                tc_fence_after();
+                const uint32_t sk = smem_u32(smem + kA3OffK + ks * kA2KStage);
+                const uint32_t d_tmem = tmem_base + g * 64;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint64_t da = umma_desc_sw128(sq + (pass == 1 ? 16384 : 0));
+                    const uint64_t db = umma_desc_sw128(sk + (pass == 2 ? 8192 : 0));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&ctl->k_empty[ks]);
+                umma_commit(&ctl->s_full[g]);
+                ++kc;
+                s_par ^= 1u << g;
+            };
+            auto issue_pv = [&](int j) {
+                const int g = j % kA3Groups;
+                const int vs = vc % kA3Ring;
+                const uint32_t par = (p_par >> g) & 1;
+                mbar_wait(&ctl->v_full[vs], (vc / kA3Ring) & 1);
+                mbar_wait(&ctl->p_full[g], par);
+                const bool first = j < kA3Groups;           // this group's first block of the tile: fresh accumulator
+                if (first) mbar_wait(&ctl->o_empty[g], (it & 1) ^ 1);      // the group has read the previous tile's result out of it
+                tc_fence_after();
+                const uint32_t sv = smem_u32(smem + kA3OffV + vs * kA2VStage);
+                const uint32_t sp = smem_u32(smem + kA3OffP + g * kA2PBuf);
+                const uint32_t d_tmem = tmem_base + 256 + g * 64;
+#pragma unroll
+                for (int pass = 0; pass < 3; ++pass) {
+                    const uint64_t da = umma_desc_sw128(sp + (pass == 1 ? 16384 : 0));
+                    const uint64_t db = umma_desc_sw128(sv + (pass == 2 ? 8192 : 0));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0 || !first) ? 1u : 0u);
+                }
+                umma_commit(&ctl->v_empty[vs]);
+                umma_commit(&ctl->o_full[g]);
+                ++vc;
+                p_par ^= 1u << g;
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                mbar_wait(&ctl->q_full, it & 1);
+                const int ahead = nkv < kA3Groups ? nkv : kA3Groups;
+                for (int j = 0; j < ahead; ++j) issue_qk(j);
+                if (nkv <= kA3Groups) umma_commit(&ctl->q_empty);
+                for (int j = 0; j < nkv; ++j) {
+                    issue_pv(j);
+                    if (j + kA3Groups < nkv) {
+                        issue_qk(j + kA3Groups);
+                        if (j + kA3Groups + 1 == nkv) umma_commit(&ctl->q_empty);
+                    }
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax groups
+        const int g = (warp - 2) >> 2;                  // group g: warps 2 + 4 g .. 5 + 4 g
+        const int quad = warp & 3;                      // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;               // query row inside the tile
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_s = t_row + g * 64;
+        const uint32_t t_o = t_row + 256 + g * 64;
+        const uint32_t sP = smem_u32(smem + kA3OffP + g * kA2PBuf);
+        float* xO = reinterpret_cast<float*>(smem + kA3OffP + g * kA2PBuf);     // this group's P buffer doubles as its hand-over area [64][128]
+        const int ng = nkv < kA3Groups ? nkv : kA3Groups;                       // groups that have blocks
+        uint32_t bc = 0, it = 0;                        // key blocks processed by this group / tiles processed
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int qt = tile % p.q_tiles;
+            const int z = tile / p.q_tiles;
+            const int h = z % p.nh, b = z / p.nh;
+            float m_ref = -INFINITY, l = 0.f;
+            bool have = false;
+            for (int j = g; j < nkv; j += kA3Groups) {
+                if (g > 0 && !have) mbar_wait(&ctl->x_empty[g], (it & 1) ^ 1);   // group 0 has read the previous tile's hand-over out of P[g]
+                mbar_wait(&ctl->s_full[g], bc & 1);
+                tc_fence_after();
+                const int kvalid = p.Lk - j * 64;        // keys of this block that exist (>= 64: all)
+                const float t = (kvalid >= 64 ? attn3_row_max<false>(t_s, 64) : attn3_row_max<true>(t_s, kvalid)) * p.scale_log2e;
+                if (!have) {
+                    m_ref = t;                           // first block of the row in this group: exact maximum, nothing to rescale
+                } else {
+                    // the previous P.V of this group has completed: the P buffer may be overwritten and the accumulator is stable
+                    mbar_wait(&ctl->o_full[g], (bc - 1) & 1);
+                    tc_fence_after();
+                    const bool need = t > m_ref + kA3RescaleThreshold;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float m_new = need ? t : m_ref;
+                        const float alpha = ex2_approx(m_ref - m_new);           // 1 for the rows that keep their reference
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            uint32_t v[32];
+                            DSB_TMEM_LD_32(t_o + c * 32, v);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                            DSB_TMEM_ST_32(t_o + c * 32, v);
+                        }
+                        tmem_st_wait();
+                        l *= alpha;
+                        m_ref = m_new;
+                    }
+                }
+                l += (kvalid >= 64) ? attn3_exp_store<false>(t_s, sP, row, 64, p.scale_log2e, m_ref)
+                                    : attn3_exp_store<true>(t_s, sP, row, kvalid, p.scale_log2e, m_ref);
+                have = true;
+                ++bc;
+                tc_fence_before();
+                fence_proxy_async();                    // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&ctl->s_empty[g]);
+                    mbar_arrive(&ctl->p_full[g]);
+                }
+            }
+            if (!have) continue;                         // fewer key blocks than groups: nothing for this group in any tile
+            // ---- this group's result of the tile: O = accumulator / l relative to m_ref
+            float O[64];
+            mbar_wait(&ctl->o_full[g], (bc - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                DSB_TMEM_LD_32(t_o + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) O[c * 32 + i] = __uint_as_float(v[i]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl->o_empty[g]);
+            const float inv = 1.f / l;
+            float lam = m_ref + lg2_approx(l);           // this partial result carries weight 2^lam
+#pragma unroll
+            for (int i = 0; i < 64; ++i) O[i] *= inv;
+            if (g > 0) {
+                ctl->xl[g - 1][row] = lam;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) xO[i * 128 + row] = O[i];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->x_full[g]);     // release: the stores above are visible to whoever acquires the phase
+                continue;
+            }
+            // group 0 merges the partial results of groups 1 .. ng - 1 (normalised rows, weights 2^lambda) and writes the output
+            float wsum = 1.f;
+#pragma unroll 1
+            for (int og = 1; og < ng; ++og) {
+                mbar_wait(&ctl->x_full[og], it & 1);
+                const float lo = ctl->xl[og - 1][row];
+                const float ln = fmaxf(lam, lo);
+                const float fa = ex2_approx(lam - ln), fb = ex2_approx(lo - ln);
+                const float* src = reinterpret_cast<const float*>(smem + kA3OffP + og * kA2PBuf) + row;
+#pragma unroll
+                for (int i = 0; i < 64; ++i) O[i] = O[i] * fa + src[i * 128] * fb;
+                wsum = wsum * fa + fb;
+                lam = ln;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ctl->x_empty[og]);
+            }
+            const int grow = qt * 128 + row;
+            if (grow < p.L) {
+                const float winv = 1.f / wsum;
+                __half* o = p.out + ((long long)b * p.L + grow) * p.o_pitch + h * 64;
+#pragma unroll
+                for (int q8 = 0; q8 < 8; ++q8) {
+                    uint32_t hw[4], lw[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float a0 = O[q8 * 8 + 2 * i] * winv, a1 = O[q8 * 8 + 2 * i + 1] * winv;
+                        const __half2 h2 = __floats2half2_rn(a0, a1);
+                        const float2 hf = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+                        hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                        lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                    *reinterpret_cast<uint4*>(o + q8 * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *reinterpret_cast<uint4*>(o + p.o_plane + q8 * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------ host
+// kernel generation: 3 (default: four softmax groups, output in TMEM), 2 (two groups, output in registers), 1 (round 1).
+// DSB_ATTN=1|2|3 selects it for the process; DSB_ATTN_V1=1 is the round-2a spelling of DSB_ATTN=1.
+static int attn_version() {
+    static const int v = [] {
+        const char* e1 = getenv("DSB_ATTN_V1");
+        if (e1 && atoi(e1)) return 1;
+        const char* e = getenv("DSB_ATTN");
+        const int x = e ? atoi(e) : 3;
+        return (x >= 1 && x <= 3) ? x : 3;
+    }();
+    return v;
+}
+static bool attn_use_v1() { return attn_version() == 1; }
 
 int attn_build(const ds_attn_desc* d, AttnKernelParams* kp) {
     if (d->nplanes != 2 || d->B <= 0 || d->nh <= 0 || d->L <= 0 || d->Lk <= 0 || !(d->scale > 0.f)) return -30;
@@ -729,6 +1121,30 @@ int attn_build(const ds_attn_desc* d, AttnKernelParams* kp) {
 
 size_t attn_params_size() { return sizeof(AttnKernelParams); }
 
+template <int NG>
+static int attn3_launch(const AttnKernelParams* kp, cudaStream_t stream) {
+    static bool attr_set[64] = {};
+    static int sms[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return -39;
+    if (!attr_set[dev]) {
+        if (cudaFuncSetAttribute(attn3_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes) != cudaSuccess) return -36;
+        cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        attr_set[dev] = true;
+    }
+    const long long tiles = (long long)kp->B * kp->nh * kp->q_tiles;
+    if (tiles <= 0 || tiles > 0x7fffffffLL) return -37;
+    const int grid = (int)(tiles < sms[dev] ? tiles : sms[dev]);
+    attn3_kernel<NG><<<grid, A3<NG>::kThreads, kA3SmemBytes, stream>>>(*kp);
+    return cudaGetLastError() == cudaSuccess ? 0 : -38;
+}
+
+static int attn3_run(const AttnKernelParams* kp, cudaStream_t stream) {
+    static const int groups = [] { const char* e = getenv("DSB_ATTN_GROUPS"); const int x = e ? atoi(e) : 4; return x == 3 ? 3 : 4; }();
+    return groups == 3 ? attn3_launch<3>(kp, stream) : attn3_launch<4>(kp, stream);
+}
+
 static int attn2_run(const AttnKernelParams* kp, cudaStream_t stream) {
     static bool attr_set[64] = {};
     static int sms[64] = {};
@@ -749,7 +1165,8 @@ static int attn2_run(const AttnKernelParams* kp, cudaStream_t stream) {
 }
 
 int attn_run(const AttnKernelParams* kp, cudaStream_t stream) {
-    if (!attn_use_v1()) return attn2_run(kp, stream);
+    if (attn_version() == 3) return attn3_run(kp, stream);
+    if (attn_version() == 2) return attn2_run(kp, stream);
     static bool attr_set = false;
     const size_t smem = kOffCtl + sizeof(AttnCtl) + 1024;
     if (!attr_set) {

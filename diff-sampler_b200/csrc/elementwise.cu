@@ -67,22 +67,36 @@ __global__ void gn_stats_kernel(ds_gn_stats_desc d, int pix_per_cta) {
 // ------------------------------------------------------------------------------------------ GN statistics from quad partials
 // One CTA per sample.  Step 1: thread t owns the (quad, sum|sumsq) column t of the concatenated partial row (C/2 columns) and adds
 // it over the sample's slabs in fp64 (coalesced along t).  Step 2: thread j < 2*groups adds the cpg/4 quads of its group.
-__global__ void __launch_bounds__(256) gn_finalize_kernel(ds_gn_finalize_desc d) {
-    extern __shared__ double s_cols[];
+__global__ void __launch_bounds__(1024) gn_finalize_kernel(ds_gn_finalize_desc d) {
+    extern __shared__ double s_cols[];                    // [cols] column sums, then [SG][cols] partials
     __shared__ float s_mu[64], s_rstd[64];
     const int n = blockIdx.x;
     const int C = d.C0 + d.C1;
     if (d.quads0) {
-        // partial rows: {sum, sumsq} per unit of u0 / u1 channels (4 = quads, 2 = pairs) -> w floats per 32-row slab
+        // partial rows: {sum, sumsq} per unit of u0 / u1 channels (4 = quads, 2 = pairs) -> w floats per 32-row slab.
+        // Thread (column, slab group): the 1024 threads split the sample's slabs SG ways (round 2: one thread per column walked all
+        // HW / 32 slabs alone, 35 us per launch at 64 x 64); the SG partials of a column are added in a fixed order (deterministic).
         const int u0 = d.unit0 == 2 ? 2 : 4, u1 = d.unit1 == 2 ? 2 : 4;
         const int w0 = d.C0 / u0 * 2, w1 = d.C1 / u1 * 2;
-        for (int t = threadIdx.x; t < w0 + w1; t += blockDim.x) {
+        const int cols = w0 + w1;
+        int SG = blockDim.x / cols;
+        if (SG < 1) SG = 1;
+        if (SG > d.slabs_per_sample) SG = d.slabs_per_sample;
+        double* part = s_cols + cols;
+        for (int idx = threadIdx.x; idx < cols * SG; idx += blockDim.x) {
+            const int t = idx % cols, sg = idx / cols;
             const float* src = (t < w0) ? d.quads0 + (long long)n * d.slabs_per_sample * w0 + t
                                         : d.quads1 + (long long)n * d.slabs_per_sample * w1 + (t - w0);
             const int pitch = (t < w0) ? w0 : w1;
             double acc = 0.0;
-#pragma unroll 8
-            for (int sl = 0; sl < d.slabs_per_sample; ++sl) acc += (double)__ldg(src + (long long)sl * pitch);
+#pragma unroll 4
+            for (int sl = sg; sl < d.slabs_per_sample; sl += SG) acc += (double)__ldg(src + (long long)sl * pitch);
+            part[(long long)sg * cols + t] = acc;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < cols; t += blockDim.x) {
+            double acc = 0.0;
+            for (int sg = 0; sg < SG; ++sg) acc += part[(long long)sg * cols + t];
             s_cols[t] = acc;
         }
         __syncthreads();
@@ -889,7 +903,17 @@ extern "C" int ds_gn_finalize_launch(const ds_gn_finalize_desc* d, cudaStream_t 
     }
     if (!d->quads0 && !d->coef) return -2;               // nothing to do
     if (d->coef && (!d->gamma || !d->beta || d->HW <= 0)) return -2;
-    gn_finalize_kernel<<<d->B, 256, (size_t)(C + 2) * sizeof(double), stream>>>(*d);
+    // threads: enough for (columns x slab groups), at most 1024; shared memory: [cols] + [SG][cols] doubles, cols <= C, SG * cols <= max(cols, threads)
+    int threads = 256;
+    size_t smem = (size_t)(C + 2) * sizeof(double);
+    if (d->quads0) {
+        const int u0 = d->unit0 == 2 ? 2 : 4, u1 = d->unit1 == 2 ? 2 : 4;
+        const int cols = d->C0 / u0 * 2 + d->C1 / u1 * 2;
+        threads = 1024;
+        const int sg = cols >= threads ? 1 : threads / cols;
+        smem = (size_t)(cols + (size_t)sg * cols + 2) * sizeof(double);
+    }
+    gn_finalize_kernel<<<d->B, threads, smem, stream>>>(*d);
     return ok();
 }
 

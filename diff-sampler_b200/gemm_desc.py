@@ -10,31 +10,33 @@ H16 = 2  # bytes per fp16
 NUM_SMS = 148
 
 
+def _tile_cost(bn):
+    """Duration of one 64-wide K step of a 128 x bn tile, in SM cycles.  Measured (profiles/r02/gemm_tiles_microbench_r02d.txt: 3x3
+    convolutions at 192..1280 channels, every N tile from 64 to 256, fp16x3 and f8): ~690 + bn cycles -- a fixed cost per K step (the
+    16 KB activation tile: 128 rows of 128 B through TMA and the shared-memory port) plus one cycle per weight row; the tensor pipe
+    itself needs 2 x bn, so narrow tiles are far from proportionally cheaper (round 1 modelled max(bn / 2, 32 + bn / 4))."""
+    return 690.0 + bn
+
+
 def pick_bn(n):
-    """N tile (UMMA N: any multiple of 16 up to 256): narrow outputs get the smallest covering tile; otherwise the widest tile among
-    the tilings with the least padding (wide tiles lower the per-MMA shared-memory traffic): 320 -> 160x2, 384 -> 192x2, 1344 -> 224x6."""
+    """N tile (UMMA N: any multiple of 16 up to 256): narrow outputs get the smallest covering tile; otherwise the tiling with the least
+    total cost tiles x _tile_cost(bn), ties to less padding: 192 -> 192, 320 -> 160x2, 384 -> 192x2, 576 -> 192x3, 640 -> 224x3 (5 % of
+    zero rows beat a fourth 160-wide tile: measured 411 us with 256x3 against 482 us with 160x4 at 32x32x16 samples), 1280 -> 256x5."""
     for bn in (16, 32, 64):
         if n <= bn:
             return bn, 1
     best = None
     for bn in range(256, 63, -16):
         tiles = -(-n // bn)
-        key = (tiles * bn - n, -bn)
+        key = (tiles * _tile_cost(bn), tiles * bn - n, -bn)
         if best is None or key < best[0]:
             best = (key, bn, tiles)
     return best[1], best[2]
 
 
-def _tile_cost(bn):
-    """Relative duration of one K step of a 128 x bn tile: tensor-core time bn/2 cycles, but never less than the shared-memory
-    read of the operands (128 x 16 A + bn x 16 B fp16 at 128 B/clk) -- narrow tiles do not get proportionally cheaper."""
-    return max(bn / 2.0, 32.0 + bn / 4.0)
-
-
 def fill_bn(n, m_tiles, num_z=1):
     """N tile for a problem with few tiles (small batch / low resolution): the persistent grid runs ceil(tiles / 148) waves, so
-    160 tiles cost two full waves.  Choose the multiple of 16 that minimises waves x per-tile cost (e.g. N = 1280 over 32 M tiles:
-    144 x 9 = 288 tiles = 2 waves of 72 instead of 256 x 5 = 160 tiles = 2 waves of 128).  Large problems keep pick_bn's tiling.
+    160 tiles cost two full waves.  Choose the multiple of 16 that minimises waves x per-tile cost.  Large problems keep pick_bn's tiling.
     The packed weight keeps pick_bn's padded row count; rows past it are zero-filled by TMA."""
     bn, tiles = pick_bn(n)
     if m_tiles * tiles * num_z >= 4 * NUM_SMS or bn <= 64:
