@@ -43,6 +43,30 @@ struct alignas(64) AttnKernelParams {
     __half* out;
     long long o_plane;
     int o_pitch;
+    // debug timeline (ds_debug_attn_trace): CTA 0 records (tag << 40 | clock) for its first tiles; NULL in normal runs
+    unsigned long long* trace;
+    int trace_cap;
+    int interleave;             // attn3: issue the MMAs of P.V(j) and of the next score product alternately (two independent accumulation chains)
+};
+
+// trace tags: who (0 TMA, 1 MMA, 2 + g softmax group g) << 16 | event << 8 | block index (low 8 bits).  Every role writes its own region
+// of the buffer through a private counter: one plain store + one clock read per event (an atomic slot allocation costs a round trip to
+// L2, ~900 cycles, which would drown the waits being measured).
+struct AttnTracer {
+    unsigned long long* base;
+    unsigned n, cap;
+    __device__ __forceinline__ AttnTracer(const AttnKernelParams& p, int who) {
+        const int per = p.trace ? p.trace_cap / 8 : 0;
+        base = (p.trace && blockIdx.x == 0 && (threadIdx.x & 31) == 0) ? p.trace + (long long)who * per : nullptr;
+        n = 1;
+        cap = per;
+    }
+    __device__ __forceinline__ void operator()(unsigned it, int who, int ev, int j) {
+        if (base && it < 2 && n < cap) {
+            base[n] = ((unsigned long long)((who << 16) | (ev << 8) | (j & 255) | (it << 20)) << 40) | (clock64() & 0xFFFFFFFFFFULL);
+            base[0] = ++n;                       // events written + 1
+        }
+    }
 };
 
 struct AttnCtl {
@@ -835,6 +859,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
         // P.V products that consume V): the thread polls both rings without blocking on either, so a V stage that is still being read
         // never holds back the K block the MMA warp is waiting for.
         if (lane == 0) {
+            AttnTracer tr(p, 0);
             uint32_t kc = 0, vc = 0, it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const int qt = tile % p.q_tiles;
@@ -851,6 +876,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                     if (kj < nkv) {
                         const int ks = kc % kA3Ring;
                         if (mbar_try_wait(&ctl->k_empty[ks], ((kc / kA3Ring) & 1) ^ 1)) {
+                            tr(it, 0, 0, kj);
                             mbar_arrive_expect_tx(&ctl->k_full[ks], kA2KStage);
                             uint8_t* sk = smem + kA3OffK + ks * kA2KStage;
                             tma_load_3d(&p.tmK, &ctl->k_full[ks], sk, p.k_c0 + h * 64, kj * 64, b);
@@ -862,6 +888,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                     if (vj < nkv) {
                         const int vs = vc % kA3Ring;
                         if (mbar_try_wait(&ctl->v_empty[vs], ((vc / kA3Ring) & 1) ^ 1)) {
+                            tr(it, 0, 1, vj);
                             mbar_arrive_expect_tx(&ctl->v_full[vs], kA2VStage);
                             uint8_t* sv = smem + kA3OffV + vs * kA2VStage;
                             tma_load_3d(&p.tmV, &ctl->v_full[vs], sv, vj * 64, h * 64, b);
@@ -876,30 +903,38 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (whole warp converged; tcgen05 instructions elected)
+        {
             const uint32_t idesc = umma_idesc_f16(64);
             const uint32_t sq = smem_u32(smem);
+            AttnTracer tr(p, 1);
             uint32_t kc = 0, vc = 0, it = 0;
             uint32_t s_par = 0, p_par = 0;       // bit g: parity of group g's next S product / P.V product
             auto issue_qk = [&](int j) {
                 const int g = j % kA3Groups;
                 const int ks = kc % kA3Ring;
                 const uint32_t par = (s_par >> g) & 1;
+                tr(it, 1, 0, j);
                 mbar_wait(&ctl->k_full[ks], (kc / kA3Ring) & 1);
+                tr(it, 1, 1, j);
                 mbar_wait(&ctl->s_empty[g], par ^ 1);
+                tr(it, 1, 2, j);
                 tc_fence_after();
                 const uint32_t sk = smem_u32(smem + kA3OffK + ks * kA2KStage);
                 const uint32_t d_tmem = tmem_base + g * 64;
+                __syncwarp();
+                if (elect_one()) {
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint64_t da = umma_desc_sw128(sq + (pass == 1 ? 16384 : 0));
-                    const uint64_t db = umma_desc_sw128(sk + (pass == 2 ? 8192 : 0));
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint64_t da = umma_desc_sw128(sq + (pass == 1 ? 16384 : 0));
+                        const uint64_t db = umma_desc_sw128(sk + (pass == 2 ? 8192 : 0));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&ctl->k_empty[ks]);
+                    umma_commit(&ctl->s_full[g]);
                 }
-                umma_commit(&ctl->k_empty[ks]);
-                umma_commit(&ctl->s_full[g]);
+                __syncwarp();
                 ++kc;
                 s_par ^= 1u << g;
             };
@@ -907,36 +942,96 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 const int g = j % kA3Groups;
                 const int vs = vc % kA3Ring;
                 const uint32_t par = (p_par >> g) & 1;
+                tr(it, 1, 4, j);
                 mbar_wait(&ctl->v_full[vs], (vc / kA3Ring) & 1);
+                tr(it, 1, 5, j);
                 mbar_wait(&ctl->p_full[g], par);
+                tr(it, 1, 6, j);
                 const bool first = j < kA3Groups;           // this group's first block of the tile: fresh accumulator
                 if (first) mbar_wait(&ctl->o_empty[g], (it & 1) ^ 1);      // the group has read the previous tile's result out of it
                 tc_fence_after();
                 const uint32_t sv = smem_u32(smem + kA3OffV + vs * kA2VStage);
                 const uint32_t sp = smem_u32(smem + kA3OffP + g * kA2PBuf);
                 const uint32_t d_tmem = tmem_base + 256 + g * 64;
+                __syncwarp();
+                if (elect_one()) {
 #pragma unroll
-                for (int pass = 0; pass < 3; ++pass) {
-                    const uint64_t da = umma_desc_sw128(sp + (pass == 1 ? 16384 : 0));
-                    const uint64_t db = umma_desc_sw128(sv + (pass == 2 ? 8192 : 0));
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint64_t da = umma_desc_sw128(sp + (pass == 1 ? 16384 : 0));
+                        const uint64_t db = umma_desc_sw128(sv + (pass == 2 ? 8192 : 0));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0 || !first) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0 || !first) ? 1u : 0u);
+                    }
+                    umma_commit(&ctl->v_empty[vs]);
+                    umma_commit(&ctl->o_full[g]);
                 }
-                umma_commit(&ctl->v_empty[vs]);
-                umma_commit(&ctl->o_full[g]);
+                __syncwarp();
+                tr(it, 1, 7, j);
                 ++vc;
                 p_par ^= 1u << g;
+            };
+            // P.V(j) and the score product of block j + NG in ONE issue sequence, their MMAs alternating: consecutive tcgen05.mma into the
+            // same accumulator form a dependent chain (timeline in profiles/r02: ~95 cycles per 128x64x16 MMA issued back to back into one
+            // accumulator, three times its tensor time), two chains into different accumulators overlap.
+            auto issue_pv_qk = [&](int j, int jq) {
+                const int g = j % kA3Groups, gq = jq % kA3Groups;          // the same group (jq = j + NG), kept general
+                const int vs = vc % kA3Ring, ks = kc % kA3Ring;
+                const uint32_t ppar = (p_par >> g) & 1, spar = (s_par >> gq) & 1;
+                tr(it, 1, 4, j);
+                mbar_wait(&ctl->v_full[vs], (vc / kA3Ring) & 1);
+                mbar_wait(&ctl->p_full[g], ppar);
+                const bool first = j < kA3Groups;
+                if (first) mbar_wait(&ctl->o_empty[g], (it & 1) ^ 1);
+                tr(it, 1, 6, j);
+                mbar_wait(&ctl->k_full[ks], (kc / kA3Ring) & 1);
+                mbar_wait(&ctl->s_empty[gq], spar ^ 1);
+                tr(it, 1, 2, jq);
+                tc_fence_after();
+                const uint32_t sv = smem_u32(smem + kA3OffV + vs * kA2VStage);
+                const uint32_t sp = smem_u32(smem + kA3OffP + g * kA2PBuf);
+                const uint32_t sk = smem_u32(smem + kA3OffK + ks * kA2KStage);
+                const uint32_t d_o = tmem_base + 256 + g * 64, d_s = tmem_base + gq * 64;
+                __syncwarp();
+                if (elect_one()) {
+#pragma unroll
+                    for (int pass = 0; pass < 3; ++pass) {
+                        const uint64_t pa = umma_desc_sw128(sp + (pass == 1 ? 16384 : 0));
+                        const uint64_t pb = umma_desc_sw128(sv + (pass == 2 ? 8192 : 0));
+                        const uint64_t qa = umma_desc_sw128(sq + (pass == 1 ? 16384 : 0));
+                        const uint64_t qb = umma_desc_sw128(sk + (pass == 2 ? 8192 : 0));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16(d_o, pa + 2 * k, pb + 2 * k, idesc, (pass > 0 || k > 0 || !first) ? 1u : 0u);
+                            umma_f16(d_s, qa + 2 * k, qb + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&ctl->v_empty[vs]);
+                    umma_commit(&ctl->k_empty[ks]);
+                    umma_commit(&ctl->o_full[g]);
+                    umma_commit(&ctl->s_full[gq]);
+                }
+                __syncwarp();
+                tr(it, 1, 7, j);
+                ++vc; ++kc;
+                p_par ^= 1u << g;
+                s_par ^= 1u << gq;
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 mbar_wait(&ctl->q_full, it & 1);
                 const int ahead = nkv < kA3Groups ? nkv : kA3Groups;
                 for (int j = 0; j < ahead; ++j) issue_qk(j);
-                if (nkv <= kA3Groups) umma_commit(&ctl->q_empty);
+                if (nkv <= kA3Groups) { __syncwarp(); if (elect_one()) umma_commit(&ctl->q_empty); __syncwarp(); }
                 for (int j = 0; j < nkv; ++j) {
-                    issue_pv(j);
                     if (j + kA3Groups < nkv) {
-                        issue_qk(j + kA3Groups);
-                        if (j + kA3Groups + 1 == nkv) umma_commit(&ctl->q_empty);
+                        if (p.interleave) {
+                            issue_pv_qk(j, j + kA3Groups);
+                        } else {
+                            issue_pv(j);
+                            issue_qk(j + kA3Groups);
+                        }
+                        if (j + kA3Groups + 1 == nkv) { __syncwarp(); if (elect_one()) umma_commit(&ctl->q_empty); __syncwarp(); }
+                    } else {
+                        issue_pv(j);
                     }
                 }
             }
@@ -952,6 +1047,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
         const uint32_t sP = smem_u32(smem + kA3OffP + g * kA2PBuf);
         float* xO = reinterpret_cast<float*>(smem + kA3OffP + g * kA2PBuf);     // this group's P buffer doubles as its hand-over area [64][128]
         const int ng = nkv < kA3Groups ? nkv : kA3Groups;                       // groups that have blocks
+        AttnTracer tr(p, 2 + g);
         uint32_t bc = 0, it = 0;                        // key blocks processed by this group / tiles processed
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int qt = tile % p.q_tiles;
@@ -961,10 +1057,13 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
             bool have = false;
             for (int j = g; j < nkv; j += kA3Groups) {
                 if (g > 0 && !have) mbar_wait(&ctl->x_empty[g], (it & 1) ^ 1);   // group 0 has read the previous tile's hand-over out of P[g]
+                if (quad == 0 && lane == 0) tr(it, 2 + g, 0, j);
                 mbar_wait(&ctl->s_full[g], bc & 1);
+                if (quad == 0 && lane == 0) tr(it, 2 + g, 1, j);
                 tc_fence_after();
                 const int kvalid = p.Lk - j * 64;        // keys of this block that exist (>= 64: all)
                 const float t = (kvalid >= 64 ? attn3_row_max<false>(t_s, 64) : attn3_row_max<true>(t_s, kvalid)) * p.scale_log2e;
+                if (quad == 0 && lane == 0) tr(it, 2 + g, 2, j);
                 if (!have) {
                     m_ref = t;                           // first block of the row in this group: exact maximum, nothing to rescale
                 } else {
@@ -989,13 +1088,16 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                         m_ref = m_new;
                     }
                 }
+                if (quad == 0 && lane == 0) tr(it, 2 + g, 3, j);
                 l += (kvalid >= 64) ? attn3_exp_store<false>(t_s, sP, row, 64, p.scale_log2e, m_ref)
                                     : attn3_exp_store<true>(t_s, sP, row, kvalid, p.scale_log2e, m_ref);
                 have = true;
                 ++bc;
+                if (quad == 0 && lane == 0) tr(it, 2 + g, 4, j);
                 tc_fence_before();
                 fence_proxy_async();                    // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
+                if (quad == 0 && lane == 0) tr(it, 2 + g, 5, j);
                 if (lane == 0) {
                     mbar_arrive(&ctl->s_empty[g]);
                     mbar_arrive(&ctl->p_full[g]);
@@ -1088,6 +1190,10 @@ static int attn_version() {
 }
 static bool attn_use_v1() { return attn_version() == 1; }
 
+static unsigned long long* g_attn_trace = nullptr;
+static int g_attn_trace_cap = 0;
+void attn_set_trace(unsigned long long* dev_buf, int capacity) { g_attn_trace = dev_buf; g_attn_trace_cap = capacity; }
+
 int attn_build(const ds_attn_desc* d, AttnKernelParams* kp) {
     if (d->nplanes != 2 || d->B <= 0 || d->nh <= 0 || d->L <= 0 || d->Lk <= 0 || !(d->scale > 0.f)) return -30;
     if (d->q_pitch % 8 || d->k_pitch % 8 || d->vt_pitch % 8 || d->o_pitch % 8 || d->q_c0 % 8 || d->k_c0 % 8) return -31;
@@ -1116,6 +1222,10 @@ int attn_build(const ds_attn_desc* d, AttnKernelParams* kp) {
     kp->out = reinterpret_cast<__half*>(d->out);
     kp->o_plane = (long long)d->B * d->L * d->o_pitch;
     kp->o_pitch = d->o_pitch;
+    kp->trace = g_attn_trace;
+    kp->trace_cap = g_attn_trace_cap;
+    static const int inter = [] { const char* e = getenv("DSB_ATTN_INTERLEAVE"); return e ? atoi(e) : 1; }();
+    kp->interleave = inter;
     return 0;
 }
 

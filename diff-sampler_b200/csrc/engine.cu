@@ -23,6 +23,7 @@ struct AttnKernelParams;
 int attn_build(const ds_attn_desc* d, AttnKernelParams* kp);
 int attn_run(const AttnKernelParams* kp, cudaStream_t stream);
 size_t attn_params_size();
+void attn_set_trace(unsigned long long* dev_buf, int capacity);
 }  // namespace dsb
 
 static thread_local std::string g_err;
@@ -474,6 +475,11 @@ int ds_amed_predict(const float* weights, const int* dims6, const float* bottlen
     NvtxRange nvtx_range("ds_amed_predict");
     int rc = ds_amed_predict_launch(weights, dims6, bottleneck, t_cur, t_next, scale_dir, scale_time, out4, B, static_cast<cudaStream_t>(stream));
     if (rc) return fail(rc, std::string("ds_amed_predict: launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return 0;
+}
+
+int ds_debug_attn_trace(unsigned long long* dev_buf, int capacity) {
+    dsb::attn_set_trace(dev_buf, capacity);
     return 0;
 }
 

@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint32_t tmem_base = ctl->tmem_base;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer (whole warp converged; the copies elected)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -332,7 +332,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + kATileBytes;
-                    mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
+                    __syncwarp();
+                    const bool leader = elect_one();
+                    if (leader) mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
                     if (it < 2 * nkb8) {
                         // e4m3 block: 128 channels = one 128-byte swizzle row, same tile bytes as an fp16 block
                         const int pass8 = it >= nkb8 ? 1 : 0;
@@ -341,11 +343,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         if (kb < p.nkb8_main) {
                             const int tap = kb / p.cpb8;
                             const int c0 = (kb - tap * p.cpb8) * 128;
-                            tma_load_4d(&p.tmA8, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an8);
+                            if (leader) tma_load_4d(&p.tmA8, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an8);
                         } else {
-                            tma_load_4d(&p.tmA2_8, &ctl->full[stage], sa, (kb - p.nkb8_main) * 128, aw0, ah0, an8);
+                            if (leader) tma_load_4d(&p.tmA2_8, &ctl->full[stage], sa, (kb - p.nkb8_main) * 128, aw0, ah0, an8);
                         }
-                        tma_load_3d(&p.tmB8, &ctl->full[stage], sb, kb * 128, b_row, pass8);
+                        if (leader) tma_load_3d(&p.tmB8, &ctl->full[stage], sb, kb * 128, b_row, pass8);
+                        __syncwarp();
                         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -358,19 +361,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         const int tap = kb / p.cpb;
                         const int c0 = (kb - tap * p.cpb) * 64 + p.tap_cb[tap];
                         const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-                        tma_load_4d(&p.tmA, &ctl->full[stage], sa, c0 + a_c_off, aw0 + dw, ah0 + dh, an0 + pa * p.a_plane_n);
+                        if (leader) tma_load_4d(&p.tmA, &ctl->full[stage], sa, c0 + a_c_off, aw0 + dw, ah0 + dh, an0 + pa * p.a_plane_n);
                     } else {
                         const int c0 = (kb - p.nkb_main) * 64;
-                        tma_load_4d(&p.tmA2, &ctl->full[stage], sa, c0, aw0, ah0, an0 + pa * p.a2_plane_n);
+                        if (leader) tma_load_4d(&p.tmA2, &ctl->full[stage], sa, c0, aw0, ah0, an0 + pa * p.a2_plane_n);
                     }
-                    tma_load_3d(&p.tmB, &ctl->full[stage], sb, kb * 64 + b_k_off, b_row, b_z + pb * p.b_plane_batch);
+                    if (leader) tma_load_3d(&p.tmB, &ctl->full[stage], sb, kb * 64 + b_k_off, b_row, b_z + pb * p.b_plane_batch);
+                    __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (whole warp converged; tcgen05 instructions elected)
+        {
             const uint32_t idesc = umma_idesc_f16((uint32_t)p.BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -388,19 +392,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     const uint32_t sb = sa + kATileBytes;
                     const uint64_t da = umma_desc_sw128(sa);
                     const uint64_t db = umma_desc_sw128(sb);
-                    if (it < 2 * nkb8) {
+                    __syncwarp();
+                    if (elect_one()) {
+                        if (it < 2 * nkb8) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)      // 32 e4m3 = 32 bytes per MMA: the same +2 descriptor step as 16 fp16
-                            umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    } else {
+                            for (int k = 0; k < 4; ++k)      // 32 e4m3 = 32 bytes per MMA: the same +2 descriptor step as 16 fp16
+                                umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) {
+                                // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                                umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            }
                         }
+                        umma_commit(&ctl->empty[stage]);
+                        if (it == n_iters - 1) umma_commit(&ctl->tmem_full[acc]);
                     }
-                    umma_commit(&ctl->empty[stage]);
-                    if (it == n_iters - 1) umma_commit(&ctl->tmem_full[acc]);
+                    __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -518,8 +526,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
     const uint32_t tmem_base = ctl->tmem_base;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs)
-        if (lane == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs; warp converged, copies elected)
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = first; tile < total_tiles; tile += step) {
@@ -539,7 +547,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                     mbar_wait(&ctl->empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + kATileBytes;
-                    if (rank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)stage_bytes);
+                    __syncwarp();
+                    const bool leader = elect_one();
+                    if (leader && rank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)stage_bytes);
                     if (it < 2 * nkb8) {
                         const int pass8 = it >= nkb8 ? 1 : 0;
                         const int kb = it - pass8 * nkb8;
@@ -547,11 +557,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                         if (kb < p.nkb8_main) {
                             const int tap = kb / p.cpb8;
                             const int c0 = (kb - tap * p.cpb8) * 128;
-                            tma_load_4d_pair(&p.tmA8, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an8);
+                            if (leader) tma_load_4d_pair(&p.tmA8, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an8);
                         } else {
-                            tma_load_4d_pair(&p.tmA2_8, &ctl->full[stage], sa, (kb - p.nkb8_main) * 128, aw0, ah0, an8);
+                            if (leader) tma_load_4d_pair(&p.tmA2_8, &ctl->full[stage], sa, (kb - p.nkb8_main) * 128, aw0, ah0, an8);
                         }
-                        tma_load_3d_pair(&p.tmB8h, &ctl->full[stage], sb, kb * 128, b_row, pass8);
+                        if (leader) tma_load_3d_pair(&p.tmB8h, &ctl->full[stage], sb, kb * 128, b_row, pass8);
                     } else {
                         const int it16 = it - 2 * nkb8;
                         const int pass = it16 / nkb_total;
@@ -561,19 +571,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                         if (kb < p.nkb_main) {
                             const int tap = kb / p.cpb;
                             const int c0 = (kb - tap * p.cpb) * 64;
-                            tma_load_4d_pair(&p.tmA, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an0 + pa * p.a_plane_n);
+                            if (leader) tma_load_4d_pair(&p.tmA, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an0 + pa * p.a_plane_n);
                         } else {
-                            tma_load_4d_pair(&p.tmA2, &ctl->full[stage], sa, (kb - p.nkb_main) * 64, aw0, ah0, an0 + pa * p.a2_plane_n);
+                            if (leader) tma_load_4d_pair(&p.tmA2, &ctl->full[stage], sa, (kb - p.nkb_main) * 64, aw0, ah0, an0 + pa * p.a2_plane_n);
                         }
-                        tma_load_3d_pair(&p.tmBh, &ctl->full[stage], sb, kb * 64, b_row, pb * p.b_plane_batch);
+                        if (leader) tma_load_3d_pair(&p.tmBh, &ctl->full[stage], sb, kb * 64, b_row, pb * p.b_plane_batch);
                     }
+                    __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-        if (lane == 0 && rank == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only; warp converged, tcgen05 elected)
+        if (rank == 0) {
             const uint32_t idesc = umma_idesc_pair((uint32_t)p.BN);
             int stage = 0;
             uint32_t phase = 0;
@@ -591,15 +602,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                     const uint32_t sb = sa + kATileBytes;
                     const uint64_t da = umma_desc_sw128(sa);
                     const uint64_t db = umma_desc_sw128(sb);
-                    if (it < 2 * nkb8) {
+                    __syncwarp();
+                    if (elect_one()) {
+                        if (it < 2 * nkb8) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                    } else {
+                            for (int k = 0; k < 4; ++k) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        } else {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        }
+                        umma_commit_pair(&ctl->empty[stage]);             // frees this stage in both CTAs
+                        if (it == n_iters - 1) umma_commit_pair(&ctl->tmem_full[acc]);
                     }
-                    umma_commit_pair(&ctl->empty[stage]);                 // frees this stage in both CTAs
-                    if (it == n_iters - 1) umma_commit_pair(&ctl->tmem_full[acc]);
+                    __syncwarp();
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
                 }
             }

@@ -17,6 +17,20 @@ __device__ __forceinline__ uint32_t lane_id() {
     return l;
 }
 
+// One elected lane of a fully converged warp (elect.sync over all 32 lanes).  The tcgen05 issue loops run with the whole warp converged
+// and only the tcgen05.mma / tcgen05.commit instructions elected: when the loop itself sits inside `if (lane == 0)`, ptxas cannot assume
+// convergence and wraps EVERY warp-level tcgen05 instruction in an ELECT / BRA.U.ANY serialisation loop (~75 cycles of single-thread
+// latency per MMA, measured with the attention timeline in profiles/r02): the issue thread, not the tensor pipe, set the pace.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred px;\n\t"
+        "elect.sync _|px, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

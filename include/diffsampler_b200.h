@@ -114,6 +114,11 @@ int ds_amed_predict(const float* weights, const int* dims6, const float* bottlen
  * sample.py:311.  images [B, C, H*W] fp32 NCHW -> out [B, H*W, C] uint8 NHWC (what is written to PNG / gathered for FID). */
 int ds_images_to_uint8(const float* images, unsigned char* out, int B, int C, int HW, void* stream);
 
+/* Debug timeline of the fused attention kernel (profiles/attn_timeline.py): attention ops BUILT after this call make CTA 0 record
+ * (tag << 40 | clock) events of its TMA / MMA / softmax roles for its first two tiles into dev_buf[1..capacity) (dev_buf[0] = count,
+ * zeroed by the caller).  NULL switches it off.  Not part of the sampling path. */
+int ds_debug_attn_trace(unsigned long long* dev_buf, int capacity);
+
 /* ---- kernel-level entry points (used by the parity tests and micro-benchmarks) ------------------
  * `desc` points to the matching struct of csrc/ops.h with absolute device pointers. */
 int ds_op_launch(int op_type, const void* desc, size_t desc_size, void* stream);
