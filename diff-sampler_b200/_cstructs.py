@@ -8,7 +8,7 @@ I64 = C.c_int64
 F32 = C.c_float
 
 DS_OP_GEMM, DS_OP_GN_STATS, DS_OP_GN_APPLY, DS_OP_SOFTMAX, DS_OP_POSEMB, DS_OP_LINEAR = 1, 2, 3, 4, 5, 6
-DS_OP_PREP_INPUT, DS_OP_CHANMEAN, DS_OP_MEMSET, DS_OP_LAYERNORM, DS_OP_GEGLU, DS_OP_GN_FINALIZE, DS_OP_ATTN = 7, 8, 9, 10, 11, 12, 13
+DS_OP_PREP_INPUT, DS_OP_CHANMEAN, DS_OP_MEMSET, DS_OP_LAYERNORM, DS_OP_GEGLU, DS_OP_GN_FINALIZE, DS_OP_ATTN, DS_OP_EMBED = 7, 8, 9, 10, 11, 12, 13, 14
 DS_IO_X, DS_IO_D, DS_IO_SIGMA, DS_IO_LABELS, DS_IO_BOTTLENECK, DS_IO_CTX = 0, 1, 2, 3, 4, 5
 DS_M_X0, DS_M_EPS, DS_M_DIV, DS_M_NONE = 0, 1, 2, 3
 DS_F8_SH_A16, DS_F8_SH_LO8, DS_F8_SH_HI8 = 6, 13, 2      # csrc/ops.h: power-of-two operand scales of the f8 GEMM mode
@@ -78,7 +78,7 @@ class LayernormDesc(C.Structure):
 
 
 class GegluDesc(C.Structure):
-    _fields_ = [('src', P), ('out', P), ('rows', I64), ('I', I32), ('nplanes', I32), ('fmt', I32), ('pad0', I32)]
+    _fields_ = [('src', P), ('out', P), ('rows', I64), ('I', I32), ('nplanes', I32), ('fmt', I32), ('mode', I32)]
 
 
 class GnFinalizeDesc(C.Structure):
@@ -90,7 +90,11 @@ class GnFinalizeDesc(C.Structure):
 class AttnDesc(C.Structure):
     _fields_ = [('q', P), ('k', P), ('vt', P), ('out', P), ('B', I32), ('nh', I32), ('L', I32), ('Lk', I32),
                 ('q_pitch', I32), ('q_c0', I32), ('k_pitch', I32), ('k_c0', I32), ('vt_pitch', I32), ('o_pitch', I32),
-                ('nplanes', I32), ('scale', F32)]
+                ('nplanes', I32), ('scale', F32), ('causal', I32), ('pad0', I32)]
+
+
+class EmbedDesc(C.Structure):
+    _fields_ = [('ids', P), ('tok', P), ('pos', P), ('out', P), ('rows', I64), ('T', I32), ('C', I32), ('vocab', I32), ('pad0', I32)]
 
 
 class MemsetDesc(C.Structure):
@@ -100,7 +104,8 @@ class MemsetDesc(C.Structure):
 class _OpUnion(C.Union):
     _fields_ = [('gemm', GemmDesc), ('gn_stats', GnStatsDesc), ('gn_apply', GnApplyDesc), ('softmax', SoftmaxDesc),
                 ('posemb', PosembDesc), ('linear', LinearDesc), ('prep_input', PrepInputDesc), ('chanmean', ChanmeanDesc),
-                ('memset', MemsetDesc), ('layernorm', LayernormDesc), ('geglu', GegluDesc), ('gn_finalize', GnFinalizeDesc), ('attn', AttnDesc)]
+                ('memset', MemsetDesc), ('layernorm', LayernormDesc), ('geglu', GegluDesc), ('gn_finalize', GnFinalizeDesc), ('attn', AttnDesc),
+                ('embed', EmbedDesc)]
 
 
 class PlanOp(C.Structure):
@@ -111,13 +116,15 @@ SIZEOF_CHECKS = {
     0: PlanOp, DS_OP_GEMM: GemmDesc, DS_OP_GN_STATS: GnStatsDesc, DS_OP_GN_APPLY: GnApplyDesc, DS_OP_SOFTMAX: SoftmaxDesc,
     DS_OP_POSEMB: PosembDesc, DS_OP_LINEAR: LinearDesc, DS_OP_PREP_INPUT: PrepInputDesc, DS_OP_CHANMEAN: ChanmeanDesc,
     DS_OP_MEMSET: MemsetDesc, DS_OP_LAYERNORM: LayernormDesc, DS_OP_GEGLU: GegluDesc, DS_OP_GN_FINALIZE: GnFinalizeDesc, DS_OP_ATTN: AttnDesc,
+    DS_OP_EMBED: EmbedDesc,
 }
 
 UNION_FIELD = {
     DS_OP_GEMM: 'gemm', DS_OP_GN_STATS: 'gn_stats', DS_OP_GN_APPLY: 'gn_apply', DS_OP_SOFTMAX: 'softmax', DS_OP_POSEMB: 'posemb',
     DS_OP_LINEAR: 'linear', DS_OP_PREP_INPUT: 'prep_input', DS_OP_CHANMEAN: 'chanmean', DS_OP_MEMSET: 'memset',
-    DS_OP_LAYERNORM: 'layernorm', DS_OP_GEGLU: 'geglu', DS_OP_GN_FINALIZE: 'gn_finalize', DS_OP_ATTN: 'attn',
+    DS_OP_LAYERNORM: 'layernorm', DS_OP_GEGLU: 'geglu', DS_OP_GN_FINALIZE: 'gn_finalize', DS_OP_ATTN: 'attn', DS_OP_EMBED: 'embed',
 }
 OP_TYPE_OF = {GemmDesc: DS_OP_GEMM, GnStatsDesc: DS_OP_GN_STATS, GnApplyDesc: DS_OP_GN_APPLY, SoftmaxDesc: DS_OP_SOFTMAX,
               PosembDesc: DS_OP_POSEMB, LinearDesc: DS_OP_LINEAR, PrepInputDesc: DS_OP_PREP_INPUT, ChanmeanDesc: DS_OP_CHANMEAN,
-              MemsetDesc: DS_OP_MEMSET, LayernormDesc: DS_OP_LAYERNORM, GegluDesc: DS_OP_GEGLU, GnFinalizeDesc: DS_OP_GN_FINALIZE, AttnDesc: DS_OP_ATTN}
+              MemsetDesc: DS_OP_MEMSET, LayernormDesc: DS_OP_LAYERNORM, GegluDesc: DS_OP_GEGLU, GnFinalizeDesc: DS_OP_GN_FINALIZE, AttnDesc: DS_OP_ATTN,
+              EmbedDesc: DS_OP_EMBED}

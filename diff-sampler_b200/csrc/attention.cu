@@ -47,6 +47,7 @@ struct alignas(64) AttnKernelParams {
     unsigned long long* trace;
     int trace_cap;
     int interleave;             // attn3: issue the MMAs of P.V(j) and of the next score product alternately (two independent accumulation chains)
+    int causal;                 // attn3: query l sees keys <= l
 };
 
 // trace tags: who (0 TMA, 1 MMA, 2 + g softmax group g) << 16 | event << 8 | block index (low 8 bits).  Every role writes its own region
@@ -915,9 +916,9 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 const int ks = kc % kA3Ring;
                 const uint32_t par = (s_par >> g) & 1;
                 tr(it, 1, 0, j);
-                mbar_wait(&ctl->k_full[ks], (kc / kA3Ring) & 1);
+                mbar_wait_warp(&ctl->k_full[ks], (kc / kA3Ring) & 1);
                 tr(it, 1, 1, j);
-                mbar_wait(&ctl->s_empty[g], par ^ 1);
+                mbar_wait_warp(&ctl->s_empty[g], par ^ 1);
                 tr(it, 1, 2, j);
                 tc_fence_after();
                 const uint32_t sk = smem_u32(smem + kA3OffK + ks * kA2KStage);
@@ -943,12 +944,12 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 const int vs = vc % kA3Ring;
                 const uint32_t par = (p_par >> g) & 1;
                 tr(it, 1, 4, j);
-                mbar_wait(&ctl->v_full[vs], (vc / kA3Ring) & 1);
+                mbar_wait_warp(&ctl->v_full[vs], (vc / kA3Ring) & 1);
                 tr(it, 1, 5, j);
-                mbar_wait(&ctl->p_full[g], par);
+                mbar_wait_warp(&ctl->p_full[g], par);
                 tr(it, 1, 6, j);
                 const bool first = j < kA3Groups;           // this group's first block of the tile: fresh accumulator
-                if (first) mbar_wait(&ctl->o_empty[g], (it & 1) ^ 1);      // the group has read the previous tile's result out of it
+                if (first) mbar_wait_warp(&ctl->o_empty[g], (it & 1) ^ 1);      // the group has read the previous tile's result out of it
                 tc_fence_after();
                 const uint32_t sv = smem_u32(smem + kA3OffV + vs * kA2VStage);
                 const uint32_t sp = smem_u32(smem + kA3OffP + g * kA2PBuf);
@@ -978,13 +979,13 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 const int vs = vc % kA3Ring, ks = kc % kA3Ring;
                 const uint32_t ppar = (p_par >> g) & 1, spar = (s_par >> gq) & 1;
                 tr(it, 1, 4, j);
-                mbar_wait(&ctl->v_full[vs], (vc / kA3Ring) & 1);
-                mbar_wait(&ctl->p_full[g], ppar);
+                mbar_wait_warp(&ctl->v_full[vs], (vc / kA3Ring) & 1);
+                mbar_wait_warp(&ctl->p_full[g], ppar);
                 const bool first = j < kA3Groups;
-                if (first) mbar_wait(&ctl->o_empty[g], (it & 1) ^ 1);
+                if (first) mbar_wait_warp(&ctl->o_empty[g], (it & 1) ^ 1);
                 tr(it, 1, 6, j);
-                mbar_wait(&ctl->k_full[ks], (kc / kA3Ring) & 1);
-                mbar_wait(&ctl->s_empty[gq], spar ^ 1);
+                mbar_wait_warp(&ctl->k_full[ks], (kc / kA3Ring) & 1);
+                mbar_wait_warp(&ctl->s_empty[gq], spar ^ 1);
                 tr(it, 1, 2, jq);
                 tc_fence_after();
                 const uint32_t sv = smem_u32(smem + kA3OffV + vs * kA2VStage);
@@ -1017,7 +1018,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 s_par ^= 1u << gq;
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                mbar_wait(&ctl->q_full, it & 1);
+                mbar_wait_warp(&ctl->q_full, it & 1);
                 const int ahead = nkv < kA3Groups ? nkv : kA3Groups;
                 for (int j = 0; j < ahead; ++j) issue_qk(j);
                 if (nkv <= kA3Groups) { __syncwarp(); if (elect_one()) umma_commit(&ctl->q_empty); __syncwarp(); }
@@ -1061,8 +1062,13 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 mbar_wait(&ctl->s_full[g], bc & 1);
                 if (quad == 0 && lane == 0) tr(it, 2 + g, 1, j);
                 tc_fence_after();
-                const int kvalid = p.Lk - j * 64;        // keys of this block that exist (>= 64: all)
-                const float t = (kvalid >= 64 ? attn3_row_max<false>(t_s, 64) : attn3_row_max<true>(t_s, kvalid)) * p.scale_log2e;
+                int kvalid = p.Lk - j * 64;              // keys of this block that exist (>= 64: all) ...
+                if (p.causal) {                          // ... and that this thread's query may attend to (<= 0: none)
+                    const int lim = qt * 128 + row - j * 64 + 1;
+                    kvalid = lim < kvalid ? lim : kvalid;
+                }
+                const bool all_keys = __all_sync(0xffffffffu, kvalid >= 64);
+                const float t = (all_keys ? attn3_row_max<false>(t_s, 64) : attn3_row_max<true>(t_s, kvalid)) * p.scale_log2e;
                 if (quad == 0 && lane == 0) tr(it, 2 + g, 2, j);
                 if (!have) {
                     m_ref = t;                           // first block of the row in this group: exact maximum, nothing to rescale
@@ -1073,7 +1079,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                     const bool need = t > m_ref + kA3RescaleThreshold;
                     if (__any_sync(0xffffffffu, need)) {
                         const float m_new = need ? t : m_ref;
-                        const float alpha = ex2_approx(m_ref - m_new);           // 1 for the rows that keep their reference
+                        const float alpha = need ? ex2_approx(m_ref - m_new) : 1.f;      // rows that keep their reference (possibly -inf: no key seen yet)
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
                             uint32_t v[32];
@@ -1089,8 +1095,8 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                     }
                 }
                 if (quad == 0 && lane == 0) tr(it, 2 + g, 3, j);
-                l += (kvalid >= 64) ? attn3_exp_store<false>(t_s, sP, row, 64, p.scale_log2e, m_ref)
-                                    : attn3_exp_store<true>(t_s, sP, row, kvalid, p.scale_log2e, m_ref);
+                l += all_keys ? attn3_exp_store<false>(t_s, sP, row, 64, p.scale_log2e, m_ref)
+                              : attn3_exp_store<true>(t_s, sP, row, kvalid, p.scale_log2e, m_ref);
                 have = true;
                 ++bc;
                 if (quad == 0 && lane == 0) tr(it, 2 + g, 4, j);
@@ -1119,8 +1125,9 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ctl->o_empty[g]);
-            const float inv = 1.f / l;
-            float lam = m_ref + lg2_approx(l);           // this partial result carries weight 2^lam
+            // a row may have seen no key at all in this group's blocks (causal mask): it then carries weight 2^-inf = 0
+            const float inv = l > 0.f ? 1.f / l : 0.f;
+            float lam = l > 0.f ? m_ref + lg2_approx(l) : -INFINITY;       // this partial result carries weight 2^lam
 #pragma unroll
             for (int i = 0; i < 64; ++i) O[i] *= inv;
             if (g > 0) {
@@ -1226,6 +1233,8 @@ int attn_build(const ds_attn_desc* d, AttnKernelParams* kp) {
     kp->trace_cap = g_attn_trace_cap;
     static const int inter = [] { const char* e = getenv("DSB_ATTN_INTERLEAVE"); return e ? atoi(e) : 1; }();
     kp->interleave = inter;
+    kp->causal = d->causal ? 1 : 0;
+    if (d->causal && (attn_version() != 3 || d->L != d->Lk)) return -40;       // the causal mask exists in the attn3 kernel only (self-attention)
     return 0;
 }
 

@@ -732,6 +732,10 @@ __global__ void layernorm_kernel(ds_layernorm_desc d) {
             const float4 b = *reinterpret_cast<const float4*>(d.beta + 4 * j);
             const float y[4] = {(v[k].x - mean) * rstd * g.x + b.x, (v[k].y - mean) * rstd * g.y + b.y,
                                 (v[k].z - mean) * rstd * g.z + b.z, (v[k].w - mean) * rstd * g.w + b.w};
+            if (d.fmt == 2) {                    // fp32 result (the last LayerNorm of the CLIP text encoder)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(d.out) + row * d.C + 4 * j) = make_float4(y[0], y[1], y[2], y[3]);
+                continue;
+            }
             __align__(8) __half hi[4];
             __align__(8) __half lo[4];
 #pragma unroll
@@ -740,6 +744,36 @@ __global__ void layernorm_kernel(ds_layernorm_desc d) {
             if (d.nplanes > 1) *reinterpret_cast<uint2*>(out + plane + row * d.C + 4 * j) = *reinterpret_cast<const uint2*>(lo);
         }
     }
+}
+
+// quick-GELU (ds_geglu_desc.mode == 1): out = x * sigmoid(1.702 x) on fp32 [rows][I] -> fp16 hi/lo planes (CLIP MLP activation)
+__global__ void quick_gelu_kernel(ds_geglu_desc d) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 4 values
+    const long long total = d.rows * (d.I / 4);
+    if (idx >= total) return;
+    const float4 a = *reinterpret_cast<const float4*>(d.src + idx * 4);
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    __align__(8) __half hi[4];
+    __align__(8) __half lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_h16(av[q] / (1.0f + expf(-1.702f * av[q])), hi[q], lo[q]);
+    __half* out = reinterpret_cast<__half*>(d.out);
+    *reinterpret_cast<uint2*>(out + idx * 4) = *reinterpret_cast<const uint2*>(hi);
+    if (d.nplanes > 1) *reinterpret_cast<uint2*>(out + d.rows * d.I + idx * 4) = *reinterpret_cast<const uint2*>(lo);
+}
+
+// token + position embedding (ds_embed_desc): one thread per 4 channels of one row
+__global__ void embed_kernel(ds_embed_desc d) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c4 = d.C / 4;
+    if (idx >= d.rows * c4) return;
+    const long long row = idx / c4;
+    const int j = (int)(idx - row * c4) * 4;
+    int id = d.ids[row];
+    id = id < 0 ? 0 : (id >= d.vocab ? d.vocab - 1 : id);
+    const float4 t = *reinterpret_cast<const float4*>(d.tok + (long long)id * d.C + j);
+    const float4 p = *reinterpret_cast<const float4*>(d.pos + (long long)(row % d.T) * d.C + j);
+    *reinterpret_cast<float4*>(d.out + row * d.C + j) = make_float4(t.x + p.x, t.y + p.y, t.z + p.z, t.w + p.w);
 }
 
 __global__ void geglu_kernel(ds_geglu_desc d) {
@@ -970,6 +1004,13 @@ extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream
     return ok();
 }
 
+extern "C" int ds_embed_launch(const ds_embed_desc* d, cudaStream_t stream) {
+    if (d->C % 4 || d->rows <= 0 || d->T <= 0 || d->vocab <= 0) return -2;
+    const long long total = d->rows * (d->C / 4);
+    embed_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(*d);
+    return ok();
+}
+
 extern "C" int ds_layernorm_launch(const ds_layernorm_desc* d, cudaStream_t stream) {
     if (d->C % 4 || d->C > 2048) return -2;
     const int wpb = 8;
@@ -985,6 +1026,11 @@ extern "C" int ds_layernorm_launch(const ds_layernorm_desc* d, cudaStream_t stre
 extern "C" int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream) {
     if (d->I % 4) return -2;
     const long long total = d->rows * (d->I / 4);
+    if (d->mode == 1) {
+        if (d->fmt != 0) return -2;
+        quick_gelu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(*d);
+        return ok();
+    }
     if (d->fmt == 1) {
         if (d->nplanes != 2) return -2;
         geglu_f8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(*d);

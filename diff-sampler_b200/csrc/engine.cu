@@ -99,6 +99,7 @@ static void visit_ptrs(ds_plan_op& op, F f) {
         case DS_OP_GEGLU: { auto& d = op.u.geglu; P(d.src); P(d.out); break; }
         case DS_OP_GN_FINALIZE: { auto& d = op.u.gn_finalize; P(d.quads0); P(d.quads1); P(d.sums); P(d.gamma); P(d.beta); P(d.ada); P(d.coef); break; }
         case DS_OP_ATTN: { auto& d = op.u.attn; P(d.q); P(d.k); P(d.vt); P(d.out); break; }
+        case DS_OP_EMBED: { auto& d = op.u.embed; P(d.ids); P(d.tok); P(d.pos); P(d.out); break; }
         default: break;
     }
 #undef P
@@ -119,6 +120,7 @@ static int launch_op(const ds_plan_op& op, const unsigned char* gemm_kp, cudaStr
         case DS_OP_LAYERNORM: return ds_layernorm_launch(&op.u.layernorm, s);
         case DS_OP_GEGLU: return ds_geglu_launch(&op.u.geglu, s);
         case DS_OP_GN_FINALIZE: return ds_gn_finalize_launch(&op.u.gn_finalize, s);
+        case DS_OP_EMBED: return ds_embed_launch(&op.u.embed, s);
         case DS_OP_ATTN:
             if (gemm_kp) return dsb::attn_run(reinterpret_cast<const dsb::AttnKernelParams*>(gemm_kp), s);
             return ds_attn_launch(&op.u.attn, s);
@@ -457,6 +459,7 @@ size_t ds_sizeof(int which) {
         case DS_OP_GEGLU: return sizeof(ds_geglu_desc);
         case DS_OP_GN_FINALIZE: return sizeof(ds_gn_finalize_desc);
         case DS_OP_ATTN: return sizeof(ds_attn_desc);
+        case DS_OP_EMBED: return sizeof(ds_embed_desc);
         default: return 0;
     }
 }

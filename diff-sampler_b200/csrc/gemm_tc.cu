@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const int b_row = nt * p.BN + zh * p.b_row_per_zh;
                 const int b_z = zb * p.b_z_per_zb + zh * p.b_z_per_zh;
                 for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    mbar_wait_warp(&ctl->empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + kATileBytes;
                     __syncwarp();
@@ -382,11 +382,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
-                mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+                mbar_wait_warp(&ctl->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait(&ctl->full[stage], phase);
+                    mbar_wait_warp(&ctl->full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + kATileBytes;
@@ -544,7 +544,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 const int aw0 = rem - ah0 * p.conv_W;
                 const int b_row = nt * p.BN + rank * half_bn;
                 for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait(&ctl->empty[stage], phase ^ 1);
+                    mbar_wait_warp(&ctl->empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + kATileBytes;
                     __syncwarp();
@@ -592,11 +592,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
             for (int tile = first; tile < total_tiles; tile += step, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
-                mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+                mbar_wait_warp(&ctl->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait(&ctl->full[stage], phase);
+                    mbar_wait_warp(&ctl->full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + kATileBytes;

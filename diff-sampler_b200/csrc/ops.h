@@ -183,6 +183,8 @@ typedef struct ds_attn_desc {
     int32_t q_pitch, q_c0, k_pitch, k_c0, vt_pitch, o_pitch;
     int32_t nplanes;        // must be 2
     float scale;            // > 0
+    int32_t causal;         // 1: query l attends to keys <= l only (CLIP text encoder; L == Lk).  attn3 kernel only
+    int32_t pad0;
 } ds_attn_desc;
 
 // Row softmax: P = softmax(S) over the last dim, fp32 in, fp16 hi/lo planes out. Reference: networks_edm.py:108.
@@ -248,7 +250,8 @@ typedef struct ds_layernorm_desc {
     int32_t C;
     int32_t nplanes;
     float eps;
-    int32_t fmt;            // 0: fp16 hi/lo planes.  1: operand image of an f8 GEMM (ds_gemm_desc.f8)
+    int32_t fmt;            // 0: fp16 hi/lo planes.  1: operand image of an f8 GEMM (ds_gemm_desc.f8).  2: fp32 [rows][C] (final LayerNorm of
+                            // the CLIP text encoder: the output IS the conditioning tensor)
 } ds_layernorm_desc;
 
 // GEGLU gate: out = x[:, :I] * gelu(x[:, I:]) on fp32 [rows][2I] -> fp16 hi/lo planes [rows][I]  (attention.py:42-44, exact erf GELU).
@@ -258,9 +261,21 @@ typedef struct ds_geglu_desc {
     int64_t rows;
     int32_t I;
     int32_t nplanes;
-    int32_t fmt;            // as ds_layernorm_desc.fmt
-    int32_t pad0;
+    int32_t fmt;            // as ds_layernorm_desc.fmt (0 or 1)
+    int32_t mode;           // 0: GEGLU (above).  1: quick-GELU, out = x * sigmoid(1.702 x) on fp32 [rows][I] (CLIP MLP, modeling_clip.py quick_gelu)
 } ds_geglu_desc;
+
+// Token + position embedding (CLIPTextEmbeddings.forward): out[row][c] = tok[ids[row]][c] + pos[row % T][c], fp32.
+typedef struct ds_embed_desc {
+    const int32_t* ids;     // [rows] token ids
+    const float* tok;       // [vocab][C]
+    const float* pos;       // [T][C]
+    float* out;             // [rows][C]
+    int64_t rows;
+    int32_t T, C;
+    int32_t vocab;
+    int32_t pad0;
+} ds_embed_desc;
 
 // Channel mean of an NHWC fp32 tensor (AMED bottleneck read-out, solvers_amed.py:24,27).
 typedef struct ds_chanmean_desc {
@@ -339,6 +354,7 @@ int ds_prep_input_launch(const ds_prep_input_desc* d, cudaStream_t stream);
 int ds_chanmean_launch(const ds_chanmean_desc* d, cudaStream_t stream);
 int ds_layernorm_launch(const ds_layernorm_desc* d, cudaStream_t stream);
 int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream);
+int ds_embed_launch(const ds_embed_desc* d, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // Plan records.  The Python plan compiler (diff-sampler_b200/plan.py) lowers one denoiser network at
@@ -347,7 +363,7 @@ int ds_geglu_launch(const ds_geglu_desc* d, cudaStream_t stream);
 //   bits 60..63 = space (0 absolute/NULL, 1 arena, 2 weights, 3 io slot), bits 0..59 = byte offset / slot.
 enum { DS_OP_GEMM = 1, DS_OP_GN_STATS = 2, DS_OP_GN_APPLY = 3, DS_OP_SOFTMAX = 4, DS_OP_POSEMB = 5, DS_OP_LINEAR = 6,
        DS_OP_PREP_INPUT = 7, DS_OP_CHANMEAN = 8, DS_OP_MEMSET = 9, DS_OP_LAYERNORM = 10, DS_OP_GEGLU = 11,
-       DS_OP_GN_FINALIZE = 12, DS_OP_ATTN = 13 };
+       DS_OP_GN_FINALIZE = 12, DS_OP_ATTN = 13, DS_OP_EMBED = 14 };
 enum { DS_IO_X = 0, DS_IO_D = 1, DS_IO_SIGMA = 2, DS_IO_LABELS = 3, DS_IO_BOTTLENECK = 4, DS_IO_CTX = 5, DS_IO_COUNT = 6 };
 
 typedef struct ds_memset_desc {
@@ -372,6 +388,7 @@ typedef struct ds_plan_op {
         ds_geglu_desc geglu;
         ds_gn_finalize_desc gn_finalize;
         ds_attn_desc attn;
+        ds_embed_desc embed;
     } u;
 } ds_plan_op;
 

@@ -67,6 +67,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// The same for a fully converged warp: lane 0 polls, the other lanes wait at the warp barrier (one poller per barrier instead of 32;
+// __syncwarp orders lane 0's acquire before the other lanes' subsequent accesses).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if (lane_id() == 0) mbar_wait(bar, parity);
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -447,11 +447,18 @@ def _layernorm(mem, d):
     rows, C = int(d.rows), int(d.C)
     x = mem.view(d.src, torch.float32, rows * C).reshape(rows, C).double()
     y = torch.nn.functional.layer_norm(x, (C,), mem.view(d.gamma, torch.float32, C).double(), mem.view(d.beta, torch.float32, C).double(), float(d.eps))
+    if int(d.fmt) == 2:                                        # fp32 result
+        mem.view(d.out, torch.float32, rows * C)[:] = y.reshape(-1).float()
+        return
     _store_planes(mem, d.out, y, int(d.nplanes), int(d.fmt))
 
 
 def _geglu(mem, d):
     rows, I = int(d.rows), int(d.I)
+    if int(d.mode) == 1:                                       # quick-GELU on [rows][I]
+        x = mem.view(d.src, torch.float32, rows * I).reshape(rows, I).double()
+        _store_planes(mem, d.out, x * torch.sigmoid(1.702 * x), int(d.nplanes), 0)
+        return
     x = mem.view(d.src, torch.float32, rows * 2 * I).reshape(rows, 2 * I).double()
     _store_planes(mem, d.out, x[:, :I] * torch.nn.functional.gelu(x[:, I:]), int(d.nplanes), int(d.fmt))
 
@@ -475,7 +482,10 @@ def _attn(mem, d):
     for h in range(nh):
         qs = q[:, :, int(d.q_c0) + h * 64:int(d.q_c0) + (h + 1) * 64]
         ks = k[:, :, int(d.k_c0) + h * 64:int(d.k_c0) + (h + 1) * 64]
-        p = torch.softmax(float(d.scale) * qs @ ks.transpose(1, 2), dim=2)
+        sc = float(d.scale) * qs @ ks.transpose(1, 2)
+        if int(d.causal):
+            sc = sc + torch.full((L, Lk), float('-inf'), dtype=torch.float64).triu(1)
+        p = torch.softmax(sc, dim=2)
         out[:, :, h * 64:(h + 1) * 64] = p @ vt[:, h * 64:(h + 1) * 64, :Lk].transpose(1, 2)
     idx = None
     if op != nh * 64:
@@ -483,11 +493,20 @@ def _attn(mem, d):
     _store_planes(mem, d.out, out, 2, index=idx)
 
 
+def _embed(mem, d):
+    rows, T, C_, V = int(d.rows), int(d.T), int(d.C), int(d.vocab)
+    ids = mem.view(d.ids, torch.int32, rows).long().clamp(0, V - 1)
+    tok = mem.view(d.tok, torch.float32, V * C_).reshape(V, C_)
+    pos = mem.view(d.pos, torch.float32, T * C_).reshape(T, C_)
+    mem.view(d.out, torch.float32, rows * C_)[:] = (tok[ids] + pos[torch.arange(rows) % T]).reshape(-1)
+
+
 _DISPATCH = {
     S.DS_OP_GEMM: ('gemm', _gemm), S.DS_OP_GN_STATS: ('gn_stats', _gn_stats), S.DS_OP_GN_APPLY: ('gn_apply', _gn_apply),
     S.DS_OP_SOFTMAX: ('softmax', _softmax), S.DS_OP_POSEMB: ('posemb', _posemb), S.DS_OP_LINEAR: ('linear', _linear),
     S.DS_OP_PREP_INPUT: ('prep_input', _prep_input), S.DS_OP_CHANMEAN: ('chanmean', _chanmean), S.DS_OP_LAYERNORM: ('layernorm', _layernorm),
     S.DS_OP_GEGLU: ('geglu', _geglu), S.DS_OP_GN_FINALIZE: ('gn_finalize', _gn_finalize), S.DS_OP_ATTN: ('attn', _attn),
+    S.DS_OP_EMBED: ('embed', _embed),
 }
 
 
