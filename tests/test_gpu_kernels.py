@@ -496,6 +496,17 @@ def test_fused_stats_rejects_partial_slabs(lib):
                                          # many short tiles per CTA (L = 64: 300 tiles)
                                          (4, 6, 1024, 1024, 64), (2, 2, 320, 192, 64), (1, 3, 128, 64, 64), (50, 6, 64, 64, 64), (3, 5, 200, 130, 40)])
 def test_fused_attention(lib, B, nh, L, Lk, d):
+    _fused_attention(lib, B, nh, L, Lk, d, causal=False)
+
+
+@pytest.mark.parametrize('B,nh,L,d', [(3, 12, 77, 64), (2, 2, 64, 64), (1, 3, 200, 40), (2, 4, 1024, 64), (5, 1, 9, 64)])
+def test_fused_attention_causal(lib, B, nh, L, d):
+    """Causal self-attention (CLIP text encoder): query l sees keys <= l.  77 tokens put rows without any visible key into the second
+    softmax group (weight 2^-inf in the merge); 1024 exercises rows whose later key blocks are entirely masked."""
+    _fused_attention(lib, B, nh, L, L, d, causal=True)
+
+
+def _fused_attention(lib, B, nh, L, Lk, d, causal):
     """attn_kernel (QK^T -> online softmax -> PV in one kernel, head dim padded to 64) against float64 softmax attention on the
     same fp16 hi+lo operands: self-attention shapes, a cross-attention shape (77 keys, pitch 80), partial query / key tiles."""
     from diff_sampler_b200 import _cstructs as S
@@ -527,17 +538,20 @@ def test_fused_attention(lib, B, nh, L, Lk, d):
     vta = planes(vt)
     out = torch.full((2, B, L, hp), float('nan'), dtype=torch.float16, device=dev())
     lib.op_launch(S.AttnDesc(q=q_ptr, k=k_ptr, vt=vta.data_ptr(), out=out.data_ptr(), B=B, nh=nh, L=L, Lk=Lk, q_pitch=q_pitch, q_c0=q_c0,
-                             k_pitch=k_pitch, k_c0=k_c0, vt_pitch=vt_pitch, o_pitch=hp, nplanes=2, scale=scale))
+                             k_pitch=k_pitch, k_c0=k_c0, vt_pitch=vt_pitch, o_pitch=hp, nplanes=2, scale=scale, causal=int(causal)))
     sync()
     got = (out[0].double() + out[1].double()).reshape(B, L, nh, 64).permute(0, 2, 1, 3)
     # reference on the operands as the kernel sees them (hi + lo), float64
     qd = (planes(q)[0].double() + planes(q)[1].double())
     kd = (planes(k)[0].double() + planes(k)[1].double())
     vd = (planes(v)[0].double() + planes(v)[1].double())
-    ref = torch.softmax(scale * qd @ kd.transpose(-1, -2), dim=-1) @ vd
+    sc = scale * qd @ kd.transpose(-1, -2)
+    if causal:
+        sc = sc + torch.full((L, Lk), float('-inf'), dtype=torch.float64, device=dev()).triu(1)
+    ref = torch.softmax(sc, dim=-1) @ vd
     err = (got[..., :d] - ref).abs().max().item()
     pad = got[..., d:].abs().max().item() if d < 64 else 0.0
-    print(f'fused attention B{B} nh{nh} L{L} Lk{Lk} d{d}: err {err:.3e} (max {ref.abs().max().item():.2f}), pad {pad:.1e}')
+    print(f'fused attention B{B} nh{nh} L{L} Lk{Lk} d{d} causal={causal}: err {err:.3e} (max {ref.abs().max().item():.2f}), pad {pad:.1e}')
     assert err < 2e-5 * max(1.0, ref.abs().max().item()) and pad == 0.0
 
 

@@ -932,3 +932,37 @@ def test_vae_decoder_parity(name, R):
     print(f'{name}: image err {err:.3e} (max|x| {ref.abs().max().item():.2f})')
     assert got.shape == ref.shape and err < TOL
 
+
+
+# --------------------------------------------------------------------------------------------- text encoder
+@pytest.mark.parametrize('name,B', [('tiny_clip', 3), ('clip_l', 2)])
+def test_clip_text_encoder_parity(name, B):
+    """get_learned_conditioning's encoder through B200CLIPTextEncoder vs the CPU oracle (pinned to transformers' CLIPTextModel) and, for
+    tiny_clip, the committed transformers output itself; clip_l has the dimensions Stable Diffusion v1.x conditions on (12 layers,
+    12 x 64 heads, 768 wide, 49408 tokens), seeded weights."""
+    import os
+    import numpy as np
+    from oracle import clip_oracle as CO
+    from diff_sampler_b200.clip_net import B200CLIPTextEncoder
+    P, cfg = CO.make_params(name, seed=0)
+    enc = B200CLIPTextEncoder(P, num_heads=cfg['num_attention_heads'], device=_dev())
+    if name == 'tiny_clip':
+        d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_clip.npz'))
+        ids = torch.from_numpy(d['tiny_clip/ids'])[:B]
+    else:
+        g = torch.Generator().manual_seed(5)
+        ids = torch.randint(0, cfg['vocab_size'], (B, 77), generator=g)
+        ids[:, 0] = 49406
+        ids[0, 9:] = 49407
+    taps = {}
+    with torch.no_grad():
+        ref = CO.text_forward(P, cfg, ids, taps=taps)
+    got = enc(ids.to(_dev())).cpu()
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item()
+    print(f'{name}: last_hidden_state err {err:.3e} (max|x| {ref.abs().max().item():.2f}); launches {enc.total_launches}')
+    assert got.shape == ref.shape == (B, 77, cfg['hidden_size']) and err < TOL
+    if name == 'tiny_clip':
+        assert (got - torch.from_numpy(d['tiny_clip/out'])[:B]).abs().max().item() < TOL
+    with pytest.raises(Exception):
+        enc(ids)                                           # host tensor: no CPU fallback

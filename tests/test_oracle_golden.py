@@ -250,3 +250,23 @@ def test_vae_oracle_matches_reference():
         ref = d[f'vae/{name}/x']
         assert x.shape == ref.shape
         assert np.abs(x - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()), np.abs(x - ref).max()
+
+
+def test_clip_oracle_matches_transformers():
+    """Text-encoder restatement (oracle/clip_oracle.py) vs Hugging Face transformers' own CLIPTextModel -- the module the reference's
+    FrozenCLIPEmbedder wraps -- run in this container (oracle/gen_clip_golden.py)."""
+    from oracle import clip_oracle as CO
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_clip.npz'))
+    P, cfg = CO.make_params('tiny_clip', seed=0)
+    ids = torch.from_numpy(d['tiny_clip/ids'])
+    with torch.no_grad():
+        got = CO.text_forward(P, cfg, ids).numpy()
+    ref = d['tiny_clip/out']
+    assert got.shape == ref.shape == (3, 77, cfg['hidden_size'])
+    assert np.abs(got - ref).max() < 2e-5
+    # causal: changing a later token leaves earlier positions bit-identical
+    ids2 = ids.clone()
+    ids2[:, 40] = (ids2[:, 40] + 1) % cfg['vocab_size']
+    with torch.no_grad():
+        got2 = CO.text_forward(P, cfg, ids2).numpy()
+    assert np.array_equal(got2[:, :40], got[:, :40]) and np.abs(got2[:, 40:] - got[:, 40:]).max() > 1e-3

@@ -123,3 +123,34 @@ def test_vae_decoder_plan_on_the_cpu_interpreter():
         mine = PI.read_buffer(mem, pl, 'h:' + mname, (n, h, w, c)).permute(0, 3, 1, 2)
         assert (mine - t).abs().max().item() < 3e-5 * max(1.0, t.abs().max().item()), mname
     assert (out - ref).abs().max().item() < 3e-5
+
+
+def test_clip_text_encoder_plan_on_the_cpu_interpreter():
+    """The text-encoder plan (embedding gather, pre-LN layers with the causal fused attention, quick-GELU MLP, fp32 final LayerNorm)
+    against transformers' CLIPTextModel output (tests/golden/ref_clip.npz) and the oracle."""
+    import os
+    import numpy as np
+    from diff_sampler_b200 import clip_plan
+    from oracle import clip_oracle as CO
+    d = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_clip.npz'))
+    P, cfg = CO.make_params('tiny_clip', seed=0)
+    got_cfg = clip_plan.clip_config(P)
+    assert all(got_cfg[k] == cfg[k] for k in got_cfg)
+    wb = clip_plan.pack_clip_weights(P, got_cfg)
+    ids = torch.from_numpy(d['tiny_clip/ids'])
+    B, T = ids.shape
+    pl = clip_plan.compile_clip_plan(got_cfg, wb, B, T)
+    assert pl.meta['n_gemm'] == 5 * cfg['num_hidden_layers']
+    out = torch.zeros(B, T, cfg['hidden_size'])
+    PI.run_plan(pl, wb.bytes(), {S.DS_IO_X: ids.to(torch.int32).contiguous(), S.DS_IO_D: out})
+    err = (out - torch.from_numpy(d['tiny_clip/out'])).abs().max().item()
+    print(f'clip plan on the interpreter vs transformers: {err:.3e}')
+    assert err < 3e-5
+    # a shorter sequence is its own plan (position rows 0..T-1; causal => equal to the prefix of the long run)
+    T2 = 20
+    pl2 = clip_plan.compile_clip_plan(got_cfg, wb, B, T2)
+    out2 = torch.zeros(B, T2, cfg['hidden_size'])
+    PI.run_plan(pl2, wb.bytes(), {S.DS_IO_X: ids[:, :T2].to(torch.int32).contiguous(), S.DS_IO_D: out2})
+    assert (out2 - out[:, :T2]).abs().max().item() < 3e-5
+    with pytest.raises(ValueError):
+        clip_plan.compile_clip_plan(got_cfg, wb, B, 78)
