@@ -386,6 +386,9 @@ struct Attn2Ctl {
     float xm[128], xl[128];         // group 1's running max / sum per row
 };
 
+__device__ __forceinline__ void lds128(uint32_t saddr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr) : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -747,6 +750,7 @@ template <int NG> struct Attn3Ctl {
     uint64_t k_full[A3<NG>::kRing], k_empty[A3<NG>::kRing], v_full[A3<NG>::kRing], v_empty[A3<NG>::kRing];
     uint64_t s_full[NG], s_empty[NG], p_full[NG], o_full[NG], o_empty[NG];
     uint64_t x_full[NG], x_empty[NG];
+    uint64_t qt_full, qt_free;      // MODE 2: query tile copied into TMEM / all score products of the tile have read it
     uint32_t tmem_base;
     float xl[NG - 1][128];          // lambda = m + log2(l) of groups 1 .. NG - 1, per row
 };
@@ -809,8 +813,45 @@ __device__ __forceinline__ float attn3_exp_store(uint32_t t_s, uint32_t sP, int 
     return (l4[0] + l4[1]) + (l4[2] + l4[3]);
 }
 
-template <int NG>
+// P in tensor memory (PT variant): the probabilities replace the scores they were computed from.  Scores of keys 32 c .. 32 c + 31 sit in
+// columns 32 c .. 32 c + 31 (fp32); their fp16 hi parts go to columns 32 c .. 32 c + 15 (two keys per column), the lo parts to
+// columns 32 c + 16 .. 32 c + 31: each 16-key K slice of the P.V product is 8 consecutive columns (A operand from TMEM).
+template <bool MASKED>
+__device__ __forceinline__ float attn3_exp_store_tmem(uint32_t t_s, int kvalid, float scale_log2e, float m_ref) {
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t v[32], u[32];
+        DSB_TMEM_LD_32(t_s + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int col = c * 32 + 2 * i;
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2e, -m_ref));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2e, -m_ref));
+            if (MASKED) {
+                if (col >= kvalid) p0 = 0.f;
+                if (col + 1 >= kvalid) p1 = 0.f;
+            }
+            l4[i & 3] += p0 + p1;
+            const __half2 h2 = __floats2half2_rn(p0, p1);
+            const float2 hf = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+            u[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            u[16 + i] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        DSB_TMEM_ST_32(t_s + c * 32, u);
+    }
+    return (l4[0] + l4[1]) + (l4[2] + l4[3]);
+}
+
+// MODE 0: P through shared memory; 1: P in tensor memory (A operand of P.V from TMEM); 2: Q in tensor memory as well (NG = 3: columns
+// 192 .. 255 hold the query tile, hi parts in 192 .. 223, lo parts in 224 .. 255, two fp16 per column) -- then every MMA of the kernel
+// reads only its 2 KB B operand from shared memory.
+template <int NG, int MODE>
 __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid_constant__ AttnKernelParams p) {
+    constexpr bool PT = MODE >= 1, QT = MODE == 2;
+    static_assert(!QT || NG == 3, "the query tile in TMEM needs the 64 columns a fourth group would use");
     constexpr int kA3Groups = NG, kA3Ring = A3<NG>::kRing;
     constexpr int kA3OffK = A3<NG>::kOffK, kA3OffV = A3<NG>::kOffV, kA3OffP = A3<NG>::kOffP, kA3OffCtl = A3<NG>::kOffCtl;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -828,7 +869,9 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
         tma_prefetch_desc(&p.tmK);
         tma_prefetch_desc(&p.tmV);
         mbar_init(&ctl->q_full, 1);
-        mbar_init(&ctl->q_empty, 1);
+        mbar_init(&ctl->q_empty, QT ? 4 : 1);         // MODE 2: released by the four warps that copied the tile into TMEM
+        mbar_init(&ctl->qt_full, 4);
+        mbar_init(&ctl->qt_free, 1);
         for (int s = 0; s < kA3Ring; ++s) {
             mbar_init(&ctl->k_full[s], 1);
             mbar_init(&ctl->k_empty[s], 1);
@@ -918,7 +961,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 tr(it, 1, 0, j);
                 mbar_wait_warp(&ctl->k_full[ks], (kc / kA3Ring) & 1);
                 tr(it, 1, 1, j);
-                mbar_wait_warp(&ctl->s_empty[g], par ^ 1);
+                if (!PT) mbar_wait_warp(&ctl->s_empty[g], par ^ 1);      // PT: the P.V product that read P out of S[g] was issued earlier (pipeline order)
                 tr(it, 1, 2, j);
                 tc_fence_after();
                 const uint32_t sk = smem_u32(smem + kA3OffK + ks * kA2KStage);
@@ -929,8 +972,12 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                     for (int pass = 0; pass < 3; ++pass) {
                         const uint64_t da = umma_desc_sw128(sq + (pass == 1 ? 16384 : 0));
                         const uint64_t db = umma_desc_sw128(sk + (pass == 2 ? 8192 : 0));
+                        const uint32_t tq = tmem_base + 192 + (pass == 1 ? 32 : 0);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) {
+                            if (QT) umma_f16_ts(d_tmem, tq + 8 * k, db + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                            else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&ctl->k_empty[ks]);
                     umma_commit(&ctl->s_full[g]);
@@ -960,8 +1007,13 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                     for (int pass = 0; pass < 3; ++pass) {
                         const uint64_t da = umma_desc_sw128(sp + (pass == 1 ? 16384 : 0));
                         const uint64_t db = umma_desc_sw128(sv + (pass == 2 ? 8192 : 0));
+                        const uint32_t ta = tmem_base + g * 64 + (pass == 1 ? 16 : 0);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (pass > 0 || k > 0 || !first) ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) {
+                            const uint32_t acc = (pass > 0 || k > 0 || !first) ? 1u : 0u;
+                            if (PT) umma_f16_ts(d_tmem, ta + (k >> 1) * 32 + (k & 1) * 8, db + 2 * k, idesc, acc);
+                            else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, acc);
+                        }
                     }
                     umma_commit(&ctl->v_empty[vs]);
                     umma_commit(&ctl->o_full[g]);
@@ -975,7 +1027,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
             // same accumulator form a dependent chain (timeline in profiles/r02: ~95 cycles per 128x64x16 MMA issued back to back into one
             // accumulator, three times its tensor time), two chains into different accumulators overlap.
             auto issue_pv_qk = [&](int j, int jq) {
-                const int g = j % kA3Groups, gq = jq % kA3Groups;          // the same group (jq = j + NG), kept general
+                const int g = j % kA3Groups, gq = jq % kA3Groups;          // jq = j + NG (same group), or j + NG - 1 (previous group) with P in TMEM
                 const int vs = vc % kA3Ring, ks = kc % kA3Ring;
                 const uint32_t ppar = (p_par >> g) & 1, spar = (s_par >> gq) & 1;
                 tr(it, 1, 4, j);
@@ -985,7 +1037,7 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 if (first) mbar_wait_warp(&ctl->o_empty[g], (it & 1) ^ 1);
                 tr(it, 1, 6, j);
                 mbar_wait_warp(&ctl->k_full[ks], (kc / kA3Ring) & 1);
-                mbar_wait_warp(&ctl->s_empty[gq], spar ^ 1);
+                if (!PT) mbar_wait_warp(&ctl->s_empty[gq], spar ^ 1);
                 tr(it, 1, 2, jq);
                 tc_fence_after();
                 const uint32_t sv = smem_u32(smem + kA3OffV + vs * kA2VStage);
@@ -1000,10 +1052,14 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                         const uint64_t pb = umma_desc_sw128(sv + (pass == 2 ? 8192 : 0));
                         const uint64_t qa = umma_desc_sw128(sq + (pass == 1 ? 16384 : 0));
                         const uint64_t qb = umma_desc_sw128(sk + (pass == 2 ? 8192 : 0));
+                        const uint32_t ta = tmem_base + g * 64 + (pass == 1 ? 16 : 0);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            umma_f16(d_o, pa + 2 * k, pb + 2 * k, idesc, (pass > 0 || k > 0 || !first) ? 1u : 0u);
-                            umma_f16(d_s, qa + 2 * k, qb + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                            const uint32_t acc = (pass > 0 || k > 0 || !first) ? 1u : 0u;
+                            if (PT) umma_f16_ts(d_o, ta + (k >> 1) * 32 + (k & 1) * 8, pb + 2 * k, idesc, acc);
+                            else umma_f16(d_o, pa + 2 * k, pb + 2 * k, idesc, acc);
+                            if (QT) umma_f16_ts(d_s, tmem_base + 192 + (pass == 1 ? 32 : 0) + 8 * k, qb + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
+                            else umma_f16(d_s, qa + 2 * k, qb + 2 * k, idesc, (pass > 0 || k > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(&ctl->v_empty[vs]);
@@ -1018,19 +1074,22 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                 s_par ^= 1u << gq;
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                mbar_wait_warp(&ctl->q_full, it & 1);
-                const int ahead = nkv < kA3Groups ? nkv : kA3Groups;
+                mbar_wait_warp(QT ? &ctl->qt_full : &ctl->q_full, it & 1);
+                // score products run `look` blocks ahead of the P.V products.  With P in TMEM the scores of block j + NG go where P(j) is
+                // read from, so an interleaved pair is (P.V(j), S(j + NG - 1)): the S buffer of the previous group, whose P.V was issued before.
+                const int look = (PT && p.interleave) ? kA3Groups - 1 : kA3Groups;
+                const int ahead = nkv < look ? nkv : look;
                 for (int j = 0; j < ahead; ++j) issue_qk(j);
-                if (nkv <= kA3Groups) { __syncwarp(); if (elect_one()) umma_commit(&ctl->q_empty); __syncwarp(); }
+                if (nkv <= look) { __syncwarp(); if (elect_one()) umma_commit(QT ? &ctl->qt_free : &ctl->q_empty); __syncwarp(); }
                 for (int j = 0; j < nkv; ++j) {
-                    if (j + kA3Groups < nkv) {
+                    if (j + look < nkv) {
                         if (p.interleave) {
-                            issue_pv_qk(j, j + kA3Groups);
+                            issue_pv_qk(j, j + look);
                         } else {
                             issue_pv(j);
-                            issue_qk(j + kA3Groups);
+                            issue_qk(j + look);
                         }
-                        if (j + kA3Groups + 1 == nkv) { __syncwarp(); if (elect_one()) umma_commit(&ctl->q_empty); __syncwarp(); }
+                        if (j + look + 1 == nkv) { __syncwarp(); if (elect_one()) umma_commit(QT ? &ctl->qt_free : &ctl->q_empty); __syncwarp(); }
                     } else {
                         issue_pv(j);
                     }
@@ -1050,6 +1109,29 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
         const int ng = nkv < kA3Groups ? nkv : kA3Groups;                       // groups that have blocks
         AttnTracer tr(p, 2 + g);
         uint32_t bc = 0, it = 0;                        // key blocks processed by this group / tiles processed
+        // MODE 2: the last group moves the query tile of tile t from its TMA landing area into TMEM (each thread its own row: the
+        // 128-byte rows are 128B-swizzled, 16-byte chunk c of row r sits at chunk position c ^ (r & 7)) and hands the area back.
+        auto copy_q = [&](uint32_t t) {
+            mbar_wait(&ctl->qt_free, (t & 1) ^ 1);      // every score product of the previous tile has completed
+            mbar_wait(&ctl->q_full, t & 1);
+            const uint32_t sq = smem_u32(smem);
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+                uint32_t v[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    lds128(sq + pl * 16384 + row * 128 + ((c ^ (row & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                DSB_TMEM_ST_32(t_row + 192 + pl * 32, v);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&ctl->qt_full);
+                mbar_arrive(&ctl->q_empty);
+            }
+        };
+        if (QT && g == kA3Groups - 1 && (int)blockIdx.x < n_tiles) copy_q(0);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int qt = tile % p.q_tiles;
             const int z = tile / p.q_tiles;
@@ -1095,20 +1177,27 @@ __global__ void __launch_bounds__(A3<NG>::kThreads, 1) attn3_kernel(const __grid
                     }
                 }
                 if (quad == 0 && lane == 0) tr(it, 2 + g, 3, j);
-                l += all_keys ? attn3_exp_store<false>(t_s, sP, row, 64, p.scale_log2e, m_ref)
-                              : attn3_exp_store<true>(t_s, sP, row, kvalid, p.scale_log2e, m_ref);
+                if (PT) {
+                    l += all_keys ? attn3_exp_store_tmem<false>(t_s, 64, p.scale_log2e, m_ref)
+                                  : attn3_exp_store_tmem<true>(t_s, kvalid, p.scale_log2e, m_ref);
+                    tmem_st_wait();
+                } else {
+                    l += all_keys ? attn3_exp_store<false>(t_s, sP, row, 64, p.scale_log2e, m_ref)
+                                  : attn3_exp_store<true>(t_s, sP, row, kvalid, p.scale_log2e, m_ref);
+                }
                 have = true;
                 ++bc;
                 if (quad == 0 && lane == 0) tr(it, 2 + g, 4, j);
                 tc_fence_before();
-                fence_proxy_async();                    // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                if (!PT) fence_proxy_async();           // generic-proxy smem writes -> visible to the tensor core (async proxy)
                 __syncwarp();
                 if (quad == 0 && lane == 0) tr(it, 2 + g, 5, j);
                 if (lane == 0) {
-                    mbar_arrive(&ctl->s_empty[g]);
+                    if (!PT) mbar_arrive(&ctl->s_empty[g]);
                     mbar_arrive(&ctl->p_full[g]);
                 }
             }
+            if (QT && g == kA3Groups - 1 && tile + (int)gridDim.x < n_tiles) copy_q(it + 1);
             if (!have) continue;                         // fewer key blocks than groups: nothing for this group in any tile
             // ---- this group's result of the tile: O = accumulator / l relative to m_ref
             float O[64];
@@ -1240,7 +1329,7 @@ int attn_build(const ds_attn_desc* d, AttnKernelParams* kp) {
 
 size_t attn_params_size() { return sizeof(AttnKernelParams); }
 
-template <int NG>
+template <int NG, int MODE>
 static int attn3_launch(const AttnKernelParams* kp, cudaStream_t stream) {
     static bool attr_set[64] = {};
     static int sms[64] = {};
@@ -1248,20 +1337,24 @@ static int attn3_launch(const AttnKernelParams* kp, cudaStream_t stream) {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return -39;
     if (!attr_set[dev]) {
-        if (cudaFuncSetAttribute(attn3_kernel<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes) != cudaSuccess) return -36;
+        if (cudaFuncSetAttribute(attn3_kernel<NG, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kA3SmemBytes) != cudaSuccess) return -36;
         cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
         attr_set[dev] = true;
     }
     const long long tiles = (long long)kp->B * kp->nh * kp->q_tiles;
     if (tiles <= 0 || tiles > 0x7fffffffLL) return -37;
     const int grid = (int)(tiles < sms[dev] ? tiles : sms[dev]);
-    attn3_kernel<NG><<<grid, A3<NG>::kThreads, kA3SmemBytes, stream>>>(*kp);
+    attn3_kernel<NG, MODE><<<grid, A3<NG>::kThreads, kA3SmemBytes, stream>>>(*kp);
     return cudaGetLastError() == cudaSuccess ? 0 : -38;
 }
 
 static int attn3_run(const AttnKernelParams* kp, cudaStream_t stream) {
     static const int groups = [] { const char* e = getenv("DSB_ATTN_GROUPS"); const int x = e ? atoi(e) : 4; return x == 3 ? 3 : 4; }();
-    return groups == 3 ? attn3_launch<3>(kp, stream) : attn3_launch<4>(kp, stream);
+    // DSB_ATTN_TMEM: 0 = P through shared memory, 1 = P in tensor memory, 2 = P and Q in tensor memory (three groups)
+    static const int tm = [] { const char* e = getenv("DSB_ATTN_TMEM"); return e ? atoi(e) : 1; }();
+    if (tm >= 2) return attn3_launch<3, 2>(kp, stream);
+    if (tm == 1) return groups == 3 ? attn3_launch<3, 1>(kp, stream) : attn3_launch<4, 1>(kp, stream);
+    return groups == 3 ? attn3_launch<3, 0>(kp, stream) : attn3_launch<4, 0>(kp, stream);
 }
 
 static int attn2_run(const AttnKernelParams* kp, cudaStream_t stream) {
