@@ -1351,7 +1351,7 @@ static int attn3_launch(const AttnKernelParams* kp, cudaStream_t stream) {
 static int attn3_run(const AttnKernelParams* kp, cudaStream_t stream) {
     static const int groups = [] { const char* e = getenv("DSB_ATTN_GROUPS"); const int x = e ? atoi(e) : 4; return x == 3 ? 3 : 4; }();
     // DSB_ATTN_TMEM: 0 = P through shared memory, 1 = P in tensor memory, 2 = P and Q in tensor memory (three groups)
-    static const int tm = [] { const char* e = getenv("DSB_ATTN_TMEM"); return e ? atoi(e) : 1; }();
+    static const int tm = [] { const char* e = getenv("DSB_ATTN_TMEM"); return e ? atoi(e) : 2; }();
     if (tm >= 2) return attn3_launch<3, 2>(kp, stream);
     if (tm == 1) return groups == 3 ? attn3_launch<3, 1>(kp, stream) : attn3_launch<4, 1>(kp, stream);
     return groups == 3 ? attn3_launch<3, 0>(kp, stream) : attn3_launch<4, 0>(kp, stream);
