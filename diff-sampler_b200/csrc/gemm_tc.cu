@@ -98,6 +98,7 @@ template <int W>
 __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const float* v, long long grow_in_z, int col0, bool row_ok,
                                                int zb, int zh, const float4* res_pref, bool res_in_regs) {
     // v[W]: accumulators of this thread's row, columns col0 .. col0+W-1 (col0 is the global column)
+    const bool warp_rows_ok = __all_sync(0xffffffffu, row_ok);      // every lane has a valid row: the paired stores below may shuffle
     if (!row_ok) return;                                   // warp-uniform whenever statistics are fused (m_valid % 32 == 0)
     float r[W];
 #pragma unroll
@@ -219,9 +220,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     }
 
     const long long obase = (long long)zb * p.o_zb + (long long)zh * p.o_zh + grow_in_z * p.ldo + col0;
+    // Each thread owns one output row, so a plain 16-byte store per thread writes HALF of 32 different 32-byte sectors per warp
+    // instruction (ncu on the SD ff1 linear: 32 sectors per request, 2x the payload over the crossbar, L2 at 54 % while the tensor pipe
+    // idles at 27 %).  Lanes 2i / 2i+1 swap halves of an 8-float group instead: both then write the two halves of ONE sector of row 2i,
+    // and of row 2i+1 with the second store -- full sectors only.
+    const int odd = threadIdx.x & 1;
     if (p.out_f32) {
         float* o = p.out_f32 + obase;
-        if (full) {
+        if (full && warp_rows_ok) {
+            float* oe = o - odd * p.ldo + odd * 4;           // the even lane's row, this lane's half of the group
+#pragma unroll
+            for (int j = 0; j < W; j += 8) {
+                float x[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = __shfl_xor_sync(0xffffffffu, odd ? r[j + k] : r[j + 4 + k], 1);
+                const float4 s1 = odd ? make_float4(x[0], x[1], x[2], x[3]) : make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                const float4 s2 = odd ? make_float4(r[j + 4], r[j + 5], r[j + 6], r[j + 7]) : make_float4(x[0], x[1], x[2], x[3]);
+                *reinterpret_cast<float4*>(oe + j) = s1;
+                *reinterpret_cast<float4*>(oe + p.ldo + j) = s2;
+            }
+        } else if (full) {
 #pragma unroll
             for (int j = 0; j < W; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
         } else {
@@ -240,12 +258,33 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
                 hi[j] = __float2half_rn(r[j]);
                 lo[j] = __float2half_rn(r[j] - __half2float(hi[j]));
             }
+            if (warp_rows_ok && W % 16 == 0) {
+                // the same sector pairing for the fp16 planes: groups of 16 halves (32 bytes), lanes 2i / 2i+1 swap 16-byte halves
+                __half* he = oh - odd * p.ldo + odd * 8;
 #pragma unroll
-            for (int j = 0; j < W; j += 8) *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(hi + j);
-            if (p.o_plane) {
+                for (int pl = 0; pl < 2; ++pl) {
+                    if (pl == 1 && !p.o_plane) break;
+                    const __half* src = pl ? lo : hi;
+                    __half* dst = he + (pl ? p.o_plane : 0);
 #pragma unroll
-                for (int j = 0; j < W; j += 8)
-                    *reinterpret_cast<uint4*>(oh + p.o_plane + j) = *reinterpret_cast<const uint4*>(lo + j);
+                    for (int j = 0; j < W; j += 16) {
+                        const uint4 a = *reinterpret_cast<const uint4*>(src + j), b = *reinterpret_cast<const uint4*>(src + j + 8);
+                        const uint4 snd = odd ? a : b;
+                        uint4 x;
+                        x.x = __shfl_xor_sync(0xffffffffu, snd.x, 1); x.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+                        x.z = __shfl_xor_sync(0xffffffffu, snd.z, 1); x.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
+                        *reinterpret_cast<uint4*>(dst + j) = odd ? x : a;
+                        *reinterpret_cast<uint4*>(dst + p.ldo + j) = odd ? b : x;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < W; j += 8) *reinterpret_cast<uint4*>(oh + j) = *reinterpret_cast<const uint4*>(hi + j);
+                if (p.o_plane) {
+#pragma unroll
+                    for (int j = 0; j < W; j += 8)
+                        *reinterpret_cast<uint4*>(oh + p.o_plane + j) = *reinterpret_cast<const uint4*>(lo + j);
+                }
             }
         } else {
 #pragma unroll

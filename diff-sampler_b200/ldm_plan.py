@@ -179,7 +179,7 @@ def pack_ldm_weights(st, params, f8=False, f8_linear=False):
             elif kind == 'down':
                 add_conv(n, P(n + '.op.weight'), bias=P(n + '.op.bias'))
             elif kind == 'up':
-                add_conv(n, P(n + '.conv.weight'), bias=P(n + '.conv.bias'))
+                add_conv(n, P(n + '.conv.weight'), bias=P(n + '.conv.bias'), as_f8=f8)
     wb.add('affine:w', torch.cat(aff_w, dim=0))
     wb.add('affine:b', torch.cat(aff_b, dim=0))
     info['aff_total'] = aff_off
@@ -392,9 +392,10 @@ def compile_ldm_plan(st, wb, info, B, Bt, nT, R, npass=3, ctx_tokens=77, flash_a
         Ho = H * 2
         A.need('act', npl * Bt * Ho * Ho * cin * H2)
         emit(lambda R_: S.GnApplyDesc(src0=R_(src), src1=0, C0=cin, C1=0, H=H, W=H, B=Bt, groups=32, sums=0, gamma=0, beta=0, eps=0.0, silu=0,
-                                      ada=0, ada_stride=0, resample=2, nplanes=npl, out_act=0, out_raw=R_('act'), out_raw_f32=0))
+                                      ada=0, ada_stride=0, resample=2, nplanes=npl, out_act=0, out_raw=R_('act'), out_raw_f32=0, fmt=fmt_res))
         out = A.need('h:' + n, Bt * Ho * Ho * cout * F4)
-        emit(lambda R_: G.conv_gemm(R_('act'), Bt, Ho, Ho, cin, W(n + ':w'), cout, taps=9, npass=npass, out_f32=R_(out), bias=W(n + ':b'))[0])
+        emit(lambda R_: G.conv_gemm(R_('act'), Bt, Ho, Ho, cin, W(n + ':w'), cout, taps=9, npass=npass, out_f32=R_(out), bias=W(n + ':b'),
+                                    **f8_args(n))[0])
         return out, cout, Ho
 
     # ---------------- input conv --------------------------------------------------------------------------------------------

@@ -18,6 +18,9 @@ SHAPES = [  # (label, Bn, H, W, Cin, Cout)
     ('adm 64^2 192->192', 256, 64, 64, 192, 192), ('adm 32^2 384->384', 256, 32, 32, 384, 384), ('adm 16^2 576->576', 256, 16, 16, 576, 576),
     ('adm 8^2 768->768', 256, 8, 8, 768, 768), ('sd 8^2 1280->1280 x16', 16, 8, 8, 1280, 1280), ('sd 16^2 1280->1280 x16', 16, 16, 16, 1280, 1280),
     ('sd 32^2 640->640 x16', 16, 32, 32, 640, 640), ('sd 64^2 320->320 x16', 16, 64, 64, 320, 320), ('cifar 32^2 256->256', 512, 32, 32, 256, 256),
+    # short-K 1x1 convolutions / linears of the SD transformer blocks (7th field: taps)
+    ('sd1x1 64^2 320->2560 x16', 16, 64, 64, 320, 2560, 1), ('sd1x1 64^2 320->320 x16', 16, 64, 64, 320, 320, 1),
+    ('sd1x1 64^2 512->320 x16', 16, 64, 64, 512, 320, 1), ('sd1x1 32^2 640->5120 x16', 16, 32, 32, 640, 5120, 1),
 ]
 
 
@@ -43,13 +46,15 @@ def main():
     args = ap.parse_args()
     _lib.load()
     torch.manual_seed(0)
-    for label, Bn, H, W, Cin, Cout in SHAPES:
+    for label, Bn, H, W, Cin, Cout, *rest in SHAPES:
         if args.only and args.only not in label:
             continue
+        taps = rest[0] if rest else 9
+        ks = 3 if taps == 9 else 1
         x = torch.randn(Bn, H, W, Cin, device=dev)
-        w = torch.randn(Cout, Cin, 3, 3) / (3 * Cin ** 0.5)
+        w = torch.randn(Cout, Cin, ks, ks) / (ks * Cin ** 0.5)
         out = torch.empty(Bn * H * W, Cout, device=dev)
-        flops = 2.0 * Bn * H * W * Cout * Cin * 9
+        flops = 2.0 * Bn * H * W * Cout * Cin * taps
         m_tiles = -(-(Bn * H * W) // 128)
         auto_bn, _ = G.fill_bn(Cout, m_tiles)
         cands = sorted({c for c in (64, 80, 96, 128, 144, 160, 192, 256, auto_bn) if c <= 256 and (Cout % c == 0 or c == auto_bn or Cout > 256)})
@@ -72,7 +77,7 @@ def main():
                     if pair and (bn % 32 or m_tiles < 2):
                         continue
                     try:
-                        d, _ = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=9, npass=3, out_f32=out.data_ptr(), bn=bn, pair=pair, **kw)
+                        d, _ = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=taps, npass=3, out_f32=out.data_ptr(), bn=bn, pair=pair, **kw)
                         n = max(20, int(0.25 / max(flops * (2 if f8 else 3) / 1.2e15, 1e-5)))     # ~0.25 s of launches
                         ms = timed(d, args.reps if args.reps else min(n, 2000))
                     except Exception as e:

@@ -1,0 +1,17 @@
+#!/bin/bash
+# sector-paired epilogue stores (+ f8 Upsample convs in the LDM plan): correctness, 1x1 GEMM table, SD-v1.5 / CIFAR-10 benches
+O=gpurun_out/r02o
+mkdir -p $O; rm -f $O/status.txt $O/gemm_tiles_1x1.txt
+timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x > $O/tests_kernels.log 2>&1; echo "kernels rc=$? $(tail -1 $O/tests_kernels.log)" >> $O/status.txt
+timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > $O/tests_parity.log 2>&1; echo "parity rc=$? $(tail -1 $O/tests_parity.log)" >> $O/status.txt
+timeout 600 python profiles/bench_gemm_tiles.py --only "sd1x1 64^2 320->2560" --bn 256 > $O/gemm_tiles_1x1.txt 2> $O/gemm_tiles.err
+timeout 600 python profiles/bench_gemm_tiles.py --only "sd1x1 64^2 320->320" --bn 160 >> $O/gemm_tiles_1x1.txt 2>> $O/gemm_tiles.err
+timeout 600 python profiles/bench_gemm_tiles.py --only "cifar 32" --bn 256 >> $O/gemm_tiles_1x1.txt 2>> $O/gemm_tiles.err; echo "gemm tiles rc=$?" >> $O/status.txt
+ab() { name=$1; shift; envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
+    env "${envs[@]}" timeout 500 python bench.py --steps 6 --warmup 3 --no_cpu_baseline --all_configs 0 --gpu_eager 0 "$@" > $O/ab_$name.json 2> $O/ab_$name.err
+    echo "ab_$name rc=$? $(python -c "import json;d=json.loads(open('$O/ab_$name.json').read().strip().splitlines()[-1]);print(round(d['value'],2), d['clocks']['sm_mhz'], d.get('forward_breakdown_ms'), (d.get('roofline') or {}).get('frac'))" 2>&1 | tail -1)" >> $O/status.txt
+}
+ab cifar X=1 --
+ab sd15 X=1 -- --net sd15 --solver amed_dpm_pp --num_steps 4 --batch 8
+ab imagenet X=1 -- --net imagenet64 --solver dpm_pp --num_steps 11 --batch 256
+cat $O/status.txt | cut -c1-420; cat $O/gemm_tiles_1x1.txt | cut -c1-170; grep -E "^FAILED|^ERROR" $O/tests_*.log | head

@@ -159,8 +159,8 @@ def test_f8_operand_packing_and_plan():
 
 @pytest.mark.parametrize('f8,f8_linear', [(False, False), (True, False), (True, True)])
 def test_ldm_plan_lowering(f8, f8_linear):
-    """The latent-diffusion eps-net lowers on the host (no GPU) in every precision; f8 touches exactly the ResBlock convolutions, and the
-    opt-in f8_linear additionally the five single-consumer linears of every transformer block (with their producers' output format)."""
+    """The latent-diffusion eps-net lowers on the host (no GPU) in every precision; f8 touches exactly the ResBlock and Upsample convolutions,
+    and f8_linear additionally the five single-consumer linears of every transformer block (with their producers' output format)."""
     from diff_sampler_b200 import ldm_plan
     from oracle import ldm_oracle as LO
     P, cfg = LO.make_params('tiny_ldm')
@@ -170,6 +170,7 @@ def test_ldm_plan_lowering(f8, f8_linear):
     layers = [L for _, ls in st['inp'] + st['mid'] + st['out'] for L in ls]
     n_res = sum(1 for L in layers if L[0] == 'res')
     n_att = sum(1 for L in layers if L[0] == 'attn')
+    n_up = sum(1 for L in layers if L[0] == 'up')
     ops = [pl.ops_array[i] for i in range(pl.n_ops)]
     n_f8 = sum(1 for o in ops if o.type == S.DS_OP_GEMM and o.u.gemm.f8)
     n_fmt = sum(1 for o in ops if o.type == S.DS_OP_GN_APPLY and o.u.gn_apply.fmt == 1)
@@ -177,10 +178,11 @@ def test_ldm_plan_lowering(f8, f8_linear):
     n_gg = sum(1 for o in ops if o.type == S.DS_OP_GEGLU and o.u.geglu.fmt == 1)
     assert pl.n_ops > 50 and pl.arena_bytes > 0 and n_res > 0 and n_att > 0
     lin = 1 if f8_linear else 0
-    assert n_f8 == (2 * n_res if f8 else 0) + 5 * n_att * lin
-    assert n_fmt == (2 * n_res if f8 else 0) + 2 * n_att * lin           # + norm -> proj_in and the cast before proj_out
+    assert n_up > 0
+    assert n_f8 == (2 * n_res + n_up if f8 else 0) + 5 * n_att * lin
+    assert n_fmt == (2 * n_res + n_up if f8 else 0) + 2 * n_att * lin    # + norm -> proj_in and the cast before proj_out
     assert (n_ln, n_gg) == (2 * n_att * lin, n_att * lin)                # norm2, norm3; norm1 feeds both an A and a B operand and stays fp16
-    assert len(info['f8_shift']) == (2 * n_res if f8 else 0) + 5 * n_att * lin
+    assert len(info['f8_shift']) == (2 * n_res + n_up if f8 else 0) + 5 * n_att * lin
     # every f8 GEMM reads an operand some producer wrote in the f8 image: same buffer reference
     f8_inputs = {o.u.gemm.a_ptr for o in ops if o.type == S.DS_OP_GEMM and o.u.gemm.f8} | \
                 {o.u.gemm.a2_ptr for o in ops if o.type == S.DS_OP_GEMM and o.u.gemm.f8 and o.u.gemm.a2_c}
