@@ -63,6 +63,13 @@ struct alignas(64) GemmKernelParams {
     // CTA-pair variant (gemm_tc_pair_kernel; appended so that the single-CTA kernel's parameter offsets stay put)
     CUtensorMap tmBh, tmB8h;             // B boxes of BN/2 rows: each CTA of a pair loads half of the N tile
     int pair;
+    // measurement only (DSB_GEMM_DIAG, profiles/bench_gemm_tiles.py --diag): 1 = no MMAs (operand feed alone), 2 = no TMA loads (MMA issue +
+    // epilogue alone), 4 = no epilogue work (accumulators are released unread).  Results are garbage in every mode but 0.
+    int diag;
+    // debug timeline (ds_debug_gemm_trace, profiles/gemm_timeline.py): CTA 0 stores clock64 per ring stage -- producer after its empty-slot
+    // wait in trace[it], MMA warp after its full-slot wait in trace[trace_cap / 2 + it]; NULL in normal runs
+    unsigned long long* trace;
+    int trace_cap;
 };
 
 struct SmemCtl {
@@ -298,6 +305,70 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const 
     }
 }
 
+// ------------------------------------------------------------------------------------------ TMA producer: the K loop of one tile
+// r02p/r02q finding (profiles/r02/gemm_feed_diagnosis.txt): with the stage index decoded per iteration (two integer divisions, dynamically
+// indexed parameter loads, a dozen R2UR moves) ONE producer iteration cost ~860 cycles of dependent single-warp latency -- more than the
+// MMAs of a stage (520 e4m3 / 690-780 fp16 cycles) -- so the ring never ran more than one stage ahead and every conv GEMM was bound by the
+// issue rate of its producer warp, not by L2, shared memory or the tensor pipe.  The loop nest below walks (pass, tap, channel block) with
+// running coordinates: no division, one parameter load per tap, everything else loop-invariant.
+struct RingPos {
+    int stage;
+    uint32_t phase;
+};
+
+template <bool PAIR>
+__device__ __forceinline__ void producer_tile(const GemmKernelParams& p, uint8_t* smem, SmemCtl* ctl, RingPos& r, const int stage_bytes,
+                                              const uint32_t tx_bytes, const bool arm, const int aw0, const int ah0, const int an0,
+                                              const int a_c_off, const int b_k_off, const int b_row, const int b_z, int& trace_n) {
+    const bool ldA = !(p.diag & (2 | 8)), ldB = !(p.diag & (2 | 16));
+    const bool tracing = p.trace && blockIdx.x == 0 && lane_id() == 0;
+    const CUtensorMap* const mB = PAIR ? &p.tmBh : &p.tmB;
+    const CUtensorMap* const mB8 = PAIR ? &p.tmB8h : &p.tmB8;
+    auto load = [&](const CUtensorMap* ma, int ac, int aw, int ah, int an, const CUtensorMap* mb, int bk, int bz) {
+        mbar_wait_warp(&ctl->empty[r.stage], r.phase ^ 1);
+        if (tracing && trace_n < p.trace_cap / 2) p.trace[trace_n++] = clock64();
+        uint8_t* sa = smem + r.stage * stage_bytes;
+        uint64_t* full = &ctl->full[r.stage];
+        if (elect_one()) {
+            if (arm) mbar_arrive_expect_tx(full, tx_bytes);
+            if (PAIR) {
+                if (ldA) tma_load_4d_pair(ma, full, sa, ac, aw, ah, an);
+                if (ldB) tma_load_3d_pair(mb, full, sa + kATileBytes, bk, b_row, bz);
+            } else {
+                if (ldA) tma_load_4d(ma, full, sa, ac, aw, ah, an);
+                if (ldB) tma_load_3d(mb, full, sa + kATileBytes, bk, b_row, bz);
+            }
+        }
+        __syncwarp();
+        if (++r.stage == p.num_stages) { r.stage = 0; r.phase ^= 1; }
+    };
+    if (p.f8) {
+        // e4m3 blocks (128 channels = one 128-byte swizzle row): A_lo8 x W_hi8 over all of K, then A_hi8 x W_lo8
+        for (int pass8 = 0; pass8 < 2; ++pass8) {
+            const int an8 = an0 + pass8 * p.a8_plane_n;
+            int bk = 0;
+            for (int tap = 0; tap < p.taps; ++tap) {
+                const int aw = aw0 + p.tap_dw[tap], ah = ah0 + p.tap_dh[tap];
+                for (int cb = 0; cb < p.cpb8; ++cb, bk += 128) load(&p.tmA8, cb * 128, aw, ah, an8, mB8, bk, pass8);
+            }
+            for (int j = 0; j < p.nkb8_aux; ++j, bk += 128) load(&p.tmA2_8, j * 128, aw0, ah0, an8, mB8, bk, pass8);
+        }
+    }
+    const int npass16 = p.f8 ? 1 : p.npass;                 // fp16 passes: hi x hi (, lo x hi, hi x lo)
+    for (int pass = 0; pass < npass16; ++pass) {
+        const int an = an0 + (pass == 1 ? p.a_plane_n : 0);
+        const int an2 = an0 + (pass == 1 ? p.a2_plane_n : 0);
+        const int bz = b_z + (pass == 2 ? p.b_plane_batch : 0);
+        int bk = b_k_off;
+        for (int tap = 0; tap < p.taps; ++tap) {
+            const int aw = aw0 + p.tap_dw[tap], ah = ah0 + p.tap_dh[tap];
+            const int ac0 = p.tap_cb[tap] + a_c_off;
+            for (int cb = 0; cb < p.cpb; ++cb, bk += 64) load(&p.tmA, ac0 + cb * 64, aw, ah, an, mB, bk, bz);
+        }
+        for (int j = 0; j < p.nkb_aux; ++j, bk += 64) load(&p.tmA2, j * 64, aw0, ah0, an2, mB, bk, bz);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle; the runtime only guarantees 16.
@@ -307,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    int trace_n = 0;
     const int nkb_total = p.nkb_main + p.nkb_aux;
     // f8 mode: 2 * nkb8 e4m3 blocks (A_lo8 x W_hi8, then A_hi8 x W_lo8; 128 channels each) followed by the nkb_total fp16 hi x hi blocks
     const int nkb8 = p.f8 ? p.nkb8_main + p.nkb8_aux : 0;
@@ -343,8 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (whole warp converged; the copies elected)
         {
-            int stage = 0;
-            uint32_t phase = 0;
+            RingPos ring{0, 0u};
+            const uint32_t tx_bytes = (p.diag & 2) ? 0u : (uint32_t)(((p.diag & 8) ? 0 : kATileBytes) + ((p.diag & 16) ? 0 : p.BN * 128));
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int z = tile / tiles_per_z;
                 const int t2 = tile - z * tiles_per_z;
@@ -354,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 int aw0, ah0, an0;
                 if (p.a_mode == 0) {
                     const int HW = p.conv_H * p.conv_W;
-                    const int p0 = mt * 128;
+                    const int p0 = (p.diag & 64) ? 0 : mt * 128;
                     an0 = p0 / HW;
                     ah0 = (p0 - an0 * HW) / p.conv_W;
                     aw0 = 0;
@@ -367,48 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const int b_k_off = p.b_k0 + zh * p.b_k_per_zh;
                 const int b_row = nt * p.BN + zh * p.b_row_per_zh;
                 const int b_z = zb * p.b_z_per_zb + zh * p.b_z_per_zh;
-                for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait_warp(&ctl->empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * stage_bytes;
-                    uint8_t* sb = sa + kATileBytes;
-                    __syncwarp();
-                    const bool leader = elect_one();
-                    if (leader) mbar_arrive_expect_tx(&ctl->full[stage], (uint32_t)stage_bytes);
-                    if (it < 2 * nkb8) {
-                        // e4m3 block: 128 channels = one 128-byte swizzle row, same tile bytes as an fp16 block
-                        const int pass8 = it >= nkb8 ? 1 : 0;
-                        const int kb = it - pass8 * nkb8;
-                        const int an8 = an0 + pass8 * p.a8_plane_n;
-                        if (kb < p.nkb8_main) {
-                            const int tap = kb / p.cpb8;
-                            const int c0 = (kb - tap * p.cpb8) * 128;
-                            if (leader) tma_load_4d(&p.tmA8, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an8);
-                        } else {
-                            if (leader) tma_load_4d(&p.tmA2_8, &ctl->full[stage], sa, (kb - p.nkb8_main) * 128, aw0, ah0, an8);
-                        }
-                        if (leader) tma_load_3d(&p.tmB8, &ctl->full[stage], sb, kb * 128, b_row, pass8);
-                        __syncwarp();
-                        if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
-                        continue;
-                    }
-                    const int it16 = it - 2 * nkb8;
-                    const int pass = it16 / nkb_total;
-                    const int kb = it16 - pass * nkb_total;
-                    const int pa = (pass == 1) ? 1 : 0;
-                    const int pb = (pass == 2) ? 1 : 0;
-                    if (kb < p.nkb_main) {
-                        const int tap = kb / p.cpb;
-                        const int c0 = (kb - tap * p.cpb) * 64 + p.tap_cb[tap];
-                        const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
-                        if (leader) tma_load_4d(&p.tmA, &ctl->full[stage], sa, c0 + a_c_off, aw0 + dw, ah0 + dh, an0 + pa * p.a_plane_n);
-                    } else {
-                        const int c0 = (kb - p.nkb_main) * 64;
-                        if (leader) tma_load_4d(&p.tmA2, &ctl->full[stage], sa, c0, aw0, ah0, an0 + pa * p.a2_plane_n);
-                    }
-                    if (leader) tma_load_3d(&p.tmB, &ctl->full[stage], sb, kb * 64 + b_k_off, b_row, b_z + pb * p.b_plane_batch);
-                    __syncwarp();
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
-                }
+                producer_tile<false>(p, smem, ctl, ring, stage_bytes, tx_bytes, true, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
             }
         }
     } else if (warp == 1) {
@@ -426,6 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int it = 0; it < n_iters; ++it) {
                     mbar_wait_warp(&ctl->full[stage], phase);
+                    if (p.trace && blockIdx.x == 0 && lane == 0 && trace_n < p.trace_cap / 2) p.trace[p.trace_cap / 2 + trace_n++] = clock64();
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + kATileBytes;
@@ -433,7 +465,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     const uint64_t db = umma_desc_sw128(sb);
                     __syncwarp();
                     if (elect_one()) {
-                        if (it < 2 * nkb8) {
+                        if (p.diag & 1) {
+                        } else if (it < 2 * nkb8) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k)      // 32 e4m3 = 32 bytes per MMA: the same +2 descriptor step as 16 fp16
                                 umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
@@ -479,8 +512,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int q = 0; q < 8; ++q) res_next[q] = *reinterpret_cast<const float4*>(res_row + cc + 4 * q);
                 }
             };
-            prefetch(0);
-            int c = 0;
+            if (!(p.diag & 4)) prefetch(0);
+            int c = (p.diag & 4) ? p.BN : 0;
             for (; c + 32 <= p.BN; c += 32) {
                 float4 res_cur[8];
 #pragma unroll
@@ -530,6 +563,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    int trace_n = 0;
     const int rank = (int)cluster_ctarank();
     const int nkb_total = p.nkb_main + p.nkb_aux;
     const int nkb8 = p.f8 ? p.nkb8_main + p.nkb8_aux : 0;
@@ -567,8 +601,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs; warp converged, copies elected)
         {
-            int stage = 0;
-            uint32_t phase = 0;
+            RingPos ring{0, 0u};
+            // the leader's full barrier collects both CTAs' bytes
+            const uint32_t tx_bytes = (p.diag & 2) ? 0u : 2u * (uint32_t)(((p.diag & 8) ? 0 : kATileBytes) + ((p.diag & 16) ? 0 : half_bn * 128));
             for (int tile = first; tile < total_tiles; tile += step) {
                 const int pm = tile / p.n_tiles;
                 const int nt = tile - pm * p.n_tiles;
@@ -576,49 +611,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 // 128 consecutive NHWC pixels: whole image rows (W <= 128, box (64, W, 128/W.., ..)) or a 128-pixel segment of one row
                 // (W a multiple of 128 > 128, box (64, 128, 1, 1): the first-stage decoder's 256- and 512-wide layers)
                 const int HW = p.conv_H * p.conv_W;
-                const int p0 = mt * 128;
+                const int p0 = (p.diag & 64) ? rank * 128 : mt * 128;
                 const int an0 = p0 / HW;
                 const int rem = p0 - an0 * HW;
                 const int ah0 = rem / p.conv_W;
                 const int aw0 = rem - ah0 * p.conv_W;
                 const int b_row = nt * p.BN + rank * half_bn;
-                for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait_warp(&ctl->empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * stage_bytes;
-                    uint8_t* sb = sa + kATileBytes;
-                    __syncwarp();
-                    const bool leader = elect_one();
-                    if (leader && rank == 0) mbar_arrive_expect_tx(&ctl->full[stage], 2u * (uint32_t)stage_bytes);
-                    if (it < 2 * nkb8) {
-                        const int pass8 = it >= nkb8 ? 1 : 0;
-                        const int kb = it - pass8 * nkb8;
-                        const int an8 = an0 + pass8 * p.a8_plane_n;
-                        if (kb < p.nkb8_main) {
-                            const int tap = kb / p.cpb8;
-                            const int c0 = (kb - tap * p.cpb8) * 128;
-                            if (leader) tma_load_4d_pair(&p.tmA8, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an8);
-                        } else {
-                            if (leader) tma_load_4d_pair(&p.tmA2_8, &ctl->full[stage], sa, (kb - p.nkb8_main) * 128, aw0, ah0, an8);
-                        }
-                        if (leader) tma_load_3d_pair(&p.tmB8h, &ctl->full[stage], sb, kb * 128, b_row, pass8);
-                    } else {
-                        const int it16 = it - 2 * nkb8;
-                        const int pass = it16 / nkb_total;
-                        const int kb = it16 - pass * nkb_total;
-                        const int pa = (pass == 1) ? 1 : 0;
-                        const int pb = (pass == 2) ? 1 : 0;
-                        if (kb < p.nkb_main) {
-                            const int tap = kb / p.cpb;
-                            const int c0 = (kb - tap * p.cpb) * 64;
-                            if (leader) tma_load_4d_pair(&p.tmA, &ctl->full[stage], sa, c0, aw0 + p.tap_dw[tap], ah0 + p.tap_dh[tap], an0 + pa * p.a_plane_n);
-                        } else {
-                            if (leader) tma_load_4d_pair(&p.tmA2, &ctl->full[stage], sa, (kb - p.nkb_main) * 64, aw0, ah0, an0 + pa * p.a2_plane_n);
-                        }
-                        if (leader) tma_load_3d_pair(&p.tmBh, &ctl->full[stage], sb, kb * 64, b_row, pb * p.b_plane_batch);
-                    }
-                    __syncwarp();
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
-                }
+                producer_tile<true>(p, smem, ctl, ring, stage_bytes, tx_bytes, rank == 0, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
             }
         }
     } else if (warp == 1) {
@@ -636,6 +635,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int it = 0; it < n_iters; ++it) {
                     mbar_wait_warp(&ctl->full[stage], phase);
+                    if (p.trace && blockIdx.x == 0 && lane == 0 && trace_n < p.trace_cap / 2) p.trace[p.trace_cap / 2 + trace_n++] = clock64();
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * stage_bytes);
                     const uint32_t sb = sa + kATileBytes;
@@ -643,7 +643,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                     const uint64_t db = umma_desc_sw128(sb);
                     __syncwarp();
                     if (elect_one()) {
-                        if (it < 2 * nkb8) {
+                        if (p.diag & 1) {
+                        } else if (it < 2 * nkb8) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
                         } else {
@@ -682,8 +683,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                     for (int q = 0; q < 8; ++q) res_next[q] = *reinterpret_cast<const float4*>(res_row + cc + 4 * q);
                 }
             };
-            prefetch(0);
-            int c = 0;
+            if (!(p.diag & 4)) prefetch(0);
+            int c = (p.diag & 4) ? p.BN : 0;
             for (; c + 32 <= p.BN; c += 32) {
                 float4 res_cur[8];
 #pragma unroll
@@ -745,6 +746,9 @@ static int encode_map_typed(CUtensorMap* m, const void* ptr, int rank, const int
     }
     return 0;
 }
+
+static unsigned long long* g_trace_buf = nullptr;
+static int g_trace_cap = 0;
 
 static bool all_tap_cb_zero(const ds_gemm_desc* d) {
     for (int t = 0; t < 9; ++t) if (d->tap_cb[t]) return false;
@@ -822,6 +826,9 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
         if (encode_map_typed(&kp->tmB8, b8, 3, bd8, bs8, bbox8, true)) return -19;
     }
     for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = d->tap_dh[t]; kp->tap_dw[t] = d->tap_dw[t]; kp->tap_cb[t] = d->tap_cb[t]; }
+    { const char* e = getenv("DSB_GEMM_DIAG"); kp->diag = e ? atoi(e) : 0; }
+    kp->trace = g_trace_buf; kp->trace_cap = g_trace_cap;
+    if (kp->diag & 32) for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = 0; kp->tap_dw[t] = 0; }      // every tap reads the unshifted box
     if (d->taps != 1 && d->taps != 9) return -15;
     // image rows wider than one M tile are only handled by the pair kernel's tile -> (w, h, n) mapping
     if (d->a_mode == 0 && d->conv_W > 128 && !((d->f8 & 2) && d->BN % 32 == 0 && d->num_z == 1 && d->conv_W % 128 == 0)) return -13;
@@ -852,9 +859,12 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     }
     int ns = (227 * 1024 - 2048) / stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;
+    { const char* e = getenv("DSB_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < ns) ns = atoi(e); }      // measurement only
     kp->num_stages = ns;
     return 0;
 }
+
+void gemm_set_trace(unsigned long long* buf, int cap) { g_trace_buf = buf; g_trace_cap = cap; }
 
 size_t gemm_params_size() { return sizeof(GemmKernelParams); }
 void gemm_patch_edm(GemmKernelParams* kp, const float* x, float* D) { kp->edm_x = x; kp->edm_D = D; }
@@ -898,6 +908,11 @@ int gemm_run(const GemmKernelParams* kp, cudaStream_t stream) {
 }
 
 }  // namespace dsb
+
+extern "C" int ds_debug_gemm_trace(unsigned long long* dev_buf, int capacity) {
+    dsb::gemm_set_trace(dev_buf, dev_buf ? capacity : 0);
+    return 0;
+}
 
 extern "C" int ds_gemm_launch(const ds_gemm_desc* d, cudaStream_t stream) {
     dsb::GemmKernelParams kp;

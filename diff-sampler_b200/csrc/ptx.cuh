@@ -13,7 +13,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 __device__ __forceinline__ uint32_t lane_id() {
     uint32_t l;
-    asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+    asm("mov.u32 %0, %%laneid;" : "=r"(l));          // not volatile: the lane id is loop-invariant, let the compiler hoist it
     return l;
 }
 

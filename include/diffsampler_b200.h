@@ -118,6 +118,10 @@ int ds_images_to_uint8(const float* images, unsigned char* out, int B, int C, in
  * (tag << 40 | clock) events of its TMA / MMA / softmax roles for its first two tiles into dev_buf[1..capacity) (dev_buf[0] = count,
  * zeroed by the caller).  NULL switches it off.  Not part of the sampling path. */
 int ds_debug_attn_trace(unsigned long long* dev_buf, int capacity);
+/* Debug timeline of the conv / GEMM kernels (profiles/gemm_timeline.py): GEMM launches BUILT after this call make CTA 0 store clock64 per
+ * shared-memory ring stage: the TMA producer after its empty-slot wait in dev_buf[i], the MMA warp after its full-slot wait in
+ * dev_buf[capacity / 2 + i], i < capacity / 2.  NULL switches it off.  Not part of the sampling path. */
+int ds_debug_gemm_trace(unsigned long long* dev_buf, int capacity);
 
 /* ---- kernel-level entry points (used by the parity tests and micro-benchmarks) ------------------
  * `desc` points to the matching struct of csrc/ops.h with absolute device pointers. */

@@ -6,6 +6,7 @@ executed TFLOP/s, for fp16x3 and the f8 mode, single-CTA and CTA-pair kernels.  
 """
 import sys
 import os
+import time
 
 import torch
 
@@ -24,7 +25,24 @@ SHAPES = [  # (label, Bn, H, W, Cin, Cout)
 ]
 
 
+_nvml = None
+LAST_MHZ = 0
+
+
+def sm_mhz():
+    global _nvml
+    try:
+        import pynvml
+        if _nvml is None:
+            pynvml.nvmlInit()
+            _nvml = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+        return pynvml.nvmlDeviceGetClockInfo(_nvml, pynvml.NVML_CLOCK_SM)
+    except Exception:
+        return 0
+
+
 def timed(d, n):
+    global LAST_MHZ
     _lib.op_launch(d)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -32,7 +50,12 @@ def timed(d, n):
     for _ in range(n):
         _lib.op_launch(d)
     e1.record()
+    clocks = []
+    while not e1.query():                      # SM clock while the launches drain (power cap: the clock under THIS kernel's load)
+        clocks.append(sm_mhz())
+        time.sleep(0.01)
     torch.cuda.synchronize()
+    LAST_MHZ = sorted(clocks)[len(clocks) // 2] if clocks else 0
     return e0.elapsed_time(e1) / n
 
 
@@ -43,6 +66,8 @@ def main():
     ap.add_argument('--bn', type=int, default=0, help='only this N tile')
     ap.add_argument('--mode', default='', help='x3 | f8 (default both)')
     ap.add_argument('--reps', type=int, default=0, help='fixed number of timed launches (default: ~0.25 s worth)')
+    ap.add_argument('--diag', default='0', help='comma list of DSB_GEMM_DIAG modes (1 = no MMA, 2 = no TMA loads, 4 = no epilogue; sums allowed): '
+                                                 'which of operand feed / MMA issue / epilogue bounds the kernel')
     args = ap.parse_args()
     _lib.load()
     torch.manual_seed(0)
@@ -76,17 +101,22 @@ def main():
                 for pair in (False, True):
                     if pair and (bn % 32 or m_tiles < 2):
                         continue
-                    try:
-                        d, _ = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=taps, npass=3, out_f32=out.data_ptr(), bn=bn, pair=pair, **kw)
-                        n = max(20, int(0.25 / max(flops * (2 if f8 else 3) / 1.2e15, 1e-5)))     # ~0.25 s of launches
-                        ms = timed(d, args.reps if args.reps else min(n, 2000))
-                    except Exception as e:
-                        print(f'{label:24s} {"f8 " if f8 else "x3 "} BN={bn:3d} pair={int(pair)}  FAILED {e!r}'[:160])
-                        continue
-                    tiles = m_tiles * -(-Cout // bn)
-                    mark = ' <- fill_bn' if bn == auto_bn else ''
-                    print(f'{label:24s} {"f8 " if f8 else "x3 "} BN={bn:3d} pair={int(pair)} tiles={tiles:6d} ({tiles / 148:6.2f}/SM)  {ms * 1e3:9.1f} us  '
-                          f'{flops / ms / 1e9:7.1f} TF/s algorithmic  {flops * (2 if f8 else 3) / ms / 1e9:7.1f} executed{mark}', flush=True)
+                    for diag in args.diag.split(','):
+                        os.environ['DSB_GEMM_DIAG'] = diag
+                        try:
+                            d, _ = G.conv_gemm(xa.data_ptr(), Bn, H, W, Cin, wp.data_ptr(), Cout, taps=taps, npass=3, out_f32=out.data_ptr(), bn=bn, pair=pair, **kw)
+                            n = max(20, int(0.25 / max(flops * (2 if f8 else 3) / 1.2e15, 1e-5)))     # ~0.25 s of launches
+                            ms = timed(d, args.reps if args.reps else min(n, 2000))
+                        except Exception as e:
+                            print(f'{label:24s} {"f8 " if f8 else "x3 "} BN={bn:3d} pair={int(pair)}  FAILED {e!r}'[:160])
+                            continue
+                        tiles = m_tiles * -(-Cout // bn)
+                        mark = ' <- fill_bn' if bn == auto_bn else ''
+                        if diag != '0':
+                            mark += f'  [diag {diag}: ' + '+'.join(n_ for b_, n_ in ((1, 'no MMA'), (2, 'no TMA'), (4, 'no epilogue')) if int(diag) & b_) + ']'
+                        print(f'{label:24s} {"f8 " if f8 else "x3 "} BN={bn:3d} pair={int(pair)} tiles={tiles:6d} ({tiles / 148:6.2f}/SM)  {ms * 1e3:9.1f} us  '
+                              f'{flops / ms / 1e9:7.1f} TF/s algorithmic  {flops * (2 if f8 else 3) / ms / 1e9:7.1f} executed  {LAST_MHZ:4d} MHz{mark}', flush=True)
+                    os.environ['DSB_GEMM_DIAG'] = '0'
         del x, out
         torch.cuda.empty_cache()
 
