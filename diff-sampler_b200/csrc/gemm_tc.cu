@@ -23,7 +23,7 @@ namespace dsb {
 
 static constexpr int kMaxStages = 8;
 static constexpr int kATileBytes = 128 * 128;   // 128 rows x 64 fp16
-static constexpr int kThreads = 192;
+static constexpr int kThreads = 224;           // warp 0: A producer, 1: MMA issuer, 2..5: epilogue, 6: B producer
 
 struct alignas(64) GemmKernelParams {
     CUtensorMap tmA, tmA2, tmB;
@@ -316,12 +316,15 @@ struct RingPos {
     uint32_t phase;
 };
 
-template <bool PAIR>
+// Two producer warps walk the same loop nest: WHICH = 1 issues the A boxes (warp 0), WHICH = 2 the B boxes (warp 6); each arms the stage's
+// full barrier (count 2) with its own bytes.  Halves the dependent instruction chain per stage of either warp (r02r: one warp issuing both
+// copies needed ~515 cycles per stage, as long as the four e4m3 MMAs of a stage).
+template <bool PAIR, int WHICH>
 __device__ __forceinline__ void producer_tile(const GemmKernelParams& p, uint8_t* smem, SmemCtl* ctl, RingPos& r, const int stage_bytes,
                                               const uint32_t tx_bytes, const bool arm, const int aw0, const int ah0, const int an0,
                                               const int a_c_off, const int b_k_off, const int b_row, const int b_z, int& trace_n) {
-    const bool ldA = !(p.diag & (2 | 8)), ldB = !(p.diag & (2 | 16));
-    const bool tracing = p.trace && blockIdx.x == 0 && lane_id() == 0;
+    const bool ldA = (WHICH & 1) && !(p.diag & (2 | 8)), ldB = (WHICH & 2) && !(p.diag & (2 | 16));
+    const bool tracing = (WHICH & 1) && p.trace && blockIdx.x == 0 && lane_id() == 0;
     const CUtensorMap* const mB = PAIR ? &p.tmBh : &p.tmB;
     const CUtensorMap* const mB8 = PAIR ? &p.tmB8h : &p.tmB8;
     auto load = [&](const CUtensorMap* ma, int ac, int aw, int ah, int an, const CUtensorMap* mb, int bk, int bz) {
@@ -396,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (p.nkb8_aux) tma_prefetch_desc(&p.tmA2_8);
         }
         for (int s = 0; s < p.num_stages; ++s) {
-            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->full[s], 2);                                  // the A and the B producer warp
             mbar_init(&ctl->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -412,11 +415,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (whole warp converged; the copies elected)
+    if (warp == 0 || warp == 6) {
+        // ------------------------------------------------------------------ TMA producers (warp 0: A boxes, warp 6: B boxes; converged, copies elected)
         {
             RingPos ring{0, 0u};
-            const uint32_t tx_bytes = (p.diag & 2) ? 0u : (uint32_t)(((p.diag & 8) ? 0 : kATileBytes) + ((p.diag & 16) ? 0 : p.BN * 128));
+            const uint32_t tx_bytes = (p.diag & 2) ? 0u : (warp == 0 ? ((p.diag & 8) ? 0u : (uint32_t)kATileBytes) : ((p.diag & 16) ? 0u : (uint32_t)(p.BN * 128)));
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int z = tile / tiles_per_z;
                 const int t2 = tile - z * tiles_per_z;
@@ -439,7 +442,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const int b_k_off = p.b_k0 + zh * p.b_k_per_zh;
                 const int b_row = nt * p.BN + zh * p.b_row_per_zh;
                 const int b_z = zb * p.b_z_per_zb + zh * p.b_z_per_zh;
-                producer_tile<false>(p, smem, ctl, ring, stage_bytes, tx_bytes, true, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
+                if (warp == 0) producer_tile<false, 1>(p, smem, ctl, ring, stage_bytes, tx_bytes, true, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
+                else producer_tile<false, 2>(p, smem, ctl, ring, stage_bytes, tx_bytes, true, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
             }
         }
     } else if (warp == 1) {
@@ -582,7 +586,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
             if (p.nkb8_aux) tma_prefetch_desc(&p.tmA2_8);
         }
         for (int s = 0; s < p.num_stages; ++s) {
-            mbar_init(&ctl->full[s], 1);
+            mbar_init(&ctl->full[s], 2);                                  // the leader's A and B producer warps (arming both CTAs' bytes)
             mbar_init(&ctl->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -598,12 +602,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer (both CTAs; warp converged, copies elected)
+    if (warp == 0 || warp == 6) {
+        // ------------------------------------------------------------------ TMA producers (both CTAs; warp 0: A boxes, warp 6: B boxes)
         {
             RingPos ring{0, 0u};
             // the leader's full barrier collects both CTAs' bytes
-            const uint32_t tx_bytes = (p.diag & 2) ? 0u : 2u * (uint32_t)(((p.diag & 8) ? 0 : kATileBytes) + ((p.diag & 16) ? 0 : half_bn * 128));
+            const uint32_t tx_bytes = (p.diag & 2) ? 0u : 2u * (warp == 0 ? ((p.diag & 8) ? 0u : (uint32_t)kATileBytes) : ((p.diag & 16) ? 0u : (uint32_t)(half_bn * 128)));
             for (int tile = first; tile < total_tiles; tile += step) {
                 const int pm = tile / p.n_tiles;
                 const int nt = tile - pm * p.n_tiles;
@@ -617,7 +621,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 const int ah0 = rem / p.conv_W;
                 const int aw0 = rem - ah0 * p.conv_W;
                 const int b_row = nt * p.BN + rank * half_bn;
-                producer_tile<true>(p, smem, ctl, ring, stage_bytes, tx_bytes, rank == 0, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
+                if (warp == 0) producer_tile<true, 1>(p, smem, ctl, ring, stage_bytes, tx_bytes, rank == 0, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
+                else producer_tile<true, 2>(p, smem, ctl, ring, stage_bytes, tx_bytes, rank == 0, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
             }
         }
     } else if (warp == 1) {
@@ -841,7 +846,11 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     // power-capped sustained bench (profiles/r02b: 513.2 vs 499.0): a third fewer operand bytes through L2 / shared memory per FLOP.
     static const int pair_env = [] { const char* e = getenv("DSB_GEMM_2CTA"); return e ? atoi(e) : 1; }();
     const bool pair_forced = (d->f8 & 2) != 0;          // bit 1 of ds_gemm_desc.f8: request the pair kernel for this launch (tests, A/B)
-    if ((pair_forced || (pair_env && d->m_tiles >= 4 * 148 && d->BN >= 64)) && d->a_mode == 0 && d->num_z == 1 && d->BN % 32 == 0 &&
+    // since the producer rewrite (r02r) the pair kernel runs at the MMA instruction bound (600 cycles per stage) while the single-CTA kernel
+    // is shared-memory-port bound (770): the pair wins 12-16 % on every shape that still gives each SM pair a tile
+    static const int pair_min_tiles = [] { const char* e = getenv("DSB_GEMM_2CTA_MIN_PAIR_TILES"); return e ? atoi(e) : 74; }();
+    const bool pair_auto = pair_env && ((d->m_tiles + 1) / 2) * d->n_tiles >= pair_min_tiles && d->BN >= 64;
+    if ((pair_forced || pair_auto) && d->a_mode == 0 && d->num_z == 1 && d->b_k0 == 0 && d->BN % 32 == 0 &&
         all_tap_cb_zero(d)) {
         int32_t hbox[3] = {64, d->BN / 2, 1};
         if (encode_map(&kp->tmBh, d->b_ptr, 3, d->b_dims, d->b_strides, hbox)) return -30;
