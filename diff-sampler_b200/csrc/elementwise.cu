@@ -454,32 +454,37 @@ __global__ void __launch_bounds__(256, 3) gn_apply_v3_kernel(ds_gn_apply_desc d,
     else { base0 = d.src1; pitch = d.C1; cc = c - d.C0; }
     __half* oact = reinterpret_cast<__half*>(d.out_act);
     __half* oraw = reinterpret_cast<__half*>(d.out_raw);
-    long long u = total_units * blockIdx.x / gridDim.x;
-    const long long u_end = total_units * (blockIdx.x + 1) / gridDim.x;
+    // r02s: with one contiguous range per CTA (round-2 v3) the 444 CTAs streamed through 444 x (2 sources + up to 5 output planes) distant
+    // 2 MB pages at once and the 3.2 GB concat layers (512 channels, 32x32, act + raw outputs) ran at 2.8 TB/s against 5.3 TB/s for the
+    // 1 GB layers.  Now the grid sweeps the tensor together: chunks of kChunk units (>= 8 pixel rows, never crossing a sample) are dealt
+    // round-robin, so at any time all CTAs work inside one ~30 MB window per stream; the coefficients are refetched only when the sample
+    // changes.
+    constexpr int kChunk = 8;
+    const int chunks_per_sample = (units_per_sample + kChunk - 1) / kChunk;
+    const long long total_chunks = (long long)chunks_per_sample * d.B;
     float a[8], b[8];
-    while (u < u_end) {
-        const int n = (int)(u / units_per_sample);
-        const int uin = (int)(u - (long long)n * units_per_sample);
-        long long seg_end = (long long)(n + 1) * units_per_sample;
-        if (seg_end > u_end) seg_end = u_end;
-        const int nun = (int)(seg_end - u);
-        {
+    int n_prev = -1;
+    for (long long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+        const int n = (int)(ch / chunks_per_sample);
+        const int uin = ((int)(ch - (long long)n * chunks_per_sample)) * kChunk;
+        const int nun = min(kChunk, units_per_sample - uin);
+        if (n != n_prev) {
             const float4* cf = reinterpret_cast<const float4*>(d.coef + ((long long)n * C + c) * 2);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float4 t = __ldg(cf + j);
                 a[2 * j] = t.x; b[2 * j] = t.y; a[2 * j + 1] = t.z; b[2 * j + 1] = t.w;
             }
+            n_prev = n;
         }
         const float* base = base0 + (long long)n * npix * pitch + cc;
-        int po = uin * rows + prow;                      // pixel of this thread in the first unit of the segment
+        int po = uin * rows + prow;                      // pixel of this thread in the first unit of the chunk
         int k = 0;
         // whole units only: the last unit of a sample may be partial when rows does not divide H*W
         const int full = ((uin + nun) * rows <= npix) ? nun : nun - 1;
         for (; k + 4 <= full; k += 4, po += 4 * rows) gn_v2_pixels<4>(d, base, pitch, n, npix, C, c, plane, po, rows, true, a, b, oact, oraw);
         for (; k < full; ++k, po += rows) gn_v2_pixels<1>(d, base, pitch, n, npix, C, c, plane, po, rows, true, a, b, oact, oraw);
         if (k < nun && po < npix) gn_v2_pixels<1>(d, base, pitch, n, npix, C, c, plane, po, rows, true, a, b, oact, oraw);
-        u = seg_end;
     }
 }
 
@@ -990,8 +995,8 @@ extern "C" int ds_gn_apply_launch(const ds_gn_apply_desc* d, cudaStream_t stream
         const int ups = (npix + rows - 1) / rows;
         const long long total_units = (long long)ups * d->B;
         long long g3 = (long long)sms[dev] * occ[dev][slot];
-        const long long min_units = 8;                        // at least ~8 pixel rows per CTA
-        if (g3 > (total_units + min_units - 1) / min_units) g3 = (total_units + min_units - 1) / min_units;
+        const long long total_chunks = (long long)((ups + 7) / 8) * d->B;        // kChunk = 8 units per chunk (gn_apply_v3_kernel)
+        if (g3 > total_chunks) g3 = total_chunks;
         if (g3 < 1) g3 = 1;
         gn_apply_v3_kernel<<<(unsigned)g3, threads, 0, stream>>>(*d, nc8, rows, ups, total_units);
         return ok();
