@@ -70,6 +70,9 @@ struct alignas(64) GemmKernelParams {
     // wait in trace[it], MMA warp after its full-slot wait in trace[trace_cap / 2 + it]; NULL in normal runs
     unsigned long long* trace;
     int trace_cap;
+    // K blocks per ring stage (1 or 2): one empty/full barrier round trip, one expect_tx and one tcgen05.commit per `grp` 64-channel blocks.
+    // The role warps' per-stage instruction chains (~500-600 cycles each, r02s/r02t) were longer than the MMAs of a stage whenever BN < 256.
+    int grp;
 };
 
 struct SmemCtl {
@@ -320,20 +323,25 @@ struct RingPos {
 // full barrier (count 2) with its own bytes.  Halves the dependent instruction chain per stage of either warp (r02r: one warp issuing both
 // copies needed ~515 cycles per stage, as long as the four e4m3 MMAs of a stage).
 template <bool PAIR, int WHICH>
-__device__ __forceinline__ void producer_tile(const GemmKernelParams& p, uint8_t* smem, SmemCtl* ctl, RingPos& r, const int stage_bytes,
-                                              const uint32_t tx_bytes, const bool arm, const int aw0, const int ah0, const int an0,
-                                              const int a_c_off, const int b_k_off, const int b_row, const int b_z, int& trace_n) {
+__device__ __forceinline__ void producer_tile(const GemmKernelParams& p, uint8_t* smem, SmemCtl* ctl, RingPos& r, const int block_bytes,
+                                              const uint32_t tx_bytes, const bool arm, const int n_blocks, const int aw0, const int ah0,
+                                              const int an0, const int a_c_off, const int b_k_off, const int b_row, const int b_z, int& trace_n) {
     const bool ldA = (WHICH & 1) && !(p.diag & (2 | 8)), ldB = (WHICH & 2) && !(p.diag & (2 | 16));
     const bool tracing = (WHICH & 1) && p.trace && blockIdx.x == 0 && lane_id() == 0;
     const CUtensorMap* const mB = PAIR ? &p.tmBh : &p.tmB;
     const CUtensorMap* const mB8 = PAIR ? &p.tmB8h : &p.tmB8;
+    const int grp = p.grp;
+    const int stage_bytes = grp * block_bytes;
+    int sub = 0, left = n_blocks;                           // block inside the current stage; blocks of this tile not yet issued
     auto load = [&](const CUtensorMap* ma, int ac, int aw, int ah, int an, const CUtensorMap* mb, int bk, int bz) {
-        mbar_wait_warp(&ctl->empty[r.stage], r.phase ^ 1);
-        if (tracing && trace_n < p.trace_cap / 2) p.trace[trace_n++] = clock64();
-        uint8_t* sa = smem + r.stage * stage_bytes;
+        if (sub == 0) {
+            mbar_wait_warp(&ctl->empty[r.stage], r.phase ^ 1);
+            if (tracing && trace_n < p.trace_cap / 2) p.trace[trace_n++] = clock64();
+        }
+        uint8_t* sa = smem + r.stage * stage_bytes + sub * block_bytes;
         uint64_t* full = &ctl->full[r.stage];
         if (elect_one()) {
-            if (arm) mbar_arrive_expect_tx(full, tx_bytes);
+            if (arm && sub == 0) mbar_arrive_expect_tx(full, tx_bytes * (uint32_t)min(grp, left));
             if (PAIR) {
                 if (ldA) tma_load_4d_pair(ma, full, sa, ac, aw, ah, an);
                 if (ldB) tma_load_3d_pair(mb, full, sa + kATileBytes, bk, b_row, bz);
@@ -343,7 +351,11 @@ __device__ __forceinline__ void producer_tile(const GemmKernelParams& p, uint8_t
             }
         }
         __syncwarp();
-        if (++r.stage == p.num_stages) { r.stage = 0; r.phase ^= 1; }
+        --left;
+        if (++sub == grp || left == 0) {
+            sub = 0;
+            if (++r.stage == p.num_stages) { r.stage = 0; r.phase ^= 1; }
+        }
     };
     if (p.f8) {
         // e4m3 blocks (128 channels = one 128-byte swizzle row): A_lo8 x W_hi8 over all of K, then A_hi8 x W_lo8
@@ -372,12 +384,62 @@ __device__ __forceinline__ void producer_tile(const GemmKernelParams& p, uint8_t
     }
 }
 
+// ------------------------------------------------------------------------------------------ MMA issuer: the K loop of one tile
+// Whole warp converged, tcgen05 instructions elected.  One full-barrier wait and one commit per ring stage of p.grp K blocks.
+template <bool PAIR>
+__device__ __forceinline__ void mma_tile(const GemmKernelParams& p, uint8_t* smem, SmemCtl* ctl, RingPos& r, const int block_bytes,
+                                         const int n_iters, const int nkb8x2, const uint32_t idesc, const uint32_t d_tmem,
+                                         uint64_t* tmem_full_bar, int& trace_n) {
+    const int grp = p.grp;
+    const int stage_bytes = grp * block_bytes;
+    const bool tracing = p.trace && blockIdx.x == 0 && lane_id() == 0;
+    for (int it = 0; it < n_iters; it += grp) {
+        mbar_wait_warp(&ctl->full[r.stage], r.phase);
+        if (tracing && trace_n < p.trace_cap / 2) p.trace[p.trace_cap / 2 + trace_n++] = clock64();
+        tc_fence_after();
+        const uint32_t s0 = smem_u32(smem + r.stage * stage_bytes);
+        const int nb = min(grp, n_iters - it);
+        if (elect_one()) {
+            if (!(p.diag & 1)) {
+                for (int j = 0; j < nb; ++j) {
+                    const uint32_t sa = s0 + j * block_bytes;
+                    const uint64_t da = umma_desc_sw128(sa);
+                    const uint64_t db = umma_desc_sw128(sa + kATileBytes);
+                    const uint32_t acc0 = (it + j) > 0 ? 1u : 0u;
+                    if (it + j < nkb8x2) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {       // 32 e4m3 = 32 bytes per MMA: the same +2 descriptor step (16-byte units) as 16 fp16
+                            if (PAIR) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                            else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (PAIR) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                            else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                        }
+                    }
+                }
+            }
+            if (PAIR) {
+                umma_commit_pair(&ctl->empty[r.stage]);                   // frees this stage in both CTAs
+                if (it + nb >= n_iters) umma_commit_pair(tmem_full_bar);
+            } else {
+                umma_commit(&ctl->empty[r.stage]);
+                if (it + nb >= n_iters) umma_commit(tmem_full_bar);
+            }
+        }
+        __syncwarp();
+        if (++r.stage == p.num_stages) { r.stage = 0; r.phase ^= 1; }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmKernelParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle; the runtime only guarantees 16.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_bytes = kATileBytes + p.BN * 128;
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.num_stages * stage_bytes);
+    const int block_bytes = kATileBytes + p.BN * 128;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.num_stages * p.grp * block_bytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -442,51 +504,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const int b_k_off = p.b_k0 + zh * p.b_k_per_zh;
                 const int b_row = nt * p.BN + zh * p.b_row_per_zh;
                 const int b_z = zb * p.b_z_per_zb + zh * p.b_z_per_zh;
-                if (warp == 0) producer_tile<false, 1>(p, smem, ctl, ring, stage_bytes, tx_bytes, true, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
-                else producer_tile<false, 2>(p, smem, ctl, ring, stage_bytes, tx_bytes, true, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
+                if (warp == 0) producer_tile<false, 1>(p, smem, ctl, ring, block_bytes, tx_bytes, true, n_iters, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
+                else producer_tile<false, 2>(p, smem, ctl, ring, block_bytes, tx_bytes, true, n_iters, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (whole warp converged; tcgen05 instructions elected)
         {
             const uint32_t idesc = umma_idesc_f16((uint32_t)p.BN);
-            int stage = 0;
-            uint32_t phase = 0;
+            RingPos ring{0, 0u};
             int iter = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
                 mbar_wait_warp(&ctl->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * 256;
-                for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait_warp(&ctl->full[stage], phase);
-                    if (p.trace && blockIdx.x == 0 && lane == 0 && trace_n < p.trace_cap / 2) p.trace[p.trace_cap / 2 + trace_n++] = clock64();
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                    const uint32_t sb = sa + kATileBytes;
-                    const uint64_t da = umma_desc_sw128(sa);
-                    const uint64_t db = umma_desc_sw128(sb);
-                    __syncwarp();
-                    if (elect_one()) {
-                        if (p.diag & 1) {
-                        } else if (it < 2 * nkb8) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)      // 32 e4m3 = 32 bytes per MMA: the same +2 descriptor step as 16 fp16
-                                umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                // advance 16 fp16 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                                umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                            }
-                        }
-                        umma_commit(&ctl->empty[stage]);
-                        if (it == n_iters - 1) umma_commit(&ctl->tmem_full[acc]);
-                    }
-                    __syncwarp();
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
-                }
+                mma_tile<false>(p, smem, ctl, ring, block_bytes, n_iters, 2 * nkb8, idesc, tmem_base + acc * 256, &ctl->tmem_full[acc], trace_n);
             }
         }
     } else {
@@ -562,8 +595,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int half_bn = p.BN >> 1;
-    const int stage_bytes = kATileBytes + half_bn * 128;
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.num_stages * stage_bytes);
+    const int block_bytes = kATileBytes + half_bn * 128;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.num_stages * p.grp * block_bytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -621,47 +654,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 const int ah0 = rem / p.conv_W;
                 const int aw0 = rem - ah0 * p.conv_W;
                 const int b_row = nt * p.BN + rank * half_bn;
-                if (warp == 0) producer_tile<true, 1>(p, smem, ctl, ring, stage_bytes, tx_bytes, rank == 0, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
-                else producer_tile<true, 2>(p, smem, ctl, ring, stage_bytes, tx_bytes, rank == 0, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
+                if (warp == 0) producer_tile<true, 1>(p, smem, ctl, ring, block_bytes, tx_bytes, rank == 0, n_iters, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
+                else producer_tile<true, 2>(p, smem, ctl, ring, block_bytes, tx_bytes, rank == 0, n_iters, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only; warp converged, tcgen05 elected)
         if (rank == 0) {
             const uint32_t idesc = umma_idesc_pair((uint32_t)p.BN);
-            int stage = 0;
-            uint32_t phase = 0;
+            RingPos ring{0, 0u};
             int iter = 0;
             for (int tile = first; tile < total_tiles; tile += step, ++iter) {
                 const int acc = iter & 1;
                 const uint32_t acc_phase = (iter >> 1) & 1;
                 mbar_wait_warp(&ctl->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * 256;
-                for (int it = 0; it < n_iters; ++it) {
-                    mbar_wait_warp(&ctl->full[stage], phase);
-                    if (p.trace && blockIdx.x == 0 && lane == 0 && trace_n < p.trace_cap / 2) p.trace[p.trace_cap / 2 + trace_n++] = clock64();
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-                    const uint32_t sb = sa + kATileBytes;
-                    const uint64_t da = umma_desc_sw128(sa);
-                    const uint64_t db = umma_desc_sw128(sb);
-                    __syncwarp();
-                    if (elect_one()) {
-                        if (p.diag & 1) {
-                        } else if (it < 2 * nkb8) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                        }
-                        umma_commit_pair(&ctl->empty[stage]);             // frees this stage in both CTAs
-                        if (it == n_iters - 1) umma_commit_pair(&ctl->tmem_full[acc]);
-                    }
-                    __syncwarp();
-                    if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
-                }
+                mma_tile<true>(p, smem, ctl, ring, block_bytes, n_iters, 2 * nkb8, idesc, tmem_base + acc * 256, &ctl->tmem_full[acc], trace_n);
             }
         }
     } else {
@@ -866,6 +874,10 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
         kp->pair = 1;
         stage_bytes = kATileBytes + (d->BN / 2) * 128;
     }
+    // two K blocks per ring stage when at least three (pair) / four (single) such stages still fit
+    static const int grp_env = [] { const char* e = getenv("DSB_GEMM_GROUP"); return e ? atoi(e) : 2; }();
+    kp->grp = 1;
+    if (grp_env == 2 && (227 * 1024 - 2048) / (2 * stage_bytes) >= (kp->pair ? 3 : 4)) { kp->grp = 2; stage_bytes *= 2; }
     int ns = (227 * 1024 - 2048) / stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;
     { const char* e = getenv("DSB_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < ns) ns = atoi(e); }      // measurement only
@@ -888,7 +900,7 @@ static int gemm_run_pair(const GemmKernelParams* kp, cudaStream_t stream) {
         if (cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -22;
         g_pair_attr_set = true;
     }
-    const int stage_bytes = kATileBytes + (kp->BN / 2) * 128;
+    const int stage_bytes = kp->grp * (kATileBytes + (kp->BN / 2) * 128);
     const size_t smem = (size_t)kp->num_stages * stage_bytes + sizeof(SmemCtl) + 1024;
     const int tiles = ((kp->m_tiles + 1) / 2) * kp->n_tiles;
     int clusters = g_num_sms / 2;
@@ -907,7 +919,7 @@ int gemm_run(const GemmKernelParams* kp, cudaStream_t stream) {
         g_attr_set = true;
     }
     if (kp->pair) return gemm_run_pair(kp, stream);
-    const int stage_bytes = kATileBytes + kp->BN * 128;
+    const int stage_bytes = kp->grp * (kATileBytes + kp->BN * 128);
     const size_t smem = (size_t)kp->num_stages * stage_bytes + sizeof(SmemCtl) + 1024;
     const int tiles = kp->num_z * kp->m_tiles * kp->n_tiles;
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
