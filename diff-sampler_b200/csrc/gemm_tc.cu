@@ -73,6 +73,11 @@ struct alignas(64) GemmKernelParams {
     // K blocks per ring stage (1 or 2): one empty/full barrier round trip, one expect_tx and one tcgen05.commit per `grp` 64-channel blocks.
     // The role warps' per-stage instruction chains (~500-600 cycles each, r02s/r02t) were longer than the MMAs of a stage whenever BN < 256.
     int grp;
+    // Row reuse (pair kernel, 3x3 convolutions whose M tile is th = 128 / W whole rows of one image): a ring stage holds ONE (th + 2)-row halo
+    // box of A per (kw, channel block) and the three B blocks of kh = 0, 1, 2; the three taps read the same box through MMA descriptors
+    // offset by kh * W * 128 bytes.  A traffic through L2 and into shared memory: (th + 2) rows per three taps instead of 3 * th.
+    CUtensorMap tmA_rr, tmA8_rr;
+    int rr, rr_halo_bytes, rr_row_bytes;
 };
 
 struct SmemCtl {
@@ -583,6 +588,109 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------ row-reuse K loops (pair kernel only)
+// Stage sequence of a tile, identical in the producers and in the MMA warp:
+//   f8:   for pass8 in {A_lo8 x W_hi8, A_hi8 x W_lo8}: for kw: for channel block (128): MAIN;  then the aux (1x1 skip) blocks
+//   fp16: for pass:                                      for kw: for channel block (64):  MAIN;  then the aux blocks
+// MAIN = [A halo box][B kh=0][B kh=1][B kh=2], aux = [A 128-pixel tile][B].  Weights stay packed K = (kh, kw, cin).
+template <int WHICH>
+__device__ __forceinline__ void producer_tile_rr(const GemmKernelParams& p, uint8_t* smem, SmemCtl* ctl, RingPos& r, const int stage_bytes,
+                                                 const int hb, const bool arm, const int aw0, const int ah0, const int an0, const int b_row,
+                                                 int& trace_n) {
+    const bool tracing = (WHICH & 1) && p.trace && blockIdx.x == 0 && lane_id() == 0;
+    const uint32_t tx_main = 2u * (uint32_t)((WHICH & 1) ? p.rr_halo_bytes : 3 * hb);       // both CTAs' bytes land on the leader's barrier
+    const uint32_t tx_aux = 2u * (uint32_t)((WHICH & 1) ? kATileBytes : hb);
+    // one stage: wait for the slot, arm, issue this warp's copies
+    auto stage = [&](bool main, const CUtensorMap* ma, int ac, int aw, int ah, int an, const CUtensorMap* mb, int bk0, int bk_step, int bz) {
+        mbar_wait_warp(&ctl->empty[r.stage], r.phase ^ 1);
+        if (tracing && trace_n < p.trace_cap / 2) p.trace[trace_n++] = clock64();
+        uint8_t* sa = smem + r.stage * stage_bytes;
+        uint64_t* full = &ctl->full[r.stage];
+        if (elect_one()) {
+            if (arm) mbar_arrive_expect_tx(full, main ? tx_main : tx_aux);
+            if (WHICH & 1) {
+                tma_load_4d_pair(ma, full, sa, ac, aw, ah, an);
+            } else {
+                uint8_t* sb = sa + p.rr_halo_bytes;
+                tma_load_3d_pair(mb, full, sb, bk0, b_row, bz);
+                if (main) {
+                    tma_load_3d_pair(mb, full, sb + hb, bk0 + bk_step, b_row, bz);
+                    tma_load_3d_pair(mb, full, sb + 2 * hb, bk0 + 2 * bk_step, b_row, bz);
+                }
+            }
+        }
+        __syncwarp();
+        if (++r.stage == p.num_stages) { r.stage = 0; r.phase ^= 1; }
+    };
+    if (p.f8) {
+        const int kh_step = 3 * p.cpb8 * 128;                       // K distance between kh and kh + 1 (bytes = e4m3 elements)
+        for (int pass8 = 0; pass8 < 2; ++pass8) {
+            const int an8 = an0 + pass8 * p.a8_plane_n;
+            for (int kw = 0; kw < 3; ++kw)
+                for (int cb = 0; cb < p.cpb8; ++cb)
+                    stage(true, &p.tmA8_rr, cb * 128, aw0 + kw - 1, ah0 - 1, an8, &p.tmB8h, (kw * p.cpb8 + cb) * 128, kh_step, pass8);
+            for (int j = 0; j < p.nkb8_aux; ++j)
+                stage(false, &p.tmA2_8, j * 128, aw0, ah0, an8, &p.tmB8h, (9 * p.cpb8 + j) * 128, 0, pass8);
+        }
+    }
+    const int npass16 = p.f8 ? 1 : p.npass;
+    const int kh_step = 3 * p.cpb * 64;
+    for (int pass = 0; pass < npass16; ++pass) {
+        const int an = an0 + (pass == 1 ? p.a_plane_n : 0);
+        const int an2 = an0 + (pass == 1 ? p.a2_plane_n : 0);
+        const int bz = pass == 2 ? p.b_plane_batch : 0;
+        for (int kw = 0; kw < 3; ++kw)
+            for (int cb = 0; cb < p.cpb; ++cb)
+                stage(true, &p.tmA_rr, cb * 64, aw0 + kw - 1, ah0 - 1, an, &p.tmBh, (kw * p.cpb + cb) * 64, kh_step, bz);
+        for (int j = 0; j < p.nkb_aux; ++j)
+            stage(false, &p.tmA2, j * 64, aw0, ah0, an2, &p.tmBh, (9 * p.cpb + j) * 64, 0, bz);
+    }
+}
+
+__device__ __forceinline__ void mma_tile_rr(const GemmKernelParams& p, uint8_t* smem, SmemCtl* ctl, RingPos& r, const int stage_bytes,
+                                            const int hb, const uint32_t idesc, const uint32_t d_tmem, uint64_t* tmem_full_bar, int& trace_n) {
+    const bool tracing = p.trace && blockIdx.x == 0 && lane_id() == 0;
+    const int main8 = p.f8 ? 3 * p.cpb8 : 0, aux8 = p.f8 ? p.nkb8_aux : 0;
+    const int npass16 = p.f8 ? 1 : p.npass;
+    const int main16 = 3 * p.cpb, aux16 = p.nkb_aux;
+    const int n_f8 = 2 * (main8 + aux8);
+    const int n_stages = n_f8 + npass16 * (main16 + aux16);
+    int q = 0;                                   // stage index inside the current pass
+    int per_pass = main8 + aux8, n_main = main8;
+    for (int st = 0; st < n_stages; ++st) {
+        if (st == n_f8) { q = 0; per_pass = main16 + aux16; n_main = main16; }
+        const bool f8 = st < n_f8;
+        const bool main = q < n_main;
+        mbar_wait_warp(&ctl->full[r.stage], r.phase);
+        if (tracing && trace_n < p.trace_cap / 2) p.trace[p.trace_cap / 2 + trace_n++] = clock64();
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + r.stage * stage_bytes);
+        const uint32_t sb = sa + p.rr_halo_bytes;
+        if (elect_one()) {
+            if (!(p.diag & 1)) {
+                const int nkh = main ? 3 : 1;
+                for (int kh = 0; kh < nkh; ++kh) {
+                    const uint64_t da = umma_desc_sw128(sa + kh * p.rr_row_bytes);
+                    const uint64_t db = umma_desc_sw128(sb + kh * hb);
+                    const uint32_t acc0 = (st > 0 || kh > 0) ? 1u : 0u;
+                    if (f8) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                    }
+                }
+            }
+            umma_commit_pair(&ctl->empty[r.stage]);
+            if (st == n_stages - 1) umma_commit_pair(tmem_full_bar);
+        }
+        __syncwarp();
+        if (++r.stage == p.num_stages) { r.stage = 0; r.phase ^= 1; }
+        if (++q == per_pass) q = 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ CTA-pair variant (large convolutions; DSB_GEMM_2CTA=0 disables)
 // Same roles and pipelines over a cluster of two CTAs (one TPC): the pair owns 256 output rows (M tiles 2*pm + rank) x BN columns; each
 // CTA loads its own 128-row A tile and HALF of the B tile, the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) whose
@@ -596,7 +704,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int half_bn = p.BN >> 1;
     const int block_bytes = kATileBytes + half_bn * 128;
-    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.num_stages * p.grp * block_bytes);
+    const int rr_stage_bytes = p.rr_halo_bytes + 3 * half_bn * 128;
+    SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smem + p.num_stages * (p.rr ? rr_stage_bytes : p.grp * block_bytes));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -610,7 +719,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
     const int first = (int)cluster_id_x(), step = (int)cluster_count_x();
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(p.rr ? &p.tmA_rr : &p.tmA);
         tma_prefetch_desc(&p.tmBh);
         if (p.nkb_aux) tma_prefetch_desc(&p.tmA2);
         if (p.f8) {
@@ -654,7 +763,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 const int ah0 = rem / p.conv_W;
                 const int aw0 = rem - ah0 * p.conv_W;
                 const int b_row = nt * p.BN + rank * half_bn;
-                if (warp == 0) producer_tile<true, 1>(p, smem, ctl, ring, block_bytes, tx_bytes, rank == 0, n_iters, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
+                if (p.rr) {
+                    if (warp == 0) producer_tile_rr<1>(p, smem, ctl, ring, rr_stage_bytes, half_bn * 128, rank == 0, aw0, ah0, an0, b_row, trace_n);
+                    else producer_tile_rr<2>(p, smem, ctl, ring, rr_stage_bytes, half_bn * 128, rank == 0, aw0, ah0, an0, b_row, trace_n);
+                } else if (warp == 0) producer_tile<true, 1>(p, smem, ctl, ring, block_bytes, tx_bytes, rank == 0, n_iters, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
                 else producer_tile<true, 2>(p, smem, ctl, ring, block_bytes, tx_bytes, rank == 0, n_iters, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
             }
         }
@@ -669,7 +781,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 const uint32_t acc_phase = (iter >> 1) & 1;
                 mbar_wait_warp(&ctl->tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
-                mma_tile<true>(p, smem, ctl, ring, block_bytes, n_iters, 2 * nkb8, idesc, tmem_base + acc * 256, &ctl->tmem_full[acc], trace_n);
+                if (p.rr) mma_tile_rr(p, smem, ctl, ring, rr_stage_bytes, half_bn * 128, idesc, tmem_base + acc * 256, &ctl->tmem_full[acc], trace_n);
+                else mma_tile<true>(p, smem, ctl, ring, block_bytes, n_iters, 2 * nkb8, idesc, tmem_base + acc * 256, &ctl->tmem_full[acc], trace_n);
             }
         }
     } else {
@@ -873,11 +986,36 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
         }
         kp->pair = 1;
         stage_bytes = kATileBytes + (d->BN / 2) * 128;
+        // row reuse: plain 3x3 taps, the M tile = th >= 2 whole rows of one image (W <= 64), at least three stages of halo + 3 B blocks
+        static const int rr_env = [] { const char* e = getenv("DSB_GEMM_RR"); return e ? atoi(e) : 1; }();
+        const int Wd = (int)d->a_dims[1], Hd = (int)d->a_dims[2];
+        bool std_taps = d->taps == 9;
+        for (int t = 0; t < 9 && std_taps; ++t) std_taps = d->tap_dh[t] == t / 3 - 1 && d->tap_dw[t] == t % 3 - 1;
+        const int th = Wd > 0 ? 128 / Wd : 0;
+        const int halo = (th + 2) * Wd * 128;
+        const int rr_stage = halo + 3 * (d->BN / 2) * 128;
+        if (rr_env && std_taps && Wd <= 64 && th >= 2 && th * Wd == 128 && Hd % th == 0 && d->a_box[1] == Wd && d->a_box[2] == th && d->a_box[3] == 1 &&
+            d->conv_W == Wd && d->conv_H == Hd && (227 * 1024 - 2048) / rr_stage >= 3) {
+            const int32_t box_rr[4] = {64, Wd, th + 2, 1};
+            if (encode_map(&kp->tmA_rr, d->a_ptr, 4, d->a_dims, d->a_strides, box_rr)) return -32;
+            if (d->f8 & 1) {
+                const int64_t C = d->a_dims[0], Bn = d->a_plane_n;
+                const int32_t box8_rr[4] = {128, Wd, th + 2, 1};
+                const int64_t dims8[4] = {C, Wd, Hd, 2 * Bn};
+                const int64_t st8[3] = {C, (int64_t)Wd * C, (int64_t)Hd * Wd * C};
+                const char* a8 = static_cast<const char*>(d->a_ptr) + Bn * Hd * Wd * C * 2;
+                if (encode_map_typed(&kp->tmA8_rr, a8, 4, dims8, st8, box8_rr, true)) return -33;
+            }
+            kp->rr = 1;
+            kp->rr_halo_bytes = halo;
+            kp->rr_row_bytes = Wd * 128;
+        }
     }
     // two K blocks per ring stage when at least three (pair) / four (single) such stages still fit
     static const int grp_env = [] { const char* e = getenv("DSB_GEMM_GROUP"); return e ? atoi(e) : 2; }();
     kp->grp = 1;
-    if (grp_env == 2 && (227 * 1024 - 2048) / (2 * stage_bytes) >= (kp->pair ? 3 : 4)) { kp->grp = 2; stage_bytes *= 2; }
+    if (kp->rr) stage_bytes = kp->rr_halo_bytes + 3 * (d->BN / 2) * 128;
+    else if (grp_env == 2 && (227 * 1024 - 2048) / (2 * stage_bytes) >= (kp->pair ? 3 : 4)) { kp->grp = 2; stage_bytes *= 2; }
     int ns = (227 * 1024 - 2048) / stage_bytes;
     if (ns > kMaxStages) ns = kMaxStages;
     { const char* e = getenv("DSB_GEMM_STAGES"); if (e && atoi(e) >= 2 && atoi(e) < ns) ns = atoi(e); }      // measurement only
@@ -900,7 +1038,7 @@ static int gemm_run_pair(const GemmKernelParams* kp, cudaStream_t stream) {
         if (cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -22;
         g_pair_attr_set = true;
     }
-    const int stage_bytes = kp->grp * (kATileBytes + (kp->BN / 2) * 128);
+    const int stage_bytes = kp->rr ? kp->rr_halo_bytes + 3 * (kp->BN / 2) * 128 : kp->grp * (kATileBytes + (kp->BN / 2) * 128);
     const size_t smem = (size_t)kp->num_stages * stage_bytes + sizeof(SmemCtl) + 1024;
     const int tiles = ((kp->m_tiles + 1) / 2) * kp->n_tiles;
     int clusters = g_num_sms / 2;
