@@ -628,7 +628,7 @@ F8_MIN_CHANNELS_FOR = {'ffhq': 256}
 # bench command committed under profiles/ (a number measured under the profiler is a byte count, not a time).
 NCU_TRAFFIC = {
     ('conv3x3 256->256 @32x32 x512', 'fp16x3'): (0.539457e9 + 0.496578e9, 'profiles/r01b_ncu_gemm_conv_b512.txt (launch id 1)'),
-    ('conv3x3 256->256 @32x32 x512 f8', 'fp16f8'): (0.539682e9 + 0.498288e9, 'profiles/r01c/ncu_gemm_conv_b512_fp16f8.txt (launch id 0)'),
+    ('conv3x3 256->256 @32x32 x512 f8', 'fp16f8'): (0.540013e9 + 0.496059e9, 'profiles/r02/ncu_gemm_pair_cifar_f8_r02p.txt (gemm_tc_pair_kernel, ncu --set full)'),
 }
 
 
@@ -695,7 +695,7 @@ def roofline_leg(args, line, net, latents, labels, B, dev, pk, kw):
     f1.record()
     torch.cuda.synchronize()
     line['roofline'] = dict(bound='tensor', achieved=achieved, peak=peak, unit='TFLOP/s', frac=(achieved / peak) if achieved else None,
-                            traffic=None, kernel='gemm_tc_kernel (+ attn_kernel): all conv / linear / attention contractions of one denoiser evaluation',
+                            traffic=None, kernel='gemm_tc_pair_kernel / gemm_tc_kernel (+ attn3_kernel): all conv / linear / attention contractions of one denoiser evaluation',
                             algorithmic_flops_per_forward=flops, launches_per_forward=gemm_n + attn_n, gemm_ms_per_forward=gemm_ms,
                             attn_ms_per_forward=attn_ms, all_ops_ms_per_forward=fwd_ms, forward_ms_back_to_back=f0.elapsed_time(f1) / n_rep,
                             gemm_share_of_forward=tc_ms / fwd_ms if fwd_ms else None,

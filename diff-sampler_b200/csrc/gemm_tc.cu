@@ -5,13 +5,18 @@
 //  :174-178 qkv/proj): 3x3 and 1x1 convolutions over NHWC fp16 activations, the 1x1 skip
 // projection appended along K, and the batched Q.K^T / P.V products of self-attention.
 //
-//   warp 0      TMA producer   (cp.async.bulk.tensor 4-D boxes for A = shifted pixel tiles, 3-D for B)
+//   warp 0      TMA producer   (cp.async.bulk.tensor 4-D boxes for A = shifted pixel tiles / row-reuse halo boxes, 3-D for B)
 //   warp 1      MMA issuer     (tcgen05.mma kind::f16, 128 x BN x 16, fp32 accumulators in TMEM; in f8 mode the two split-precision
 //                               correction products are kind::f8f6f4 e4m3 MMAs, 128 x BN x 32, into the same accumulator)
-//   warps 2..5  epilogue       (tcgen05.ld -> bias / embedding / residual / scale -> fp32 and/or fp16 hi/lo)
+//   warps 2..9  epilogue       (two groups of four warps on alternate 32-column chunks: tcgen05.ld -> bias / embedding / residual /
+//                               scale / GroupNorm partial sums -> fp32 and/or fp16 hi/lo)
 //
-// Pipelines: smem ring (full/empty mbarriers) between TMA and MMA, and two TMEM accumulator
+// Pipelines: smem ring (full/empty mbarriers, one or two 64-channel K blocks per stage) between TMA and MMA, and two TMEM accumulator
 // buffers (tmem_full/tmem_empty) between MMA and epilogue so tile i+1 is multiplied while tile i drains.
+// gemm_tc_pair_kernel: the same over a cluster of two CTAs (tcgen05.mma.cta_group::2, M = 256), with row reuse for 3x3 convolutions.
+// Measurement switches (results are garbage, timings are not): DSB_GEMM_DIAG (1 no MMA, 2 no TMA, 4 no epilogue; 8 / 16 no A / B loads,
+// 32 unshifted taps, 64 hot A tile: single-CTA kernel without row reuse only), DSB_GEMM_STAGES, DSB_GEMM_GROUP, DSB_GEMM_RR,
+// DSB_GEMM_EPI_GROUPS, DSB_GEMM_2CTA(_MIN_PAIR_TILES); ds_debug_gemm_trace records the ring timeline of CTA 0.
 #include "ops.h"
 #include "ptx.cuh"
 #include <cuda_fp16.h>
@@ -23,7 +28,7 @@ namespace dsb {
 
 static constexpr int kMaxStages = 8;
 static constexpr int kATileBytes = 128 * 128;   // 128 rows x 64 fp16
-static constexpr int kThreads = 224;           // warp 0: A producer, 1: MMA issuer, 2..5: epilogue, 6: B producer
+static constexpr int kThreads = 320;           // warp 0: TMA producer, 1: MMA issuer, 2..9: epilogue (two groups of four: even / odd 32-column chunks)
 
 struct alignas(64) GemmKernelParams {
     CUtensorMap tmA, tmA2, tmB;
@@ -73,6 +78,7 @@ struct alignas(64) GemmKernelParams {
     // K blocks per ring stage (1 or 2): one empty/full barrier round trip, one expect_tx and one tcgen05.commit per `grp` 64-channel blocks.
     // The role warps' per-stage instruction chains (~500-600 cycles each, r02s/r02t) were longer than the MMAs of a stage whenever BN < 256.
     int grp;
+    int epi_groups;                      // 2 (default): both epilogue warp groups work; 1: group 1 idles (A/B only, DSB_GEMM_EPI_GROUPS)
     // Row reuse (pair kernel, 3x3 convolutions whose M tile is th = 128 / W whole rows of one image): a ring stage holds ONE (th + 2)-row halo
     // box of A per (kw, channel block) and the three B blocks of kh = 0, 1, 2; the three taps read the same box through MMA descriptors
     // offset by kh * W * 128 bytes.  A traffic through L2 and into shared memory: (th + 2) rows per three taps instead of 3 * th.
@@ -324,9 +330,9 @@ struct RingPos {
     uint32_t phase;
 };
 
-// Two producer warps walk the same loop nest: WHICH = 1 issues the A boxes (warp 0), WHICH = 2 the B boxes (warp 6); each arms the stage's
-// full barrier (count 2) with its own bytes.  Halves the dependent instruction chain per stage of either warp (r02r: one warp issuing both
-// copies needed ~515 cycles per stage, as long as the four e4m3 MMAs of a stage).
+// WHICH selects the copies this warp issues (1 = A boxes, 2 = B boxes, 3 = both: the shipped configuration).  Splitting A and B over two
+// producer warps was measured neutral (r02s) once the loop was division-free and stages carry two K blocks, so one warp issues both and
+// the freed warps went to the epilogue.
 template <bool PAIR, int WHICH>
 __device__ __forceinline__ void producer_tile(const GemmKernelParams& p, uint8_t* smem, SmemCtl* ctl, RingPos& r, const int block_bytes,
                                               const uint32_t tx_bytes, const bool arm, const int n_blocks, const int aw0, const int ah0,
@@ -466,12 +472,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (p.nkb8_aux) tma_prefetch_desc(&p.tmA2_8);
         }
         for (int s = 0; s < p.num_stages; ++s) {
-            mbar_init(&ctl->full[s], 2);                                  // the A and the B producer warp
+            mbar_init(&ctl->full[s], 1);
             mbar_init(&ctl->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ctl->tmem_full[a], 1);
-            mbar_init(&ctl->tmem_empty[a], 4);
+            mbar_init(&ctl->tmem_empty[a], 8);                            // the eight epilogue warps
         }
         fence_barrier_init();
     } else if (warp == 1) {
@@ -482,11 +488,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
 
-    if (warp == 0 || warp == 6) {
-        // ------------------------------------------------------------------ TMA producers (warp 0: A boxes, warp 6: B boxes; converged, copies elected)
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (whole warp converged; the copies elected)
         {
             RingPos ring{0, 0u};
-            const uint32_t tx_bytes = (p.diag & 2) ? 0u : (warp == 0 ? ((p.diag & 8) ? 0u : (uint32_t)kATileBytes) : ((p.diag & 16) ? 0u : (uint32_t)(p.BN * 128)));
+            const uint32_t tx_bytes = (p.diag & 2) ? 0u : (uint32_t)(((p.diag & 8) ? 0 : kATileBytes) + ((p.diag & 16) ? 0 : p.BN * 128));
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int z = tile / tiles_per_z;
                 const int t2 = tile - z * tiles_per_z;
@@ -509,8 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 const int b_k_off = p.b_k0 + zh * p.b_k_per_zh;
                 const int b_row = nt * p.BN + zh * p.b_row_per_zh;
                 const int b_z = zb * p.b_z_per_zb + zh * p.b_z_per_zh;
-                if (warp == 0) producer_tile<false, 1>(p, smem, ctl, ring, block_bytes, tx_bytes, true, n_iters, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
-                else producer_tile<false, 2>(p, smem, ctl, ring, block_bytes, tx_bytes, true, n_iters, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
+                producer_tile<false, 3>(p, smem, ctl, ring, block_bytes, tx_bytes, true, n_iters, aw0, ah0, an0, a_c_off, b_k_off, b_row, b_z, trace_n);
             }
         }
     } else if (warp == 1) {
@@ -528,8 +533,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9: two groups of four)
         const int quad = warp & 3;   // TMEM lane quadrant this warp may access
+        const int eg = (warp - 2) >> 2;
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int z = tile / tiles_per_z;
@@ -554,22 +560,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int q = 0; q < 8; ++q) res_next[q] = *reinterpret_cast<const float4*>(res_row + cc + 4 * q);
                 }
             };
-            if (!(p.diag & 4)) prefetch(0);
-            int c = (p.diag & 4) ? p.BN : 0;
-            for (; c + 32 <= p.BN; c += 32) {
+            // epilogue group eg takes the 32-column chunks eg, eg + 2, ... (and the 16-column tail if it is its turn)
+            const int cstep = 32 * p.epi_groups;
+            if (!(p.diag & 4) && eg < p.epi_groups && eg * 32 + 32 <= p.BN) prefetch(eg * 32);
+            int c = ((p.diag & 4) || eg >= p.epi_groups) ? p.BN : eg * 32;
+            for (; c + 32 <= p.BN; c += cstep) {
                 float4 res_cur[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) res_cur[q] = res_next[q];
                 const int col0 = nt * p.BN + c;
                 const bool in_regs = res_row && (col0 + 32 <= p.n_valid);
-                if (c + 64 <= p.BN) prefetch(c + 32);
+                if (c + cstep + 32 <= p.BN) prefetch(c + cstep);
                 uint32_t v[32];
                 DSB_TMEM_LD_32(t_row + c, v);
                 tmem_ld_wait();
                 if (col0 < p.n_valid)
                     epilogue_chunk<32>(p, reinterpret_cast<const float*>(v), grow, col0, row_ok, zb, zh, res_cur, in_regs);
             }
-            if (c < p.BN) {
+            if (c < p.BN && c + 32 > p.BN && !(p.diag & 4)) {
                 uint32_t v[16];
                 DSB_TMEM_LD_16(t_row + c, v);
                 tmem_ld_wait();
@@ -598,8 +606,8 @@ __device__ __forceinline__ void producer_tile_rr(const GemmKernelParams& p, uint
                                                  const int hb, const bool arm, const int aw0, const int ah0, const int an0, const int b_row,
                                                  int& trace_n) {
     const bool tracing = (WHICH & 1) && p.trace && blockIdx.x == 0 && lane_id() == 0;
-    const uint32_t tx_main = 2u * (uint32_t)((WHICH & 1) ? p.rr_halo_bytes : 3 * hb);       // both CTAs' bytes land on the leader's barrier
-    const uint32_t tx_aux = 2u * (uint32_t)((WHICH & 1) ? kATileBytes : hb);
+    const uint32_t tx_main = 2u * (uint32_t)(((WHICH & 1) ? p.rr_halo_bytes : 0) + ((WHICH & 2) ? 3 * hb : 0));   // both CTAs' bytes land on the leader's barrier
+    const uint32_t tx_aux = 2u * (uint32_t)(((WHICH & 1) ? kATileBytes : 0) + ((WHICH & 2) ? hb : 0));
     // one stage: wait for the slot, arm, issue this warp's copies
     auto stage = [&](bool main, const CUtensorMap* ma, int ac, int aw, int ah, int an, const CUtensorMap* mb, int bk0, int bk_step, int bz) {
         mbar_wait_warp(&ctl->empty[r.stage], r.phase ^ 1);
@@ -608,9 +616,8 @@ __device__ __forceinline__ void producer_tile_rr(const GemmKernelParams& p, uint
         uint64_t* full = &ctl->full[r.stage];
         if (elect_one()) {
             if (arm) mbar_arrive_expect_tx(full, main ? tx_main : tx_aux);
-            if (WHICH & 1) {
-                tma_load_4d_pair(ma, full, sa, ac, aw, ah, an);
-            } else {
+            if (WHICH & 1) tma_load_4d_pair(ma, full, sa, ac, aw, ah, an);
+            if (WHICH & 2) {
                 uint8_t* sb = sa + p.rr_halo_bytes;
                 tma_load_3d_pair(mb, full, sb, bk0, b_row, bz);
                 if (main) {
@@ -728,12 +735,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
             if (p.nkb8_aux) tma_prefetch_desc(&p.tmA2_8);
         }
         for (int s = 0; s < p.num_stages; ++s) {
-            mbar_init(&ctl->full[s], 2);                                  // the leader's A and B producer warps (arming both CTAs' bytes)
+            mbar_init(&ctl->full[s], 1);                                  // the leader's producer warp arms both CTAs' bytes
             mbar_init(&ctl->empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ctl->tmem_full[a], 1);
-            mbar_init(&ctl->tmem_empty[a], 8);                            // 4 epilogue warps of each CTA (used in the leader only)
+            mbar_init(&ctl->tmem_empty[a], 16);                           // 8 epilogue warps of each CTA (used in the leader only)
         }
         fence_barrier_init();
     } else if (warp == 1) {
@@ -744,12 +751,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
     tc_fence_after();
     const uint32_t tmem_base = ctl->tmem_base;
 
-    if (warp == 0 || warp == 6) {
-        // ------------------------------------------------------------------ TMA producers (both CTAs; warp 0: A boxes, warp 6: B boxes)
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs; warp converged, copies elected)
         {
             RingPos ring{0, 0u};
             // the leader's full barrier collects both CTAs' bytes
-            const uint32_t tx_bytes = (p.diag & 2) ? 0u : 2u * (warp == 0 ? ((p.diag & 8) ? 0u : (uint32_t)kATileBytes) : ((p.diag & 16) ? 0u : (uint32_t)(half_bn * 128)));
+            const uint32_t tx_bytes = (p.diag & 2) ? 0u : 2u * (uint32_t)(((p.diag & 8) ? 0 : kATileBytes) + ((p.diag & 16) ? 0 : half_bn * 128));
             for (int tile = first; tile < total_tiles; tile += step) {
                 const int pm = tile / p.n_tiles;
                 const int nt = tile - pm * p.n_tiles;
@@ -763,11 +770,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                 const int ah0 = rem / p.conv_W;
                 const int aw0 = rem - ah0 * p.conv_W;
                 const int b_row = nt * p.BN + rank * half_bn;
-                if (p.rr) {
-                    if (warp == 0) producer_tile_rr<1>(p, smem, ctl, ring, rr_stage_bytes, half_bn * 128, rank == 0, aw0, ah0, an0, b_row, trace_n);
-                    else producer_tile_rr<2>(p, smem, ctl, ring, rr_stage_bytes, half_bn * 128, rank == 0, aw0, ah0, an0, b_row, trace_n);
-                } else if (warp == 0) producer_tile<true, 1>(p, smem, ctl, ring, block_bytes, tx_bytes, rank == 0, n_iters, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
-                else producer_tile<true, 2>(p, smem, ctl, ring, block_bytes, tx_bytes, rank == 0, n_iters, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
+                if (p.rr) producer_tile_rr<3>(p, smem, ctl, ring, rr_stage_bytes, half_bn * 128, rank == 0, aw0, ah0, an0, b_row, trace_n);
+                else producer_tile<true, 3>(p, smem, ctl, ring, block_bytes, tx_bytes, rank == 0, n_iters, aw0, ah0, an0, 0, 0, b_row, 0, trace_n);
             }
         }
     } else if (warp == 1) {
@@ -786,8 +790,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5 of both CTAs, own 128 rows each)
+        // ------------------------------------------------------------------ epilogue (warps 2..9 of both CTAs, own 128 rows each)
         const int quad = warp & 3;
+        const int eg = (warp - 2) >> 2;
         int iter = 0;
         for (int tile = first; tile < total_tiles; tile += step, ++iter) {
             const int pm = tile / p.n_tiles;
@@ -809,15 +814,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) gemm_tc
                     for (int q = 0; q < 8; ++q) res_next[q] = *reinterpret_cast<const float4*>(res_row + cc + 4 * q);
                 }
             };
-            if (!(p.diag & 4)) prefetch(0);
-            int c = (p.diag & 4) ? p.BN : 0;
-            for (; c + 32 <= p.BN; c += 32) {
+            const int cstep = 32 * p.epi_groups;
+            if (!(p.diag & 4) && eg < p.epi_groups && eg * 32 + 32 <= p.BN) prefetch(eg * 32);
+            int c = ((p.diag & 4) || eg >= p.epi_groups) ? p.BN : eg * 32;
+            for (; c + 32 <= p.BN; c += cstep) {
                 float4 res_cur[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) res_cur[q] = res_next[q];
                 const int col0 = nt * p.BN + c;
                 const bool in_regs = res_row && (col0 + 32 <= p.n_valid);
-                if (c + 64 <= p.BN) prefetch(c + 32);
+                if (c + cstep + 32 <= p.BN) prefetch(c + cstep);
                 uint32_t v[32];
                 DSB_TMEM_LD_32(t_row + c, v);
                 tmem_ld_wait();
@@ -953,6 +959,7 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     }
     for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = d->tap_dh[t]; kp->tap_dw[t] = d->tap_dw[t]; kp->tap_cb[t] = d->tap_cb[t]; }
     { const char* e = getenv("DSB_GEMM_DIAG"); kp->diag = e ? atoi(e) : 0; }
+    { const char* e = getenv("DSB_GEMM_EPI_GROUPS"); kp->epi_groups = (e && atoi(e) == 1) ? 1 : 2; }
     kp->trace = g_trace_buf; kp->trace_cap = g_trace_cap;
     if (kp->diag & 32) for (int t = 0; t < 9; ++t) { kp->tap_dh[t] = 0; kp->tap_dw[t] = 0; }      // every tap reads the unshifted box
     if (d->taps != 1 && d->taps != 9) return -15;
