@@ -873,11 +873,12 @@ def _time_launch(lib, d, n=5):
 
 @pytest.mark.parametrize('f8', [False, True])
 @pytest.mark.parametrize('Bn,H,W,Cin,Cout,C2', [(80, 32, 32, 256, 256, 0), (75, 32, 32, 64, 128, 64), (300, 16, 16, 128, 192, 0),
-                                                (1185, 8, 8, 128, 128, 0), (3, 16, 16, 128, 256, 0)])
+                                                (1185, 8, 8, 128, 128, 0), (3, 16, 16, 128, 256, 0), (20, 64, 64, 192, 192, 0)])
 def test_conv_pair_kernel(lib, f8, Bn, H, W, Cin, Cout, C2):
     """gemm_tc_pair_kernel (tcgen05.mma.cta_group::2 over a cluster of two CTAs; requested per launch with conv_gemm(pair=True)) against
     the single-CTA kernel on the same operands and against the references: many tiles, an odd tile count whose last tile is half full
-    (1185 x 8 x 8 -> 593 tiles: phantom tile in the last pair), and a problem smaller than one wave."""
+    (1185 x 8 x 8 -> 593 tiles: phantom tile in the last pair), and a problem smaller than one wave.  The 32 x 32, 16 x 16 and 64 x 64 cases
+    run the row-reuse K loop (halo box of 6 / 10 / 4 rows, with and without the appended 1x1 skip blocks), the 8 x 8 case the plain one."""
     from diff_sampler_b200 import gemm_desc as G
     torch.manual_seed(21)
     x = torch.randn(Bn, Cin, H, W, device=dev())
