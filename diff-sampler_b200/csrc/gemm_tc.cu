@@ -78,6 +78,8 @@ struct alignas(64) GemmKernelParams {
     // K blocks per ring stage (1 or 2): one empty/full barrier round trip, one expect_tx and one tcgen05.commit per `grp` 64-channel blocks.
     // The role warps' per-stage instruction chains (~500-600 cycles each, r02s/r02t) were longer than the MMAs of a stage whenever BN < 256.
     int grp;
+    int f8_last_steps;                   // e4m3 MMAs (K = 32) of the last 128-channel block of a tap: 2 when only its first 64 channels exist
+                                         // (C = 192, 576: the other two would multiply TMA zero fill with zero-padded weights), else 4
     int epi_groups;                      // 2 (default): both epilogue warp groups work; 1: group 1 idles (A/B only, DSB_GEMM_EPI_GROUPS)
     // Row reuse (pair kernel, 3x3 convolutions whose M tile is th = 128 / W whole rows of one image): a ring stage holds ONE (th + 2)-row halo
     // box of A per (kw, channel block) and the three B blocks of kh = 0, 1, 2; the three taps read the same box through MMA descriptors
@@ -404,12 +406,25 @@ __device__ __forceinline__ void mma_tile(const GemmKernelParams& p, uint8_t* sme
     const int grp = p.grp;
     const int stage_bytes = grp * block_bytes;
     const bool tracing = p.trace && blockIdx.x == 0 && lane_id() == 0;
+    // e4m3 blocks of a pass: taps x cpb8 main blocks (the last of each tap may be half empty), then the aux blocks
+    const int nkb8 = nkb8x2 >> 1;
+    int q8 = 0, cb8 = 0;
     for (int it = 0; it < n_iters; it += grp) {
         mbar_wait_warp(&ctl->full[r.stage], r.phase);
         if (tracing && trace_n < p.trace_cap / 2) p.trace[p.trace_cap / 2 + trace_n++] = clock64();
         tc_fence_after();
         const uint32_t s0 = smem_u32(smem + r.stage * stage_bytes);
         const int nb = min(grp, n_iters - it);
+        int steps0 = 4, steps1 = 4;
+        for (int j = 0; j < nb; ++j) {
+            if (it + j < nkb8x2) {
+                if (q8 < p.nkb8_main) {
+                    if (cb8 == p.cpb8 - 1) { if (j == 0) steps0 = p.f8_last_steps; else steps1 = p.f8_last_steps; }
+                    if (++cb8 == p.cpb8) cb8 = 0;
+                }
+                if (++q8 == nkb8) { q8 = 0; cb8 = 0; }
+            }
+        }
         if (elect_one()) {
             if (!(p.diag & 1)) {
                 for (int j = 0; j < nb; ++j) {
@@ -418,10 +433,13 @@ __device__ __forceinline__ void mma_tile(const GemmKernelParams& p, uint8_t* sme
                     const uint64_t db = umma_desc_sw128(sa + kATileBytes);
                     const uint32_t acc0 = (it + j) > 0 ? 1u : 0u;
                     if (it + j < nkb8x2) {
+                        const int ns = j == 0 ? steps0 : steps1;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {       // 32 e4m3 = 32 bytes per MMA: the same +2 descriptor step (16-byte units) as 16 fp16
-                            if (PAIR) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
-                            else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                            if (k < ns) {
+                                if (PAIR) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                                else umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                            }
                         }
                     } else {
 #pragma unroll
@@ -663,6 +681,7 @@ __device__ __forceinline__ void mma_tile_rr(const GemmKernelParams& p, uint8_t* 
     const int n_f8 = 2 * (main8 + aux8);
     const int n_stages = n_f8 + npass16 * (main16 + aux16);
     int q = 0;                                   // stage index inside the current pass
+    int cb8 = 0;
     int per_pass = main8 + aux8, n_main = main8;
     for (int st = 0; st < n_stages; ++st) {
         if (st == n_f8) { q = 0; per_pass = main16 + aux16; n_main = main16; }
@@ -673,6 +692,11 @@ __device__ __forceinline__ void mma_tile_rr(const GemmKernelParams& p, uint8_t* 
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + r.stage * stage_bytes);
         const uint32_t sb = sa + p.rr_halo_bytes;
+        int ns = 4;                              // main stages of a pass run (kw, channel block): the last channel block may be half empty
+        if (f8 && main) {
+            if (cb8 == p.cpb8 - 1) ns = p.f8_last_steps;
+            if (++cb8 == p.cpb8) cb8 = 0;
+        }
         if (elect_one()) {
             if (!(p.diag & 1)) {
                 const int nkh = main ? 3 : 1;
@@ -682,7 +706,8 @@ __device__ __forceinline__ void mma_tile_rr(const GemmKernelParams& p, uint8_t* 
                     const uint32_t acc0 = (st > 0 || kh > 0) ? 1u : 0u;
                     if (f8) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
+                        for (int k = 0; k < 4; ++k)
+                            if (k < ns) umma_f8_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
                     } else {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, k > 0 ? 1u : acc0);
@@ -937,6 +962,8 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
         const char* a8 = static_cast<const char*>(d->a_ptr) + Bn * Hd * Wd * C * 2;
         if (encode_map_typed(&kp->tmA8, a8, 4, dims8, st8, box8, true)) return -17;
         kp->f8 = 1;
+        static const int half_env = [] { const char* e = getenv("DSB_GEMM_F8_HALF"); return e ? atoi(e) : 1; }();
+        kp->f8_last_steps = (half_env && (d->cpb & 1)) ? 2 : 4;
         kp->a8_plane_n = (int)Bn;
         kp->cpb8 = (d->cpb + 1) / 2;
         kp->nkb8_main = d->taps * kp->cpb8;
@@ -977,7 +1004,7 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     // since the producer rewrite (r02r) the pair kernel runs at the MMA instruction bound (600 cycles per stage) while the single-CTA kernel
     // is shared-memory-port bound (770): the pair wins 12-16 % on every shape that still gives each SM pair a tile
     static const int pair_min_tiles = [] { const char* e = getenv("DSB_GEMM_2CTA_MIN_PAIR_TILES"); return e ? atoi(e) : 74; }();
-    const bool pair_auto = pair_env && ((d->m_tiles + 1) / 2) * d->n_tiles >= pair_min_tiles && d->BN >= 64;
+    const bool pair_auto = pair_env && ((d->m_tiles + 1) / 2) * d->n_tiles >= pair_min_tiles && d->BN >= 32;
     if ((pair_forced || pair_auto) && d->a_mode == 0 && d->num_z == 1 && d->b_k0 == 0 && d->BN % 32 == 0 &&
         all_tap_cb_zero(d)) {
         int32_t hbox[3] = {64, d->BN / 2, 1};

@@ -22,7 +22,7 @@ def pick_bn(n):
     """N tile (UMMA N: any multiple of 16 up to 256): narrow outputs get the smallest covering tile; otherwise the tiling with the least
     total cost tiles x _tile_cost(bn), ties to less padding: 192 -> 192, 320 -> 160x2, 384 -> 192x2, 576 -> 192x3, 640 -> 224x3 (5 % of
     zero rows beat a fourth 160-wide tile: measured 411 us with 256x3 against 482 us with 160x4 at 32x32x16 samples), 1280 -> 256x5."""
-    for bn in (16, 32, 64):
+    for bn in (32, 64):                  # 32, not 16, for the 3- / 4-channel head convolutions: the CTA-pair kernel (row reuse) needs BN % 32 == 0
         if n <= bn:
             return bn, 1
     best = None
