@@ -1379,11 +1379,14 @@ static int attn2_run(const AttnKernelParams* kp, cudaStream_t stream) {
 int attn_run(const AttnKernelParams* kp, cudaStream_t stream) {
     if (attn_version() == 3) return attn3_run(kp, stream);
     if (attn_version() == 2) return attn2_run(kp, stream);
-    static bool attr_set = false;
+    static bool attr_set[64] = {};                  // per device (cudaFuncSetAttribute is a per-device setting)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return -39;
     const size_t smem = kOffCtl + sizeof(AttnCtl) + 1024;
-    if (!attr_set) {
+    if (!attr_set[dev]) {
         if (cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -36;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const long long grid = (long long)kp->B * kp->nh * kp->q_tiles;
     if (grid <= 0 || grid > 0x7fffffffLL) return -37;

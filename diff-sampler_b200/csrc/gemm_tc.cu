@@ -1062,20 +1062,27 @@ void gemm_set_trace(unsigned long long* buf, int cap) { g_trace_buf = buf; g_tra
 size_t gemm_params_size() { return sizeof(GemmKernelParams); }
 void gemm_patch_edm(GemmKernelParams* kp, const float* x, float* D) { kp->edm_x = x; kp->edm_D = D; }
 
-static int g_num_sms = 0;
-static bool g_attr_set = false;
+// cudaFuncSetAttribute is per device: one process may drive several GPUs (tests, notebooks), so the opt-in shared-memory size is set once per
+// (device, kernel) and the SM count is kept per device.
+static int g_num_sms[64] = {};
+static bool g_attr_set[64] = {};
+static bool g_pair_attr_set[64] = {};
 
-static bool g_pair_attr_set = false;
+static int current_device_slot() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev < 0 || dev >= 64) ? 0 : dev;
+}
 
-static int gemm_run_pair(const GemmKernelParams* kp, cudaStream_t stream) {
-    if (!g_pair_attr_set) {
+static int gemm_run_pair(const GemmKernelParams* kp, cudaStream_t stream, int slot) {
+    if (!g_pair_attr_set[slot]) {
         if (cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -22;
-        g_pair_attr_set = true;
+        g_pair_attr_set[slot] = true;
     }
     const int stage_bytes = kp->rr ? kp->rr_halo_bytes + 3 * (kp->BN / 2) * 128 : kp->grp * (kATileBytes + (kp->BN / 2) * 128);
     const size_t smem = (size_t)kp->num_stages * stage_bytes + sizeof(SmemCtl) + 1024;
     const int tiles = ((kp->m_tiles + 1) / 2) * kp->n_tiles;
-    int clusters = g_num_sms / 2;
+    int clusters = g_num_sms[slot] / 2;
     if (tiles < clusters) clusters = tiles;
     if (clusters <= 0) return 0;
     gemm_tc_pair_kernel<<<2 * clusters, kThreads, smem, stream>>>(*kp);       // cluster shape (2,1,1) is part of the kernel (__cluster_dims__)
@@ -1083,18 +1090,17 @@ static int gemm_run_pair(const GemmKernelParams* kp, cudaStream_t stream) {
 }
 
 int gemm_run(const GemmKernelParams* kp, cudaStream_t stream) {
-    if (!g_attr_set) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slot = current_device_slot();
+    if (!g_attr_set[slot]) {
+        cudaDeviceGetAttribute(&g_num_sms[slot], cudaDevAttrMultiProcessorCount, slot);
         if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return -20;
-        g_attr_set = true;
+        g_attr_set[slot] = true;
     }
-    if (kp->pair) return gemm_run_pair(kp, stream);
+    if (kp->pair) return gemm_run_pair(kp, stream, slot);
     const int stage_bytes = kp->grp * (kATileBytes + kp->BN * 128);
     const size_t smem = (size_t)kp->num_stages * stage_bytes + sizeof(SmemCtl) + 1024;
     const int tiles = kp->num_z * kp->m_tiles * kp->n_tiles;
-    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    const int grid = tiles < g_num_sms[slot] ? tiles : g_num_sms[slot];
     if (grid <= 0) return 0;
     gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(*kp);
     return cudaGetLastError() == cudaSuccess ? 0 : -21;
