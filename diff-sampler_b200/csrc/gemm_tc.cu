@@ -1005,7 +1005,8 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
     // is shared-memory-port bound (770): the pair wins 12-16 % on every shape that still gives each SM pair a tile
     static const int pair_min_tiles = [] { const char* e = getenv("DSB_GEMM_2CTA_MIN_PAIR_TILES"); return e ? atoi(e) : 74; }();
     const bool pair_auto = pair_env && ((d->m_tiles + 1) / 2) * d->n_tiles >= pair_min_tiles && d->BN >= 32;
-    if ((pair_forced || pair_auto) && d->a_mode == 0 && d->num_z == 1 && d->b_k0 == 0 && d->BN % 32 == 0 &&
+    const bool diag_single_only = (kp->diag & (8 | 16)) != 0;      // the A-only / B-only feed measurements exist for the single-CTA kernel only
+    if ((pair_forced || pair_auto) && !diag_single_only && d->a_mode == 0 && d->num_z == 1 && d->b_k0 == 0 && d->BN % 32 == 0 &&
         all_tap_cb_zero(d)) {
         int32_t hbox[3] = {64, d->BN / 2, 1};
         if (encode_map(&kp->tmBh, d->b_ptr, 3, d->b_dims, d->b_strides, hbox)) return -30;
@@ -1028,7 +1029,7 @@ int gemm_build(const ds_gemm_desc* d, GemmKernelParams* kp) {
         const int th = Wd > 0 ? 128 / Wd : 0;
         const int halo = (th + 2) * Wd * 128;
         const int rr_stage = halo + 3 * (d->BN / 2) * 128;
-        if (rr_env && std_taps && Wd <= 64 && th >= 2 && th * Wd == 128 && Hd % th == 0 && d->a_box[1] == Wd && d->a_box[2] == th && d->a_box[3] == 1 &&
+        if (rr_env && !(kp->diag & (2 | 32 | 64)) && std_taps && Wd <= 64 && th >= 2 && th * Wd == 128 && Hd % th == 0 && d->a_box[1] == Wd && d->a_box[2] == th && d->a_box[3] == 1 &&
             d->conv_W == Wd && d->conv_H == Hd && (227 * 1024 - 2048) / rr_stage >= 3) {
             const int32_t box_rr[4] = {64, Wd, th + 2, 1};
             if (encode_map(&kp->tmA_rr, d->a_ptr, 4, d->a_dims, d->a_strides, box_rr)) return -32;
